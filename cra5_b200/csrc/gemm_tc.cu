@@ -1,0 +1,88 @@
+// gemm_tc.cu -- host launcher for the tcgen05 GEMM (gemm_tc.cuh) + a plain SIMT GEMM used only by the
+// GPU self-checks (tests compare the tensor-core kernel against it and against the CPU oracle).
+#include "gemm_tc.cuh"
+#include "host_util.h"
+#include "kernels.h"
+
+namespace cra5 {
+
+template <int BN, int KIND>
+static void launch_one(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp,
+                       const EpiParams& epi) {
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<BN, KIND>;
+  if (!configured) {
+    CRA5_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL));
+    configured = true;
+  }
+  const int m_tiles = (shp.M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = (shp.N + BN - 1) / BN;
+  int grid = m_tiles * n_tiles;
+  const int sms = device_sm_count();
+  if (grid > sms) grid = sms;
+  kern<<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, st>>>(tmA, tmB, shp, epi);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+template <int BN>
+static void launch_kind(cudaStream_t st, int kind, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                        const GemmShape& shp, const EpiParams& epi) {
+  switch (kind) {
+    case EPI_F32: launch_one<BN, EPI_F32>(st, tmA, tmB, shp, epi); break;
+    case EPI_BF16: launch_one<BN, EPI_BF16>(st, tmA, tmB, shp, epi); break;
+    case EPI_GELU_BF16: launch_one<BN, EPI_GELU_BF16>(st, tmA, tmB, shp, epi); break;
+    case EPI_QKV: launch_one<BN, EPI_QKV>(st, tmA, tmB, shp, epi); break;
+    case EPI_RESID: launch_one<BN, EPI_RESID>(st, tmA, tmB, shp, epi); break;
+    case EPI_T_F32: launch_one<BN, EPI_T_F32>(st, tmA, tmB, shp, epi); break;
+    case EPI_PIXSHUF: launch_one<BN, EPI_PIXSHUF>(st, tmA, tmB, shp, epi); break;
+    case EPI_CONVT: launch_one<BN, EPI_CONVT>(st, tmA, tmB, shp, epi); break;
+    default: throw Error(ERR_INTERNAL, "unknown epilogue kind");
+  }
+}
+
+int gemm_pick_bn(int N) { return N > 128 ? 256 : 128; }
+
+void launch_gemm(cudaStream_t st, int bn, int kind, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                 const GemmShape& shp, const EpiParams& epi) {
+  CRA5_CHECK(shp.M > 0 && shp.N > 0 && shp.K > 0, ERR_INVALID, "gemm: empty problem");
+  if (bn == 256)
+    launch_kind<256>(st, kind, tmA, tmB, shp, epi);
+  else if (bn == 128)
+    launch_kind<128>(st, kind, tmA, tmB, shp, epi);
+  else
+    throw Error(ERR_INTERNAL, "gemm: unsupported BN");
+}
+
+// Plain row-major GEMM convenience: A [M,K] (row stride lda elements), B [N,K] (row stride ldb), both bf16.
+void gemm_plain(cudaStream_t st, int kind, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M,
+                int N, int K, const EpiParams& epi) {
+  const int bn = gemm_pick_bn(N);
+  CUtensorMap tmA = make_tmap_bf16_2d(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, GEMM_BK, GEMM_BM);
+  CUtensorMap tmB = make_tmap_bf16_2d(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, GEMM_BK, bn);
+  GemmShape shp{};
+  shp.M = M; shp.N = N; shp.K = K; shp.a_mode = A_PLAIN;
+  launch_gemm(st, bn, kind, tmA, tmB, shp, epi);
+}
+
+// ---------------------------------------------------------------- SIMT check kernel (tests only)
+__global__ void gemm_simt_check_kernel(const __nv_bfloat16* __restrict__ A, int lda,
+                                       const __nv_bfloat16* __restrict__ B, int ldb, const float* __restrict__ bias,
+                                       float* __restrict__ C, int ldc, int M, int N, int K) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k)
+    acc = fmaf(__bfloat162float(A[(size_t)m * lda + k]), __bfloat162float(B[(size_t)n * ldb + k]), acc);
+  if (bias) acc += bias[n];
+  C[(size_t)m * ldc + n] = acc;
+}
+
+void gemm_simt_check(cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,
+                     const float* bias, float* C, int ldc, int M, int N, int K) {
+  dim3 block(128), grid((N + 127) / 128, M);
+  gemm_simt_check_kernel<<<grid, block, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+}  // namespace cra5

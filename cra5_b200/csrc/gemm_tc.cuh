@@ -1,0 +1,397 @@
+// gemm_tc.cuh -- persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = A[M,K] * B[N,K]^T      A, B bf16 K-major in HBM, fp32 accumulation in TMEM
+//
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+// warp 2 = TMEM allocator, warp 3 idle, warps 4..11 = epilogue (two warps per TMEM lane quarter,
+// each taking half of the tile's columns). Operand tiles are 128 x 64 (A) and BN x 64 (B) bf16,
+// SWIZZLE_128B, 4-stage mbarrier ring; the accumulator is double-buffered in TMEM so the epilogue of
+// tile i overlaps the main loop of tile i+1. M/N/K tails are handled by TMA zero fill + masked stores.
+//
+// This one main loop serves every linear layer on the VAEformer hot path (reference call sites:
+// vit_nlc.py:96,242 qkv; :111,248 proj; :63-67 fc1/fc2; vaeformer.py:154-155 quant/post_quant conv;
+// vit_nlc.py:302 patch-embed conv; :629 ConvTranspose2d; :741 hyperprior head) through the A-loader modes
+// and the epilogue functors below.
+#pragma once
+#include "ptx.cuh"
+
+namespace cra5 {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_EPI_WARP0 = 4;
+
+// how the producer addresses the A operand
+enum AMode : int {
+  A_PLAIN = 0,   // 2D map (k, row)
+  A_PATCH = 1,   // 3D map (cs, j, h) over the re-laid-out frame: implicit im2col for the patch-embed conv
+  A_CONCAT = 2,  // 2D map; K = 2*D, second half reads rows shifted by -cc_shift (row-overlap of ConvTranspose2d)
+};
+
+struct GemmShape {
+  int M, N, K;
+  int a_mode;
+  // A_PATCH
+  int pe_kpr;       // k-blocks per kernel row r
+  int pe_box_rows;  // tokens per TMA box (divides tokens-per-row and 128)
+  int pe_Wp;        // tokens per patch row
+  int pe_sh;        // vertical stride in pixels
+  // A_CONCAT
+  int cc_D;      // split point in K (multiple of 64)
+  int cc_shift;  // row shift for the second half
+};
+
+// maps a row of the "attention order" (window-partitioned, zero-padded) token list back to the raster token
+struct WinMap {
+  int enabled;
+  int H, W;        // token grid
+  int wh, ww;      // window
+  int nWr, nWc;    // windows per column / row after padding
+  __device__ __forceinline__ int to_token(int a) const {  // -1 for a pad row
+    if (!enabled) return a;
+    const int wsz = wh * ww;
+    int wi = a / wsz, within = a - wi * wsz;
+    int r = within / ww, c = within - r * ww;
+    int per_frame = nWr * nWc;
+    int b = wi / per_frame;
+    wi -= b * per_frame;
+    int wr = wi / nWc, wc = wi - wr * nWc;
+    int h = wr * wh + r, w = wc * ww + c;
+    if (h >= H || w >= W) return -1;
+    return (b * H + h) * W + w;
+  }
+};
+
+enum EpiKind : int {
+  EPI_F32 = 0,        // out_f32 = acc + bias (+ add)
+  EPI_BF16 = 1,       // out_bf16 = acc + bias
+  EPI_GELU_BF16 = 2,  // out_bf16 = gelu_erf(acc + bias)
+  EPI_QKV = 3,        // head split: Q (pre-scaled), K as [head][row][hd]; V transposed [head][hd][row]
+  EPI_RESID = 4,      // out_f32[t] = resid[t] + acc + bias, t = winmap(row); optional bf16 copy
+  EPI_T_F32 = 5,      // out_f32[col * ldo + row] = acc + bias  (channel-major / NCHW result)
+  EPI_PIXSHUF = 6,    // hyperprior head: (p1 p2 c) pixel shuffle into NCHW
+  EPI_CONVT = 7,      // un-patchify scatter into NCHW
+};
+
+struct EpiParams {
+  const float* bias;      // [N] or null
+  const float* add;       // EPI_F32: extra addend [M, lda] (pos-embed), or null
+  int lda;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  int ldo;                // row stride of out (elements)
+  // EPI_RESID
+  const float* resid;
+  WinMap wm;
+  int bf16_col0;          // column offset of the optional bf16 copy (row stride ld_bf16)
+  int ld_bf16;
+  // EPI_QKV
+  __nv_bfloat16 *q, *k, *vt;
+  int D, hd, rows_total;  // model dim, head dim, number of rows (= row stride of vt)
+  float qscale;
+  // EPI_PIXSHUF
+  int ps_P1, ps_P2, ps_C, ps_Wh;  // out[c][(P1*i+p1)*(P2*Wh) + P2*j+p2], row=(i*Wh+j), col=(p1*P2+p2)*C+c
+  // EPI_CONVT
+  int ct_r0;     // first kernel row covered by this GEMM
+  int ct_CS;     // C*pw
+  int ct_pw;     // patch width (== horizontal stride)
+  int ct_sh;     // vertical stride
+  int ct_Wp;     // tokens per row
+  int ct_Himg, ct_Wimg;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int KIND>
+__device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int col0, const uint32_t (&acc)[32],
+                                               int M, int N) {
+  if (row >= M) return;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    v[i] = __uint_as_float(acc[i]);
+    if (p.bias != nullptr && col0 + i < N) v[i] += __ldg(p.bias + col0 + i);
+  }
+  const bool full = (col0 + 32 <= N);
+  if constexpr (KIND == EPI_F32) {
+    float* o = p.out_f32 + (size_t)row * p.ldo + col0;
+    if (p.add != nullptr) {
+      const float* a = p.add + (size_t)row * p.lda + col0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < N) v[i] += __ldg(a + i);
+    }
+    if (full && (p.ldo & 3) == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < N) o[i] = v[i];
+    }
+  } else if constexpr (KIND == EPI_BF16 || KIND == EPI_GELU_BF16) {
+    if constexpr (KIND == EPI_GELU_BF16) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    }
+    __nv_bfloat16* o = p.out_bf16 + (size_t)row * p.ldo + col0;
+    if (full && (p.ldo & 7) == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(v[i], v[i + 1]);
+        u.y = pack_bf16x2(v[i + 2], v[i + 3]);
+        u.z = pack_bf16x2(v[i + 4], v[i + 5]);
+        u.w = pack_bf16x2(v[i + 6], v[i + 7]);
+        *reinterpret_cast<uint4*>(o + i) = u;
+      }
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < N) o[i] = __float2bfloat16(v[i]);
+    }
+  } else if constexpr (KIND == EPI_QKV) {
+    // columns ordered [q|k|v][head][dim] (vit_nlc.py:99,242)
+#pragma unroll
+    for (int i0 = 0; i0 < 32; i0 += 8) {
+      const int col = col0 + i0;
+      if (col >= N) continue;
+      const int which = col / p.D;
+      const int within = col - which * p.D;
+      const int head = within / p.hd;
+      const int d = within - head * p.hd;
+      const bool vec = ((p.hd | p.D) & 7) == 0 && (col + 8 <= N);  // 8 columns stay inside one head
+      if (which == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (col + i < N) {
+            int c2 = col + i - 2 * p.D;
+            int h2 = c2 / p.hd, d2 = c2 - h2 * p.hd;
+            p.vt[((size_t)h2 * p.hd + d2) * p.rows_total + row] = __float2bfloat16(v[i0 + i]);
+          }
+      } else {
+        __nv_bfloat16* dst = (which == 0 ? p.q : p.k) + ((size_t)head * p.rows_total + row) * p.hd + d;
+        const float s = (which == 0) ? p.qscale : 1.0f;
+        if (vec) {
+          uint4 u;
+          u.x = pack_bf16x2(v[i0] * s, v[i0 + 1] * s);
+          u.y = pack_bf16x2(v[i0 + 2] * s, v[i0 + 3] * s);
+          u.z = pack_bf16x2(v[i0 + 4] * s, v[i0 + 5] * s);
+          u.w = pack_bf16x2(v[i0 + 6] * s, v[i0 + 7] * s);
+          *reinterpret_cast<uint4*>(dst) = u;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (col + i < N) {
+              int c2 = col + i - which * p.D;
+              int h2 = c2 / p.hd, d2 = c2 - h2 * p.hd;
+              ((which == 0 ? p.q : p.k))[((size_t)h2 * p.rows_total + row) * p.hd + d2] =
+                  __float2bfloat16(v[i0 + i] * s);
+            }
+        }
+      }
+    }
+  } else if constexpr (KIND == EPI_RESID) {
+    const int t = p.wm.to_token(row);
+    if (t < 0) return;
+    const float* r = p.resid + (size_t)t * p.ldo + col0;
+    float* o = p.out_f32 + (size_t)t * p.ldo + col0;
+    if (full && (p.ldo & 3) == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 rr = *reinterpret_cast<const float4*>(r + i);
+        v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
+        *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < N) { v[i] += r[i]; o[i] = v[i]; }
+    }
+    if (p.out_bf16 != nullptr) {
+      __nv_bfloat16* ob = p.out_bf16 + (size_t)t * p.ld_bf16 + p.bf16_col0 + col0;
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < N) ob[i] = __float2bfloat16(v[i]);
+    }
+  } else if constexpr (KIND == EPI_T_F32) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (col0 + i < N) p.out_f32[(size_t)(col0 + i) * p.ldo + row] = v[i];
+  } else if constexpr (KIND == EPI_PIXSHUF) {
+    const int i_ = row / p.ps_Wh, j_ = row - i_ * p.ps_Wh;
+    const int Wout = p.ps_P2 * p.ps_Wh;
+    for (int i = 0; i < 32; ++i) {
+      const int col = col0 + i;
+      if (col >= N) break;
+      const int pp = col / p.ps_C, c = col - pp * p.ps_C;
+      const int p1 = pp / p.ps_P2, p2 = pp - p1 * p.ps_P2;
+      p.out_f32[(size_t)c * p.ldo + (size_t)(p.ps_P1 * i_ + p1) * Wout + p.ps_P2 * j_ + p2] = v[i];
+    }
+  } else if constexpr (KIND == EPI_CONVT) {
+    // row = (i, j) patch position; col = (r - r0, c, s); out[c][sh*i + r][pw*j + s]
+    const int i_ = row / p.ct_Wp, j_ = row - i_ * p.ct_Wp;
+    for (int i = 0; i < 32; ++i) {
+      const int col = col0 + i;
+      if (col >= N) break;
+      const int rr = col / p.ct_CS, cs = col - rr * p.ct_CS;
+      const int c = cs / p.ct_pw, s = cs - c * p.ct_pw;
+      const int h = p.ct_sh * i_ + p.ct_r0 + rr;
+      if (h < p.ct_Himg)
+        p.out_f32[((size_t)c * p.ct_Himg + h) * p.ct_Wimg + p.ct_pw * j_ + s] = v[i];
+    }
+  }
+}
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = GEMM_STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+};
+
+template <int BN, int KIND>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const GemmShape shp, const EpiParams epi) {
+  using L = GemmSmem<BN>;
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // 256 or 512: power of two >= 32
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + GEMM_STAGES;
+  uint64_t* tfull_bar = empty_bar + GEMM_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (shp.M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = (shp.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (shp.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < GEMM_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 8);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % m_tiles) * GEMM_BM;
+        const int n0 = (tile / m_tiles) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % GEMM_STAGES;
+          const uint32_t ph = (it / GEMM_STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          if (shp.a_mode == A_PLAIN) {
+            tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0);
+          } else if (shp.a_mode == A_PATCH) {
+            const int r = kb / shp.pe_kpr;
+            const int cs0 = (kb - r * shp.pe_kpr) * GEMM_BK;
+            const int nbox = GEMM_BM / shp.pe_box_rows;
+            for (int g = 0; g < nbox; ++g) {
+              const int t = m0 + g * shp.pe_box_rows;
+              const int i = t / shp.pe_Wp, j0 = t - i * shp.pe_Wp;
+              tma_load_3d(sa + g * shp.pe_box_rows * 128, &tmA, &full_bar[s], cs0, j0, shp.pe_sh * i + r);
+            }
+          } else {  // A_CONCAT
+            const int k0 = kb * GEMM_BK;
+            if (k0 < shp.cc_D)
+              tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
+            else
+              tma_load_2d(sa, &tmA, &full_bar[s], k0 - shp.cc_D, m0 - shp.cc_shift);
+          }
+          tma_load_2d(sb, &tmB, &full_bar[s], kb * GEMM_BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+        const uint32_t as = tl & 1;
+        const uint32_t aph = (tl >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % GEMM_STAGES;
+          const uint32_t ph = (it / GEMM_STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint64_t adesc = umma_smem_desc_sw128(sa);
+          const uint64_t bdesc = umma_smem_desc_sw128(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in 16-byte units
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete
+      }
+    }
+  } else if (warp >= GEMM_EPI_WARP0) {
+    // ===================== epilogue =====================
+    const int ew = warp - GEMM_EPI_WARP0;      // 0..7
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                  // which half of the columns
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
+      const int m0 = (tile % m_tiles) * GEMM_BM;
+      const int n0 = (tile / m_tiles) * BN;
+      const uint32_t as = tl & 1;
+      const uint32_t aph = (tl >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN + half * (BN / 2);
+#pragma unroll 1
+      for (int c = 0; c < BN / 2; c += 32) {
+        const int col0 = n0 + half * (BN / 2) + c;
+        if (col0 >= shp.N) break;  // warp-uniform
+        uint32_t acc[32];
+        tmem_ld_32x32(taddr + c, acc);
+        tmem_ld_wait();
+        epilogue_store<KIND>(epi, row, col0, acc, shp.M, shp.N);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace cra5

@@ -1,0 +1,55 @@
+// host_util.h -- host-side helpers shared by the launchers and the C-ABI: error reporting,
+// TMA tensor-map encoding (driver entry point fetched at run time, no -lcuda link dependency).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdexcept>
+#include <string>
+
+namespace cra5 {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+// status codes returned through the C-ABI (include/cra5_b200.h)
+enum Status : int {
+  OK = 0,
+  ERR_INVALID = 1,      // bad argument / unsupported geometry   (reference: ValueError)
+  ERR_CUDA = 2,         // CUDA runtime/driver failure, or no usable sm_100 device
+  ERR_STATE = 3,        // e.g. "Uninitialized CDFs. Run update() first" (entropy_models.py:218-237)
+  ERR_BITSTREAM = 4,    // malformed container / truncated stream
+  ERR_INTERNAL = 5,
+};
+
+#define CRA5_CUDA(expr)                                                                              \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      throw ::cra5::Error(::cra5::ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+  } while (0)
+
+#define CRA5_CHECK(cond, code, msg)                                   \
+  do {                                                                \
+    if (!(cond)) throw ::cra5::Error((code), std::string(msg));       \
+  } while (0)
+
+// bf16 tensor map, up to 4 dims. dims[0] is the contiguous dimension; strides_bytes[i] is the stride of dims[i+1].
+CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box, bool swizzle128);
+
+inline CUtensorMap make_tmap_bf16_2d(const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                                     uint32_t box_inner, uint32_t box_rows) {
+  uint64_t dims[2] = {inner, rows};
+  uint64_t strides[1] = {row_stride_bytes};
+  uint32_t box[2] = {box_inner, box_rows};
+  return make_tmap_bf16(base, 2, dims, strides, box, true);
+}
+
+int device_sm_count();
+void require_sm100();
+
+}  // namespace cra5

@@ -1,0 +1,123 @@
+"""GPU parity of the individual sm_100a kernels, called through the C ABI (ctypes).
+
+Floating-point kernels: compared against a plain torch fp32 reference of the same op fed the SAME bf16-rounded
+operands, so the tolerance only has to absorb fp32 summation order (GEMM) or bf16 rounding of P (attention).
+"""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from cra5_b200 import _lib
+    return _lib
+
+
+def _gemm(A, B, bias, epi, out, resid=None):
+    L = _lib()
+    M, K = A.shape
+    N = B.shape[0]
+    ldo = out.stride(0)
+    L.check(L.lib.cra5_op_gemm(L.ptr(A), A.stride(0), L.ptr(B), B.stride(0), M, N, K, L.ptr(bias), epi, L.ptr(out),
+                               ldo, L.ptr(resid), L.stream_ptr()))
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 128, 128), (256, 512, 1024), (10368, 1024, 1024),
+                                   (648, 360, 360), (648, 1080, 360), (300, 200, 72), (10368, 3072, 1024),
+                                   (129, 257, 200)])
+def test_gemm_f32_matches_fp32_reference(M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    Kp = (K + 7) // 8 * 8  # row stride must be a multiple of 8 elements (16 B) for TMA
+    A = torch.zeros(M, Kp, device="cuda", dtype=torch.bfloat16)
+    B = torch.zeros(N, Kp, device="cuda", dtype=torch.bfloat16)
+    A[:, :K] = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    B[:, :K] = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    _gemm(A[:, :K], B[:, :K], bias, 0, out)
+    ref = A[:, :K].float() @ B[:, :K].float().t() + bias
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-4 * max(scale, 1.0), (err, scale)
+    # the SIMT self-check kernel agrees too
+    L = _lib()
+    chk = torch.empty_like(out)
+    L.check(L.lib.cra5_op_gemm_check(L.ptr(A), A.stride(0), L.ptr(B), B.stride(0), M, N, K, L.ptr(bias), L.ptr(chk),
+                                     chk.stride(0), L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert (chk - ref).abs().max().item() <= 2e-4 * max(scale, 1.0)
+
+
+def test_gemm_epilogues():
+    torch.manual_seed(0)
+    M, N, K = 520, 384, 256
+    A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    B = (torch.randn(N, K, device="cuda") * 0.1).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    ref = A.float() @ B.float().t() + bias
+    # bf16 out
+    o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    _gemm(A, B, bias, 1, o)
+    assert (o.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    # gelu (exact erf, vit_nlc.py:53 nn.GELU default)
+    _gemm(A, B, bias, 2, o)
+    rg = torch.nn.functional.gelu(ref)
+    assert (o.float() - rg).abs().max().item() <= 2 ** -7 * rg.abs().max().item()
+    # residual
+    resid = torch.randn(M, N, device="cuda")
+    of = torch.empty(M, N, device="cuda")
+    _gemm(A, B, bias, 4, of, resid)
+    assert (of - (ref + resid)).abs().max().item() <= 2e-4 * ref.abs().max().item()
+    # in-place residual
+    r2 = resid.clone()
+    _gemm(A, B, bias, 4, r2, r2)
+    assert torch.equal(r2, of)
+    # transposed (channel-major) output
+    ot = torch.empty(N, M, device="cuda")
+    _gemm(A, B, bias, 5, ot)
+    assert (ot.t() - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+
+
+def test_gemm_is_deterministic():
+    torch.manual_seed(1)
+    M, N, K = 648, 8192, 360
+    A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    B = (torch.randn(N, K, device="cuda") * 0.1).to(torch.bfloat16)
+    o1 = torch.empty(M, N, device="cuda")
+    o2 = torch.empty(M, N, device="cuda")
+    _gemm(A, B, None, 0, o1)
+    _gemm(A, B, None, 0, o2)
+    assert torch.equal(o1, o2)
+
+
+def _attention_ref(q, k, v):  # [H, S, d] fp32, q pre-scaled
+    s = q @ k.transpose(-1, -2)
+    return torch.softmax(s, dim=-1) @ v
+
+
+@pytest.mark.parametrize("heads,nseg,seg_len", [(2, 1, 128), (2, 3, 576), (4, 1, 1024), (16, 2, 576), (2, 1, 10368)])
+def test_attention_matches_fp32_reference(heads, nseg, seg_len):
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(heads * 100 + seg_len)
+    rows = nseg * seg_len
+    q = (torch.randn(heads, rows, 64, device="cuda", generator=g) * 0.125 * 2.0).to(torch.bfloat16)
+    k = (torch.randn(heads, rows, 64, device="cuda", generator=g) * 2.0).to(torch.bfloat16)
+    v = torch.randn(heads, rows, 64, device="cuda", generator=g).to(torch.bfloat16)
+    vt = v.transpose(1, 2).contiguous()
+    out = torch.full((rows, heads * 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.check(L.lib.cra5_op_attention(L.ptr(q), L.ptr(k), L.ptr(vt), L.ptr(out), heads * 64, heads, rows, seg_len,
+                                    L.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = torch.empty(rows, heads * 64, device="cuda")
+    for s in range(nseg):
+        sl = slice(s * seg_len, (s + 1) * seg_len)
+        r = _attention_ref(q[:, sl].float(), k[:, sl].float(), v[:, sl].float())  # [H, S, 64]
+        ref[sl] = r.permute(1, 0, 2).reshape(seg_len, heads * 64)
+    err = (out.float() - ref).abs().max().item()
+    # P and the output are rounded to bf16 (2^-8 relative); values are O(1)
+    assert err <= 2.5e-2, err
+    assert (out.float() - ref).abs().mean().item() <= 2e-3
