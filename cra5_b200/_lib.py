@@ -24,11 +24,20 @@ lib = _load()
 lib.cra5_last_error.restype = ctypes.c_char_p
 
 
+class Cra5ValueError(ValueError):
+    """bad argument, missing CDF tables, or malformed bitstream -- the reference raises ValueError for the first two
+    (zoo/image.py:279-290, entropy_models.py:218-256) and has undefined behaviour for the third"""
+
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
 def check(status):
     if status != 0:
         msg = lib.cra5_last_error().decode("utf-8", "replace")
-        if status == 1:
-            raise ValueError(msg)  # the reference raises ValueError for bad arguments
+        if status in (1, 3, 4):
+            raise Cra5ValueError(status, msg)
         raise Cra5Error(status, msg)
 
 

@@ -1,0 +1,215 @@
+"""`cra5_api` with the reference's surface (cra5/api/cra5_api.py:22-271), running on the B200-native codec.
+
+Kept verbatim: method names, arguments, return types, the `.bin` container and the per-channel normalisation.
+Additive extensions: every method that reads an ERA5 NetCDF file also accepts an in-memory
+`data=` array of shape (C, 721, 1440) so synthetic frames bypass NetCDF; the CDS downloader is constructed lazily;
+`net=` injects an already built model (the pretrained checkpoint needs network access).
+"""
+from __future__ import annotations
+
+import importlib.util
+import json
+import os
+import time
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from .utils import read_bin, write_bin
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load_config(path):
+    """20-line stand-in for the mmengine-style Config.fromfile the reference uses (cra5_api.py:31): executes a plain
+    Python config file and exposes its globals as attributes."""
+    spec = importlib.util.spec_from_file_location("_cra5_cfg", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return SimpleNamespace(**{k: v for k, v in vars(mod).items() if not k.startswith("_")})
+
+
+class cra5_api:
+    def __init__(self, config=f"{_HERE}/era5_268v.py", local_root=f"{os.getcwd()}/data",
+                 device="cuda" if torch.cuda.is_available() else "cpu", ceph_cfg={}, net=None, checkpoint=None):
+        self.device = device
+        print(f"The serving device is {self.device}")
+        self.cfg = _load_config(config)
+        self._era5 = None  # CDS downloader: built on first use (needs `cdsapi` + network)
+        self.level_mapping = [self.cfg.total_levels.index(v) for v in self.cfg.pressure_level if v in self.cfg.total_levels]
+        mean, std = self.get_mean_std()
+        self.mean = torch.from_numpy(mean[:, None, None]).to(device)
+        self.std = torch.from_numpy(std[:, None, None]).to(device)
+        self.channels_to_vname, self.vname_to_channels = self.channel_vname_mapping()
+        self.local_root = local_root
+        if net is None:
+            from ..zoo import vaeformer_pretrained
+            net = vaeformer_pretrained(quality=268, pretrained=checkpoint is None, checkpoint=checkpoint, device=device)
+        self.net = net.eval().to(device)
+
+    # ------------------------------------------------------------------ data access
+    @property
+    def era5(self):
+        if self._era5 is None:
+            raise RuntimeError("the Copernicus CDS downloader (cra5/api/era5_downloader.py) is outside the B200 hot "
+                               "path and is not bundled; download ERA5 files separately or pass data=")
+        return self._era5
+
+    def download_era5_data(self, time_stamp: str = None, save_root=None, data_formate="nc"):
+        save_root = save_root or self.local_root
+        return self.era5.get_form_timestamp(time_stamp=time_stamp, local_root=save_root)
+
+    def read_data_from_nc(self, time_stamp: str):
+        """(268, 721, 1440) float32 in channel order; `tp` in mm (x1000)  (cra5_api.py:195-226)"""
+        try:
+            import xarray as xr
+        except ImportError as e:
+            raise ImportError("reading ERA5 NetCDF needs xarray + netCDF4; pass data= for in-memory frames") from e
+        root = f"{self.local_root}/ERA5/{time_stamp[:4]}/{time_stamp}"
+        pressure = xr.open_dataset(f"{root}_pressure.nc", engine="netcdf4")
+        single = xr.open_dataset(f"{root}_single.nc", engine="netcdf4")
+        planes = []
+        for vname in self.cfg.vnames.get("pressure"):
+            D = pressure[vname].data
+            levels = list(pressure.level.data)
+            for li in [levels.index(v) for v in self.cfg.pressure_level if v in levels]:
+                planes.append(D[0][li][None])
+        for vname in self.cfg.vnames.get("single"):
+            D = single[vname].data
+            planes.append(D * 1000 if vname == "tp" else D)
+        return np.concatenate(planes, 0)
+
+    def _frame(self, time_stamp, data):
+        if data is None:
+            data = self.read_data_from_nc(time_stamp)
+        if isinstance(data, np.ndarray):
+            data = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32))
+        return data.to(self.device, torch.float32)
+
+    # ------------------------------------------------------------------ encode
+    def encode_to_latent(self, time_stamp: str = None, save_root=None, latent_type="float", data=None):
+        x = self.normalization(self._frame(time_stamp, data)).unsqueeze(0)
+        with torch.no_grad():
+            if latent_type == "float":
+                y, _, _ = self.net.encode_latent(x, type="float")
+                return y
+            if latent_type == "quantized":
+                _, y_hat, _ = self.net.encode_latent(x, type="quantized")
+                return y_hat
+        raise ValueError(f'Invalid latent_type "{latent_type}"')
+
+    def latent_to_bin(self, y: torch.Tensor, save_root=None):
+        with torch.no_grad():
+            return self.net.compress_from_latent(y)
+
+    def encode_era5_as_bin(self, time_stamp: str, save_root=None, return_format="bin", data=None):
+        save_root = save_root or self.local_root
+        st1 = time.time()
+        x = self.normalization(self._frame(time_stamp, data)).unsqueeze(0)
+        st2 = time.time()
+        with torch.no_grad():
+            if return_format == "latent":
+                y, _, _ = self.net.encode_latent(x, type="float")
+                return y
+            if return_format == "quantized":
+                _, y_hat, _ = self.net.encode_latent(x, type="quantized")
+                return y_hat
+            if return_format != "bin":
+                raise ValueError(f'Invalid return_format "{return_format}"')
+            output = self.net.compress(x)
+        st3 = time.time()
+        file_url = f"{save_root}/{time_stamp.split('-')[0]}/{time_stamp}.bin"
+        write_bin(file_url, output["strings"], output["z_shape"])
+        st4 = time.time()
+        return dict(output=output, reading_time=st2 - st1, encoding_time=st3 - st2, saving_time=st4 - st3,
+                    save_path=file_url)
+
+    # ------------------------------------------------------------------ decode
+    def bin_to_latent(self, bin_path=None):
+        strings, shape = read_bin(bin_path)
+        with torch.no_grad():
+            return self.net.decompress(strings, shape, return_format="latent")
+
+    def latent_to_reconstruction(self, y_hat: torch.Tensor):
+        with torch.no_grad():
+            return self.net.decode_latent(y_hat)
+
+    def decode_from_bin(self, time_stamp: str = None, custom_path=None, return_format="de_normlized"):
+        bin_path = custom_path or f"{self.local_root}/CRA5/{time_stamp[:4]}/{time_stamp}.bin"
+        t0 = time.time()
+        strings, shape = read_bin(bin_path)
+        with torch.no_grad():
+            if return_format == "latent":
+                return self.net.decompress(strings, shape, return_format="latent")
+            output = self.net.decompress(strings, shape)
+        decoding_time = time.time() - t0
+        if return_format == "normalized":
+            return dict(x_hat=output["x_hat"], decoding_time=decoding_time)
+        if return_format in ("de_normalized", "de_normlized"):  # the reference's default value carries this typo
+            return dict(x_hat=self.de_normalization(output["x_hat"].squeeze(0)), decoding_time=decoding_time)
+        return None
+
+    # ------------------------------------------------------------------ channel bookkeeping
+    def channel_vname_mapping(self):
+        c2v, v2c = {}, {}
+        idx = 0
+        for v in self.cfg.vnames.get("pressure"):
+            for level in self.cfg.pressure_level:
+                c2v[idx] = f"{v}_{int(level)}"
+                v2c[f"{v}_{int(level)}"] = idx
+                idx += 1
+        for v in self.cfg.vnames.get("single"):
+            c2v[idx] = v
+            v2c[v] = idx
+            idx += 1
+        return c2v, v2c
+
+    def get_mean_std(self):
+        with open(f"{_HERE}/era5_268v_stats.json") as f:
+            table = {r["name"]: r for r in json.load(f)["channels"]}
+        names = [f"{v}_{int(self.cfg.total_levels[i])}" for v in self.cfg.vnames.get("pressure") for i in self.level_mapping]
+        names += list(self.cfg.vnames.get("single"))
+        return (np.array([table[n]["mean"] for n in names], dtype=np.float32),
+                np.array([table[n]["std"] for n in names], dtype=np.float32))
+
+    def normalization(self, data):
+        return (data - self.mean) / self.std
+
+    def de_normalization(self, data):
+        data *= self.std
+        data += self.mean
+        return data
+
+    # ------------------------------------------------------------------ plots (outside the hot path; need matplotlib)
+    def show_image(self, reconstruct_data, time_stamp, show_variables=("z_500", "q_500", "u_500", "v_500", "t_500", "w_500"),
+                   save_images=True, save_path=None, data=None):
+        import matplotlib.pyplot as plt
+        original = data if data is not None else self.read_data_from_nc(time_stamp)
+        fig, axs = plt.subplots(len(show_variables), 3, figsize=(20, 3 * len(show_variables)), squeeze=False)
+        for i, v in enumerate(show_variables):
+            a, b = original[self.vname_to_channels[v]], reconstruct_data[self.vname_to_channels[v]]
+            for j, (img, title) in enumerate(((a, "Original"), (b, "Reconstructed"), (np.abs(a - b), "Difference"))):
+                fig.colorbar(axs[i, j].imshow(img, cmap="jet"), ax=axs[i, j])
+                axs[i, j].set_title(f"{v}_{title}")
+        plt.tight_layout()
+        path = f"{save_path}/{time_stamp}_rconstruction.png" if save_path else \
+            f"{self.local_root}/CRA5_vis/{time_stamp[:4]}/{time_stamp}_reconstruction.png"
+        if save_images:
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            plt.savefig(path)
+
+    def show_latent(self, latent, time_stamp, show_channels=(0, 10, 20, 30, 40, 50, 60, 70), save_images=True,
+                    save_path=None):
+        import matplotlib.pyplot as plt
+        fig, axs = plt.subplots(max(1, len(show_channels) // 4), 4, figsize=(24, 3 * max(1, len(show_channels) // 4)))
+        for ax, ch in zip(np.asarray(axs).flatten(), show_channels):
+            fig.colorbar(ax.imshow(latent[ch], cmap="jet"), ax=ax)
+            ax.set_title(f"Channel_{ch}")
+        plt.tight_layout()
+        path = f"{save_path}/{time_stamp}_latent.png" if save_path else \
+            f"{self.local_root}/CRA5_vis/{time_stamp[:4]}/{time_stamp}_latent.png"
+        if save_images:
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            plt.savefig(path)

@@ -4,6 +4,10 @@
 #include "capi_util.h"
 #include "gemm_tc.cuh"
 #include "kernels.h"
+#include "model.h"
+#include "coder.h"
+
+#include <memory>
 
 namespace cra5 {
 std::string& last_error_slot() {
@@ -11,6 +15,14 @@ std::string& last_error_slot() {
   return s;
 }
 }  // namespace cra5
+
+namespace cra5 {
+void pmf_to_quantized_cdf(const float* pmf, int n, int precision, uint32_t* cdf);
+}
+
+struct cra5_model {
+  std::unique_ptr<cra5::Model> impl;
+};
 
 using namespace cra5;
 
@@ -58,6 +70,187 @@ int cra5_op_attention(const void* Q, const void* K, const void* Vt, void* out, i
     attention_tc(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(Q),
                  static_cast<const __nv_bfloat16*>(K), static_cast<const __nv_bfloat16*>(Vt),
                  static_cast<__nv_bfloat16*>(out), ldo, heads, rows_total, seg_len);
+  });
+}
+
+int cra5_pmf_to_quantized_cdf(const float* pmf, int n, int precision, uint32_t* cdf_out) {
+  return guarded([&] {
+    CRA5_CHECK(pmf != nullptr && cdf_out != nullptr, ERR_INVALID, "null argument");
+    pmf_to_quantized_cdf(pmf, n, precision, cdf_out);
+  });
+}
+
+int cra5_model_create(const cra5_config* cfg, cra5_model** out) {
+  return guarded([&] {
+    CRA5_CHECK(cfg != nullptr && out != nullptr, ERR_INVALID, "null argument");
+    auto m = std::make_unique<cra5_model>();
+    m->impl = std::make_unique<Model>(*cfg);
+    *out = m.release();
+  });
+}
+
+int cra5_model_destroy(cra5_model* m) {
+  return guarded([&] { delete m; });
+}
+
+#define MODEL_GUARD(m) CRA5_CHECK((m) != nullptr && (m)->impl, ERR_INVALID, "null model handle")
+
+int cra5_model_workspace_bytes(cra5_model* m, uint64_t* bytes) {
+  return guarded([&] {
+    MODEL_GUARD(m);
+    *bytes = m->impl->workspace_bytes();
+  });
+}
+
+int cra5_model_set_tensor(cra5_model* m, const char* name, const void* dev_ptr, int dtype, int64_t numel) {
+  return guarded([&] {
+    MODEL_GUARD(m);
+    CRA5_CHECK(name != nullptr, ERR_INVALID, "null name");
+    m->impl->set_tensor(name, dev_ptr, dtype, numel);
+  });
+}
+
+int cra5_model_set_cdf(cra5_model* m, int which, const int32_t* cdf, const int32_t* len, const int32_t* off, int rows,
+                       int cols) {
+  return guarded([&] {
+    MODEL_GUARD(m);
+    m->impl->set_cdf(which, cdf, len, off, rows, cols);
+  });
+}
+
+int cra5_model_set_coder(cra5_model* m, int spc_y, int spc_z) {
+  return guarded([&] {
+    MODEL_GUARD(m);
+    m->impl->set_coder(spc_y, spc_z);
+  });
+}
+
+int cra5_encode_to_latent(cra5_model* m, const float* x, float* y, const float* mean, const float* std_, void* stream) {
+  return guarded([&] {
+    MODEL_GUARD(m);
+    CRA5_CHECK(x && y, ERR_INVALID, "null tensor");
+    m->impl->encode_to_latent(x, y, mean, std_, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int cra5_latent_quantized(cra5_model* m, const float* y, float* y_hat, void* stream) {
+  return guarded([&] {
+    MODEL_GUARD(m);
+    CRA5_CHECK(y && y_hat, ERR_INVALID, "null tensor");
+    m->impl->latent_quantized(y, y_hat, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int cra5_latent_to_bin(cra5_model* m, const float* y, const uint8_t** y_bytes, uint64_t* y_len, const uint8_t** z_bytes,
+                       uint64_t* z_len, void* stream) {
+  return guarded([&] {
+    MODEL_GUARD(m);
+    CRA5_CHECK(y && y_bytes && y_len && z_bytes && z_len, ERR_INVALID, "null argument");
+    size_t yl = 0, zl = 0;
+    m->impl->latent_to_bin(y, y_bytes, &yl, z_bytes, &zl, static_cast<cudaStream_t>(stream));
+    *y_len = yl;
+    *z_len = zl;
+  });
+}
+
+int cra5_bin_to_latent(cra5_model* m, const uint8_t* y_bytes, uint64_t y_len, const uint8_t* z_bytes, uint64_t z_len,
+                       int z_h, int z_w, float* y_hat, void* stream) {
+  return guarded([&] {
+    MODEL_GUARD(m);
+    CRA5_CHECK(y_hat != nullptr, ERR_INVALID, "null tensor");
+    m->impl->bin_to_latent(y_bytes, y_len, z_bytes, z_len, z_h, z_w, y_hat, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int cra5_latent_to_reconstruction(cra5_model* m, const float* y_hat, float* x_hat, void* stream) {
+  return guarded([&] {
+    MODEL_GUARD(m);
+    CRA5_CHECK(y_hat && x_hat, ERR_INVALID, "null tensor");
+    m->impl->latent_to_reconstruction(y_hat, x_hat, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int cra5_normalize(const float* in, float* out, const float* mean, const float* std_, int channels, uint64_t hw,
+                   int forward, void* stream) {
+  return guarded([&] {
+    require_sm100();
+    CRA5_CHECK(in && out && mean && std_ && channels > 0, ERR_INVALID, "null argument");
+    affine_channels(static_cast<cudaStream_t>(stream), in, out, mean, std_, hw, channels, forward);
+  });
+}
+
+int cra5_model_tap(cra5_model* m, const char* name, const void** dev_ptr, int64_t* numel, int* dtype) {
+  return guarded([&] {
+    MODEL_GUARD(m);
+    *dev_ptr = m->impl->tap(name, numel, dtype);
+  });
+}
+
+int cra5_model_tap_read(cra5_model* m, const char* name, void* dst_dev, uint64_t dst_bytes, void* stream) {
+  return guarded([&] {
+    MODEL_GUARD(m);
+    int64_t numel = 0;
+    int dtype = 0;
+    const void* src = m->impl->tap(name, &numel, &dtype);
+    const size_t esz = (dtype == CRA5_DT_F32 || dtype == CRA5_DT_I32) ? 4 : (dtype == CRA5_DT_BF16 ? 2 : 1);
+    CRA5_CHECK((uint64_t)numel * esz <= dst_bytes, ERR_INVALID, "tap_read: destination too small");
+    CRA5_CUDA(cudaMemcpyAsync(dst_dev, src, (size_t)numel * esz, cudaMemcpyDeviceToDevice,
+                              static_cast<cudaStream_t>(stream)));
+  });
+}
+
+int cra5_op_gc_quantize(const float* y, const float* sigma, const float* mu, const float* scale_table, int levels,
+                        float bound, int32_t* sym, uint8_t* idx, float* y_hat, uint64_t n, void* stream) {
+  return guarded([&] {
+    require_sm100();
+    CRA5_CHECK(scale_table != nullptr || idx == nullptr, ERR_INVALID, "scale table required for indexes");
+    CRA5_CHECK(y == nullptr || mu != nullptr, ERR_INVALID, "means required for symbols");
+    CRA5_CHECK(idx == nullptr || sigma != nullptr, ERR_INVALID, "scales required for indexes");
+    gc_quantize_index(static_cast<cudaStream_t>(stream), y, sigma, mu, scale_table, levels, bound, sym, idx, y_hat, n);
+  });
+}
+
+namespace {
+// the op-level coder entry points keep one lazily grown coder per thread
+RansCoder* op_coder(size_t n_symbols, int n_channels) {
+  static thread_local std::unique_ptr<RansCoder> coder;
+  static thread_local size_t cap_sym = 0;
+  static thread_local int cap_ch = 0;
+  if (!coder || n_symbols > cap_sym || n_channels > cap_ch) {
+    coder.reset();
+    cap_sym = std::max<size_t>(n_symbols, cap_sym);
+    cap_ch = std::max(n_channels, cap_ch);
+    coder = std::make_unique<RansCoder>(std::max<size_t>(cap_sym, 1), std::max(cap_ch, 1));
+  }
+  return coder.get();
+}
+}  // namespace
+
+int cra5_op_rans_encode(const int32_t* sym, const uint8_t* idx, const int32_t* cdf, int cdf_cols, const int32_t* cdf_len,
+                        const int32_t* offset, int n_channels, int L, int spc, uint8_t* out_host, uint64_t out_cap,
+                        uint64_t* out_len, void* stream) {
+  return guarded([&] {
+    require_sm100();
+    CRA5_CHECK(out_host && out_len, ERR_INVALID, "null argument");
+    CRA5_CHECK(n_channels >= 0 && L >= 0, ERR_INVALID, "negative size");
+    CdfTable t;
+    t.cdf = cdf; t.length = cdf_len; t.offset = offset; t.rows = 1 << 30; t.cols = cdf_cols;
+    if (cdf == nullptr) t.rows = 0;
+    *out_len = op_coder((size_t)n_channels * L, n_channels)
+                   ->encode(static_cast<cudaStream_t>(stream), sym, idx, t, n_channels, L, spc, out_host, out_cap);
+  });
+}
+
+int cra5_op_rans_decode(const uint8_t* bytes, uint64_t len, const uint8_t* idx, const int32_t* cdf, int cdf_cols,
+                        const int32_t* cdf_len, const int32_t* offset, int n_channels, int L, int32_t* sym,
+                        void* stream) {
+  return guarded([&] {
+    require_sm100();
+    CdfTable t;
+    t.cdf = cdf; t.length = cdf_len; t.offset = offset; t.rows = 1 << 30; t.cols = cdf_cols;
+    if (cdf == nullptr) t.rows = 0;
+    op_coder((size_t)n_channels * L, n_channels)
+        ->decode(static_cast<cudaStream_t>(stream), bytes, len, idx, t, n_channels, L, sym, nullptr, nullptr, nullptr);
   });
 }
 

@@ -1,0 +1,127 @@
+#include "coder.h"
+
+#include <string.h>
+
+#include "host_util.h"
+#include "kernels.h"
+
+namespace cra5 {
+
+RansCoder::RansCoder(size_t max_symbols, int max_channels)
+    : max_symbols_(max_symbols), max_streams_(max_channels * CR5B_MAX_SPC) {
+  scratch_words_ = 2 * max_symbols + 8 * (size_t)max_streams_;
+  payload_cap_ = scratch_words_ * 4;
+  CRA5_CUDA(cudaMalloc(&scratch_, scratch_words_ * 4));
+  CRA5_CUDA(cudaMalloc(&lengths_, (size_t)max_streams_ * 4));
+  CRA5_CUDA(cudaMalloc(&offsets_, ((size_t)max_streams_ + 1) * 4));
+  CRA5_CUDA(cudaMalloc(&payload_, payload_cap_));
+  CRA5_CUDA(cudaMalloc(&err_, sizeof(int)));
+  CRA5_CUDA(cudaMemset(err_, 0, sizeof(int)));
+  CRA5_CUDA(cudaMallocHost(&host_meta_, ((size_t)max_streams_ + 4) * 4));
+  host_stage_cap_ = payload_cap_ + (size_t)max_streams_ * 4;
+  CRA5_CUDA(cudaMallocHost(&host_stage_, host_stage_cap_));
+}
+
+RansCoder::~RansCoder() {
+  cudaFree(scratch_);
+  cudaFree(lengths_);
+  cudaFree(offsets_);
+  cudaFree(payload_);
+  cudaFree(err_);
+  cudaFreeHost(host_meta_);
+  cudaFreeHost(host_stage_);
+}
+
+static void put_u32(uint8_t* p, uint32_t v) { memcpy(p, &v, 4); }
+static uint32_t get_u32(const uint8_t* p) {
+  uint32_t v;
+  memcpy(&v, p, 4);
+  return v;
+}
+
+size_t RansCoder::encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx, const CdfTable& tab, int n_channels,
+                         int L, int spc, uint8_t* host_out, size_t host_cap) {
+  CRA5_CHECK(tab.ready(), ERR_STATE, "Uninitialized CDFs. Run update() first");
+  CRA5_CHECK(spc >= 1 && spc <= CR5B_MAX_SPC, ERR_INVALID, "streams per channel must be in [1, 64]");
+  CRA5_CHECK(n_channels >= 0 && L >= 0, ERR_INVALID, "rans_encode: negative size");
+  const int n_streams = n_channels * spc;
+  CRA5_CHECK((size_t)n_channels * L <= max_symbols_ && n_streams <= max_streams_, ERR_INVALID,
+             "rans_encode: tensor larger than the coder was sized for");
+  const size_t head = CR5B_HEADER + 4 * (size_t)n_streams;
+  CRA5_CHECK(host_cap >= head, ERR_INVALID, "rans_encode: output buffer too small");
+  const int count_max = (L + spc - 1) / spc;
+  const int cap_words = 2 * count_max + 6;
+  CRA5_CHECK((size_t)n_streams * cap_words <= scratch_words_, ERR_INTERNAL, "rans_encode: scratch sizing");
+  uint32_t total = 0;
+  if (n_streams > 0 && L > 0) {
+    rans_encode(st, sym, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, n_channels, L, spc, scratch_,
+                cap_words, lengths_, offsets_, payload_, err_);
+    CRA5_CUDA(cudaMemcpyAsync(host_meta_, lengths_, (size_t)n_streams * 4, cudaMemcpyDeviceToHost, st));
+    CRA5_CUDA(cudaMemcpyAsync(host_meta_ + n_streams, offsets_ + n_streams, 4, cudaMemcpyDeviceToHost, st));
+    CRA5_CUDA(cudaMemcpyAsync(host_meta_ + n_streams + 1, err_, 4, cudaMemcpyDeviceToHost, st));
+    CRA5_CUDA(cudaStreamSynchronize(st));
+    if (host_meta_[n_streams + 1] != 0) {
+      CRA5_CUDA(cudaMemsetAsync(err_, 0, sizeof(int), st));
+      throw Error(ERR_INTERNAL, "rans_encode: per-stream scratch overflow");
+    }
+    total = host_meta_[n_streams];
+  } else {
+    for (int s = 0; s < n_streams; ++s) host_meta_[s] = 0;
+  }
+  CRA5_CHECK(host_cap >= head + total, ERR_INVALID, "rans_encode: output buffer too small");
+  memcpy(host_out, "CR5B", 4);
+  host_out[4] = 1;
+  host_out[5] = 0;
+  host_out[6] = host_out[7] = 0;
+  put_u32(host_out + 8, (uint32_t)n_channels);
+  put_u32(host_out + 12, (uint32_t)L);
+  put_u32(host_out + 16, (uint32_t)spc);
+  put_u32(host_out + 20, (uint32_t)n_streams);
+  memcpy(host_out + CR5B_HEADER, host_meta_, (size_t)n_streams * 4);
+  if (total > 0) {
+    CRA5_CUDA(cudaMemcpyAsync(host_out + head, payload_, total, cudaMemcpyDeviceToHost, st));
+    CRA5_CUDA(cudaStreamSynchronize(st));
+  }
+  return head + total;
+}
+
+void RansCoder::decode(cudaStream_t st, const uint8_t* bytes, size_t len, const uint8_t* idx, const CdfTable& tab,
+                       int n_channels, int L, int32_t* sym_out, const float* mu, const float* median, float* val_out) {
+  CRA5_CHECK(tab.ready(), ERR_STATE, "Uninitialized CDFs. Run update() first");
+  CRA5_CHECK(bytes != nullptr && len >= CR5B_HEADER, ERR_BITSTREAM, "bitstream: truncated header");
+  CRA5_CHECK(memcmp(bytes, "CR5B", 4) == 0, ERR_BITSTREAM,
+             "bitstream: not a CR5B chunk-parallel stream (reference single-stream format is not accepted here)");
+  CRA5_CHECK(bytes[4] == 1, ERR_BITSTREAM, "bitstream: unsupported version");
+  const uint32_t nc = get_u32(bytes + 8), l = get_u32(bytes + 12), spc = get_u32(bytes + 16),
+                 ns = get_u32(bytes + 20);
+  CRA5_CHECK(nc == (uint32_t)n_channels && l == (uint32_t)L, ERR_BITSTREAM,
+             "bitstream: tensor shape does not match the model");
+  CRA5_CHECK(spc >= 1 && spc <= (uint32_t)CR5B_MAX_SPC && ns == nc * spc, ERR_BITSTREAM, "bitstream: bad stream count");
+  CRA5_CHECK((size_t)nc * l <= max_symbols_ && (int)ns <= max_streams_, ERR_BITSTREAM, "bitstream: too large");
+  const size_t head = CR5B_HEADER + 4 * (size_t)ns;
+  CRA5_CHECK(len >= head, ERR_BITSTREAM, "bitstream: truncated length table");
+  uint64_t total = 0;
+  for (uint32_t s = 0; s < ns; ++s) {
+    const uint32_t ls = get_u32(bytes + CR5B_HEADER + 4 * (size_t)s);
+    CRA5_CHECK((ls & 3) == 0 && (l == 0 || ls >= 8), ERR_BITSTREAM, "bitstream: bad sub-stream length");
+    total += ls;
+  }
+  CRA5_CHECK(head + total == len, ERR_BITSTREAM, "bitstream: payload size mismatch");
+  if (ns == 0 || l == 0) return;
+  CRA5_CHECK(total <= payload_cap_ && len <= host_stage_cap_, ERR_BITSTREAM, "bitstream: too large");
+  CRA5_CUDA(cudaStreamSynchronize(st));  // the staging buffer may still be in flight from a previous call
+  memcpy(host_stage_, bytes + CR5B_HEADER, len - CR5B_HEADER);
+  CRA5_CUDA(cudaMemcpyAsync(lengths_, host_stage_, (size_t)ns * 4, cudaMemcpyHostToDevice, st));
+  CRA5_CUDA(cudaMemcpyAsync(payload_, host_stage_ + (size_t)ns * 4, total, cudaMemcpyHostToDevice, st));
+  scan_lengths(st, lengths_, (int)ns, offsets_);
+  rans_decode(st, payload_, offsets_, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, n_channels, L,
+              (int)spc, sym_out, mu, median, val_out, err_);
+  CRA5_CUDA(cudaMemcpyAsync(host_meta_, err_, 4, cudaMemcpyDeviceToHost, st));
+  CRA5_CUDA(cudaStreamSynchronize(st));
+  if (host_meta_[0] != 0) {
+    CRA5_CUDA(cudaMemsetAsync(err_, 0, sizeof(int), st));
+    throw Error(ERR_BITSTREAM, "bitstream: sub-stream exhausted while decoding (corrupt data)");
+  }
+}
+
+}  // namespace cra5

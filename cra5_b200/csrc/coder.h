@@ -1,0 +1,51 @@
+// coder.h -- host driver of the chunk-parallel GPU rANS coder (entropy.cu) and its container format.
+//
+// Container ("CR5B", little endian), one per coded tensor -- it takes the place of the single sequential stream the
+// reference puts into `strings[i][0]` (vaeformer.py:348, cra5_api.py:108-116):
+//     0  char[4]  magic "CR5B"
+//     4  u8 version (1), u8 flags (0), u16 reserved
+//     8  u32 n_channels      12  u32 L (symbols per channel)      16  u32 spc (sub-streams per channel)
+//    20  u32 n_streams (= n_channels * spc)
+//    24  u32 length[n_streams]   (bytes, multiples of 4)
+//    ..  payload: the sub-streams back to back; sub-stream s = c * spc + k codes symbols c*L + k + i*spc, i = 0,1,..
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "model.h"
+
+namespace cra5 {
+
+constexpr uint32_t CR5B_HEADER = 24;
+constexpr int CR5B_MAX_SPC = 64;
+
+class RansCoder {
+ public:
+  RansCoder(size_t max_symbols, int max_channels);
+  ~RansCoder();
+  RansCoder(const RansCoder&) = delete;
+
+  static size_t max_container_bytes(size_t n_symbols, int n_streams) {
+    return CR5B_HEADER + 4 * (size_t)n_streams + 8 * n_symbols + 16 * (size_t)n_streams;
+  }
+  // symbols/indexes on the device -> container in host memory (pinned or pageable). Returns its size.
+  size_t encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx, const CdfTable& tab, int n_channels, int L,
+                int spc, uint8_t* host_out, size_t host_cap);
+  // container in host memory -> symbols and/or dequantised values on the device
+  void decode(cudaStream_t st, const uint8_t* bytes, size_t len, const uint8_t* idx, const CdfTable& tab,
+              int n_channels, int L, int32_t* sym_out, const float* mu, const float* median, float* val_out);
+
+ private:
+  size_t max_symbols_;
+  int max_streams_;
+  uint32_t *scratch_ = nullptr, *lengths_ = nullptr, *offsets_ = nullptr;
+  uint8_t* payload_ = nullptr;
+  size_t payload_cap_ = 0, scratch_words_ = 0;
+  int* err_ = nullptr;
+  uint32_t* host_meta_ = nullptr;  // pinned: lengths + total + err
+  uint8_t* host_stage_ = nullptr;  // pinned upload staging for decode
+  size_t host_stage_cap_ = 0;
+};
+
+}  // namespace cra5

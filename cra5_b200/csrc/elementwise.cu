@@ -1,0 +1,199 @@
+// elementwise.cu -- HBM-bound layout / normalisation kernels around the tensor-core GEMMs.
+//   frame_to_patches   NCHW fp32 frame -> bf16 [h][patch column][c*pw+s] (+ fused (x-mean)/std, cra5_api.py:264-266)
+//   layernorm_bf16     fp32 rows -> normalised bf16 rows, optionally gathered into window-partitioned order with
+//                      zero pad rows (LayerNorm vit_nlc.py:266,278 + F.pad/window_partition vit_nlc.py:229-237)
+//   im2col_latent      NCHW fp32 -> bf16 patches for the hyperprior conv (vit_nlc.py:302 with k=s=4)
+//   transpose_cast     [C][T] fp32 -> [T][C] bf16 (NCHW feature -> token rows, vit_nlc.py:683-684)
+//   cast_bf16          fp32 -> bf16
+//   affine_channels    in-place x*std+mean (cra5_api.py:268-271) and its inverse
+#include "gemm_tc.cuh"
+#include "host_util.h"
+#include "kernels.h"
+#include <algorithm>
+
+namespace cra5 {
+
+// ------------------------------------------------------------------------------------------------ frame_to_patches
+// grid: (Wp / TOK, H, ceil(C / CH)); block 256. Stages a [CH][TOK*pw] tile through shared memory so that both the
+// NCHW reads (runs of TOK*pw floats) and the patch-major writes (runs of CH*pw bf16) are coalesced.
+template <int TOK, int CH>
+__global__ void __launch_bounds__(256) frame_to_patches_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ std_, int C, int H, int W,
+                                                               int Wp, int pw, int cs_pad) {
+  extern __shared__ float tile[];  // [CH][TOK*pw]
+  const int j0 = blockIdx.x * TOK;
+  const int h = blockIdx.y;
+  const int c0 = blockIdx.z * CH;
+  const int run = TOK * pw;
+  const int nch = min(CH, C - c0);
+  for (int e = threadIdx.x; e < nch * run; e += blockDim.x) {
+    const int cl = e / run, wl = e - cl * run;
+    const int c = c0 + cl;
+    float v = x[((size_t)c * H + h) * W + (size_t)j0 * pw + wl];
+    if (mean != nullptr) v = (v - mean[c]) / std_[c];
+    tile[cl * run + wl] = v;
+  }
+  __syncthreads();
+  const int seg = nch * pw;  // contiguous output run per token
+  for (int e = threadIdx.x; e < TOK * seg; e += blockDim.x) {
+    const int jl = e / seg, q = e - jl * seg;
+    const int cl = q / pw, s = q - cl * pw;
+    out[((size_t)h * Wp + j0 + jl) * cs_pad + (size_t)c0 * pw + q] = __float2bfloat16(tile[cl * run + jl * pw + s]);
+  }
+}
+
+void frame_to_patches(cudaStream_t st, const float* x, __nv_bfloat16* out, const float* mean, const float* std_,
+                      int C, int H, int W, int Wp, int pw, int cs_pad) {
+  constexpr int TOK = 8, CH = 64;
+  CRA5_CHECK(Wp % TOK == 0, ERR_INVALID, "unsupported geometry: patches per row must be a multiple of 8");
+  CRA5_CHECK(Wp * pw <= W, ERR_INVALID, "frame_to_patches: geometry");
+  dim3 grid(Wp / TOK, H, (C + CH - 1) / CH);
+  const size_t smem = (size_t)CH * TOK * pw * sizeof(float);
+  CRA5_CHECK(smem <= 48 * 1024, ERR_INVALID, "unsupported geometry: patch width too large");
+  frame_to_patches_kernel<TOK, CH><<<grid, 256, smem, st>>>(x, out, mean, std_, C, H, W, Wp, pw, cs_pad);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------ layernorm
+// one warp per OUTPUT row. D <= 32 * MAXV.
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps,
+                                                             __nv_bfloat16* __restrict__ out, int rows_out, int D,
+                                                             WinMap wm) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows_out) return;
+  __nv_bfloat16* o = out + (size_t)warp * D;
+  const int t = wm.to_token(warp);
+  if (t < 0) {  // zero pad token (F.pad after the norm, vit_nlc.py:233)
+    for (int i = lane; i < D; i += 32) o[i] = __float2bfloat16(0.f);
+    return;
+  }
+  const float* r = x + (size_t)t * D;
+  float v[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    v[i] = (idx < D) ? r[idx] : 0.f;
+    sum += v[i];
+  }
+#pragma unroll
+  for (int o_ = 16; o_ > 0; o_ >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o_);
+  const float mean = sum / (float)D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    const float d = (idx < D) ? (v[i] - mean) : 0.f;
+    sq += d * d;
+  }
+#pragma unroll
+  for (int o_ = 16; o_ > 0; o_ >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o_);
+  const float rstd = rsqrtf(sq / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < D) o[idx] = __float2bfloat16((v[i] - mean) * rstd * gamma[idx] + beta[idx]);
+  }
+}
+
+void layernorm_bf16(cudaStream_t st, const float* x, const float* gamma, const float* beta, float eps,
+                    __nv_bfloat16* out, int rows_out, int D, const WinMap& wm) {
+  const int blocks = (rows_out + 7) / 8;
+  if (D <= 128)
+    layernorm_bf16_kernel<4><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, rows_out, D, wm);
+  else if (D <= 512)
+    layernorm_bf16_kernel<16><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, rows_out, D, wm);
+  else if (D <= 1024)
+    layernorm_bf16_kernel<32><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, rows_out, D, wm);
+  else if (D <= 2048)
+    layernorm_bf16_kernel<64><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, rows_out, D, wm);
+  else
+    throw Error(ERR_INVALID, "layernorm: width > 2048 unsupported");
+  CRA5_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------ im2col (hyper conv)
+// y [C][Hy][Wy] fp32 -> A [(i,j)][(c, r, s)] bf16 with patch == stride == (p1, p2)
+__global__ void im2col_latent_kernel(const float* __restrict__ y, __nv_bfloat16* __restrict__ A, int C, int Hy, int Wy,
+                                     int p1, int p2, int lda) {
+  const int Wh = Wy / p2;
+  const int K = C * p1 * p2;
+  const size_t total = (size_t)(Hy / p1) * Wh * K;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(e % K);
+    const int tok = (int)(e / K);
+    const int i = tok / Wh, j = tok - i * Wh;
+    const int c = k / (p1 * p2), rs = k - c * p1 * p2;
+    const int r = rs / p2, s = rs - r * p2;
+    A[(size_t)tok * lda + k] = __float2bfloat16(y[((size_t)c * Hy + i * p1 + r) * Wy + j * p2 + s]);
+  }
+}
+
+void im2col_latent(cudaStream_t st, const float* y, __nv_bfloat16* A, int C, int Hy, int Wy, int p1, int p2, int lda) {
+  const size_t total = (size_t)(Hy / p1) * (Wy / p2) * C * p1 * p2;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  im2col_latent_kernel<<<blocks, 256, 0, st>>>(y, A, C, Hy, Wy, p1, p2, lda);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------ transpose + cast
+// in [C][T] fp32 -> out [T][ldo] bf16 (columns 0..C-1)
+__global__ void transpose_cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int T,
+                                      int ldo) {
+  __shared__ float tile[32][33];
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, t = t0 + threadIdx.x;
+    tile[r][threadIdx.x] = (c < C && t < T) ? in[(size_t)c * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int t = t0 + r, c = c0 + threadIdx.x;
+    if (t < T && c < C) out[(size_t)t * ldo + c] = __float2bfloat16(tile[threadIdx.x][r]);
+  }
+}
+
+void transpose_cast(cudaStream_t st, const float* in, __nv_bfloat16* out, int C, int T, int ldo) {
+  dim3 grid((T + 31) / 32, (C + 31) / 32), block(32, 8);
+  transpose_cast_kernel<<<grid, block, 0, st>>>(in, out, C, T, ldo);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
+    out[e] = __float2bfloat16(in[e]);
+}
+
+void cast_bf16(cudaStream_t st, const float* in, __nv_bfloat16* out, size_t n) {
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+  cast_bf16_kernel<<<blocks, 256, 0, st>>>(in, out, n);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------ per-channel affine
+// forward == 1: (x - a[c]) / b[c]  (cra5_api.normalization); forward == 0: x * b[c] + a[c] (de_normalization)
+__global__ void affine_channels_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                       const float* __restrict__ a, const float* __restrict__ b, size_t hw, int C,
+                                       int forward) {
+  const int c = blockIdx.y;
+  const float m = a[c], s = b[c];
+  const float* src = in + (size_t)c * hw;
+  float* dst = out + (size_t)c * hw;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < hw; e += (size_t)gridDim.x * blockDim.x) {
+    const float v = src[e];
+    dst[e] = forward ? (v - m) / s : v * s + m;
+  }
+}
+
+void affine_channels(cudaStream_t st, const float* in, float* out, const float* a, const float* b, size_t hw, int C,
+                     int forward) {
+  dim3 grid((unsigned)std::min<size_t>((hw + 1023) / 1024, 64), C);
+  affine_channels_kernel<<<grid, 256, 0, st>>>(in, out, a, b, hw, C, forward);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+}  // namespace cra5

@@ -1,0 +1,372 @@
+// entropy.cu -- the entropy stage on the GPU: fused quantise + scale-index kernel, and a chunk-parallel rANS coder.
+//
+// Reference semantics restated (bit-exact integer work):
+//   symbols  = round_half_even(y - mu).int()                   EntropyModel.quantize, entropy_models.py:167-184
+//   index    = 63 - sum_{s in table[:63]} [max(sigma,0.11) <= s] GaussianConditional.build_indexes, :679-685
+//   rANS     64-bit state, 32-bit renormalisation, 16-bit precision, 4-bit-nibble bypass for out-of-range symbols
+//            rans_interface.cpp:108-200 (encode), :215-284 (decode); primitives as in ryg_rans rans64.h
+//
+// Parallel format: the reference codes a tensor as ONE sequential stream. Here every latent channel is split into
+// `spc` interleaved sub-streams (sub-stream k of channel c holds symbols c*L + k, c*L + k + spc, ...); each sub-stream
+// is an independent stream with EXACTLY the reference's arithmetic (so any sub-stream can be checked byte-for-byte
+// against the reference coder fed the same strided symbols), coded by one thread. Lanes of a warp read neighbouring
+// symbols, so symbol/index loads are sector-coalesced.
+#include "host_util.h"
+#include "kernels.h"
+#include <algorithm>
+
+namespace cra5 {
+
+// ------------------------------------------------------------------------------------------------ quantise + index
+// 4 elements per thread, 128-bit loads of y / sigma / mu, 128-bit store of symbols, 32-bit store of indexes.
+__device__ __forceinline__ int scale_index(float sigma, const float* __restrict__ tab, int levels, float bound) {
+  const float s = fmaxf(sigma, bound);  // LowerBound forward: torch.max(x, bound), bound_ops.py:35-36
+  // first t in [0, levels-1) with s <= tab[t], else levels-1  (== levels-1 - #{t < levels-1 : s <= tab[t]})
+  int lo = 0, hi = levels - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (s <= tab[mid]) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256)
+gc_quantize_index_kernel(const float* __restrict__ y, const float* __restrict__ sigma, const float* __restrict__ mu,
+                         const float* __restrict__ scale_table, int levels, float bound, int32_t* __restrict__ sym,
+                         uint8_t* __restrict__ idx, float* __restrict__ y_hat, size_t n) {
+  __shared__ float tab[256];
+  for (int i = threadIdx.x; i < levels; i += blockDim.x) tab[i] = scale_table[i];
+  __syncthreads();
+  const size_t n4 = n >> 2;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
+    int4 s = make_int4(0, 0, 0, 0);
+    float4 mv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y != nullptr) {
+      const float4 yv = reinterpret_cast<const float4*>(y)[e];
+      mv = reinterpret_cast<const float4*>(mu)[e];
+      s.x = __float2int_rn(__fsub_rn(yv.x, mv.x));
+      s.y = __float2int_rn(__fsub_rn(yv.y, mv.y));
+      s.z = __float2int_rn(__fsub_rn(yv.z, mv.z));
+      s.w = __float2int_rn(__fsub_rn(yv.w, mv.w));
+      if (sym != nullptr) reinterpret_cast<int4*>(sym)[e] = s;
+    }
+    if (idx != nullptr) {
+      const float4 sv = reinterpret_cast<const float4*>(sigma)[e];
+      uchar4 q;
+      q.x = (unsigned char)scale_index(sv.x, tab, levels, bound);
+      q.y = (unsigned char)scale_index(sv.y, tab, levels, bound);
+      q.z = (unsigned char)scale_index(sv.z, tab, levels, bound);
+      q.w = (unsigned char)scale_index(sv.w, tab, levels, bound);
+      reinterpret_cast<uchar4*>(idx)[e] = q;
+    }
+    if (y_hat != nullptr && y != nullptr)  // "dequantize": round(y - mu) + mu, entropy_models.py:173-178
+      reinterpret_cast<float4*>(y_hat)[e] = make_float4(__fadd_rn((float)s.x, mv.x), __fadd_rn((float)s.y, mv.y),
+                                                       __fadd_rn((float)s.z, mv.z), __fadd_rn((float)s.w, mv.w));
+  }
+  // tail
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const size_t e = (n4 << 2) + threadIdx.x;
+    if (y != nullptr) {
+      const int s = __float2int_rn(__fsub_rn(y[e], mu[e]));
+      if (sym != nullptr) sym[e] = s;
+      if (y_hat != nullptr) y_hat[e] = __fadd_rn((float)s, mu[e]);
+    }
+    if (idx != nullptr) idx[e] = (uint8_t)scale_index(sigma[e], tab, levels, bound);
+  }
+}
+
+void gc_quantize_index(cudaStream_t st, const float* y, const float* sigma, const float* mu, const float* scale_table,
+                       int levels, float bound, int32_t* sym, uint8_t* idx, float* y_hat, size_t n) {
+  CRA5_CHECK(levels >= 1 && levels <= 256, ERR_INVALID, "scale table must have 1..256 levels");
+  if (n == 0) return;
+  const int blocks = (int)std::min<size_t>(((n >> 2) + 255) / 256 + 1, 148 * 8);
+  gc_quantize_index_kernel<<<blocks, 256, 0, st>>>(y, sigma, mu, scale_table, levels, bound, sym, idx, y_hat, n);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+// EntropyBottleneck: per-channel median, index == channel (entropy_models.py:529-542, 513-523)
+__global__ void eb_quantize_kernel(const float* __restrict__ z, const float* __restrict__ median, int L,
+                                   int32_t* __restrict__ sym, float* __restrict__ z_hat, size_t n) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const float m = median[e / L];
+    const int s = __float2int_rn(__fsub_rn(z[e], m));
+    if (sym != nullptr) sym[e] = s;
+    if (z_hat != nullptr) z_hat[e] = __fadd_rn((float)s, m);
+  }
+}
+
+void eb_quantize(cudaStream_t st, const float* z, const float* median, int L, int32_t* sym, float* z_hat, size_t n) {
+  if (n == 0) return;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+  eb_quantize_kernel<<<blocks, 256, 0, st>>>(z, median, L, sym, z_hat, n);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+// sym (int32) + mean -> float; mean per element (mu != null) or per channel (median != null)
+__global__ void dequantize_kernel(const int32_t* __restrict__ sym, const float* __restrict__ mu,
+                                  const float* __restrict__ median, int L, float* __restrict__ out, size_t n) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const float m = (mu != nullptr) ? mu[e] : median[e / L];
+    out[e] = __fadd_rn((float)sym[e], m);
+  }
+}
+
+void dequantize(cudaStream_t st, const int32_t* sym, const float* mu, const float* median, int L, float* out,
+                size_t n) {
+  if (n == 0) return;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+  dequantize_kernel<<<blocks, 256, 0, st>>>(sym, mu, median, L, out, n);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------ rANS primitives
+constexpr uint32_t RANS_PRECISION = 16;      // rans_interface.cpp:49
+constexpr uint32_t RANS_BYPASS_BITS = 4;     // rans_interface.cpp:51
+constexpr int32_t RANS_BYPASS_MAX = 15;      // rans_interface.cpp:52
+constexpr uint64_t RANS_L = 1ull << 31;      // rans64.h
+
+struct RansEnc {
+  uint64_t x;
+  uint32_t* ptr;      // next word is written at --ptr
+  uint32_t* floor_;   // lowest address we may write
+  bool overflow;
+  __device__ __forceinline__ void emit() {
+    if (ptr > floor_) { --ptr; *ptr = (uint32_t)x; } else overflow = true;
+    x >>= 32;
+  }
+  __device__ __forceinline__ void put(uint32_t start, uint32_t freq) {
+    const uint64_t x_max = ((RANS_L >> RANS_PRECISION) << 32) * (uint64_t)freq;
+    if (x >= x_max) emit();
+    const uint64_t q = x / freq;
+    x = (q << RANS_PRECISION) + (x - q * freq) + start;
+  }
+  __device__ __forceinline__ void put_bits(uint32_t val, uint32_t nbits) {  // rans_interface.cpp:69-87
+    const uint64_t x_max = ((RANS_L >> 16) << 32) * (uint64_t)(1u << (16 - nbits));
+    if (x >= x_max) emit();
+    x = (x << nbits) | val;
+  }
+};
+
+// thread = sub-stream. Symbols are consumed last-to-first (the reference buffers all symbols and encodes the list in
+// reverse, rans_interface.cpp:183-193), words are written backwards into the stream's private scratch window.
+// chan_index < 0: per-symbol indexes from `idx`; otherwise index == channel (EntropyBottleneck).
+__global__ void __launch_bounds__(128)
+rans_encode_kernel(const int32_t* __restrict__ sym, const uint8_t* __restrict__ idx, int index_is_channel,
+                   const int32_t* __restrict__ cdf, int cdf_stride, const int32_t* __restrict__ cdf_len,
+                   const int32_t* __restrict__ offset, int n_channels, int L, int spc, uint32_t* __restrict__ scratch,
+                   int cap_words, uint32_t* __restrict__ lengths, int* __restrict__ err) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_channels * spc) return;
+  const int c = s / spc, k = s - c * spc;
+  const int count = (L - k + spc - 1) / spc;
+  uint32_t* top = scratch + (size_t)(s + 1) * cap_words;
+  RansEnc e;
+  e.x = RANS_L;
+  e.ptr = top;
+  e.floor_ = top - cap_words + 2;  // keep room for the 2-word flush
+  e.overflow = false;
+  const size_t base = (size_t)c * L + k;
+  for (int i = count - 1; i >= 0; --i) {
+    const size_t pos = base + (size_t)i * spc;
+    const int ci = index_is_channel ? c : (int)idx[pos];
+    const int32_t* row = cdf + (size_t)ci * cdf_stride;
+    const int32_t max_value = cdf_len[ci] - 2;
+    int32_t value = sym[pos] - offset[ci];
+    uint32_t raw = 0;
+    bool bypass = false;
+    if (value < 0) {
+      raw = (uint32_t)(-2 * value - 1);
+      value = max_value;
+      bypass = true;
+    } else if (value >= max_value) {
+      raw = (uint32_t)(2 * (value - max_value));
+      value = max_value;
+      bypass = true;
+    }
+    if (bypass) {
+      int32_t nb = 0;
+      while (nb < 8 && (raw >> (nb * RANS_BYPASS_BITS)) != 0) ++nb;
+      for (int32_t j = nb - 1; j >= 0; --j) e.put_bits((raw >> (j * RANS_BYPASS_BITS)) & RANS_BYPASS_MAX, RANS_BYPASS_BITS);
+      // count is sent as [15]*q then (nb - 15q); nb <= 8 for 32-bit raw values so q == 0, kept general
+      const int32_t q = nb / RANS_BYPASS_MAX;
+      e.put_bits((uint32_t)(nb - q * RANS_BYPASS_MAX), RANS_BYPASS_BITS);
+      for (int32_t j = 0; j < q; ++j) e.put_bits(RANS_BYPASS_MAX, RANS_BYPASS_BITS);
+    }
+    const uint32_t start = (uint32_t)row[value];
+    const uint32_t freq = (uint32_t)row[value + 1] - start;
+    e.put(start, freq);
+  }
+  // flush: stream begins with low32(x), high32(x)
+  e.ptr -= 2;
+  e.ptr[0] = (uint32_t)e.x;
+  e.ptr[1] = (uint32_t)(e.x >> 32);
+  lengths[s] = (uint32_t)(top - e.ptr) * 4u;
+  if (e.overflow) atomicExch(err, 1);
+}
+
+// single-block exclusive scan of up to a few thousand stream lengths (bytes); writes offsets[n+1]
+__global__ void __launch_bounds__(1024) scan_lengths_kernel(const uint32_t* __restrict__ lengths, int n,
+                                                            uint32_t* __restrict__ offsets) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    uint32_t v = (i < n) ? lengths[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t w = warp_sums[threadIdx.x];
+      uint32_t wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (threadIdx.x >= o) wi += t;
+      }
+      warp_sums[threadIdx.x] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    const uint32_t excl = carry + warp_sums[threadIdx.x >> 5] + incl - v;
+    if (i < n) offsets[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[n] = carry;
+}
+
+// one warp per stream: copy its words from the scratch window to the packed payload
+__global__ void __launch_bounds__(256) compact_streams_kernel(const uint32_t* __restrict__ scratch, int cap_words,
+                                                              const uint32_t* __restrict__ lengths,
+                                                              const uint32_t* __restrict__ offsets, int n_streams,
+                                                              uint8_t* __restrict__ payload) {
+  const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= n_streams) return;
+  const uint32_t words = lengths[s] >> 2;
+  const uint32_t* src = scratch + (size_t)(s + 1) * cap_words - words;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(payload + offsets[s]);
+  for (uint32_t w = lane; w < words; w += 32) dst[w] = src[w];
+}
+
+void rans_encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx, bool index_is_channel, const int32_t* cdf,
+                 int cdf_stride, const int32_t* cdf_len, const int32_t* offset, int n_channels, int L, int spc,
+                 uint32_t* scratch, int cap_words, uint32_t* lengths, uint32_t* offsets, uint8_t* payload, int* err) {
+  const int n_streams = n_channels * spc;
+  if (n_streams == 0) return;
+  rans_encode_kernel<<<(n_streams + 127) / 128, 128, 0, st>>>(sym, idx, index_is_channel ? 1 : 0, cdf, cdf_stride,
+                                                              cdf_len, offset, n_channels, L, spc, scratch, cap_words,
+                                                              lengths, err);
+  CRA5_CUDA(cudaGetLastError());
+  scan_lengths_kernel<<<1, 1024, 0, st>>>(lengths, n_streams, offsets);
+  CRA5_CUDA(cudaGetLastError());
+  compact_streams_kernel<<<(n_streams * 32 + 255) / 256, 256, 0, st>>>(scratch, cap_words, lengths, offsets, n_streams,
+                                                                       payload);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------ decode
+struct RansDec {
+  uint64_t x;
+  const uint32_t* ptr;
+  const uint32_t* end;
+  bool underflow;
+  __device__ __forceinline__ uint32_t next() {
+    if (ptr < end) return *ptr++;
+    underflow = true;
+    return 0u;
+  }
+  __device__ __forceinline__ uint32_t get_bits(uint32_t nbits) {  // rans_interface.cpp:89-105
+    const uint32_t val = (uint32_t)(x & ((1u << nbits) - 1));
+    x >>= nbits;
+    if (x < RANS_L) x = (x << 32) | next();
+    return val;
+  }
+};
+
+// thread = sub-stream. Writes int32 symbols and/or the dequantised value sym + mean.
+__global__ void __launch_bounds__(128)
+rans_decode_kernel(const uint8_t* __restrict__ payload, const uint32_t* __restrict__ offsets,
+                   const uint8_t* __restrict__ idx, int index_is_channel, const int32_t* __restrict__ cdf,
+                   int cdf_stride, const int32_t* __restrict__ cdf_len, const int32_t* __restrict__ offset,
+                   int n_channels, int L, int spc, int32_t* __restrict__ sym_out, const float* __restrict__ mu,
+                   const float* __restrict__ median, float* __restrict__ val_out, int* __restrict__ err) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_channels * spc) return;
+  const int c = s / spc, k = s - c * spc;
+  const int count = (L - k + spc - 1) / spc;
+  RansDec d;
+  d.ptr = reinterpret_cast<const uint32_t*>(payload + offsets[s]);
+  d.end = reinterpret_cast<const uint32_t*>(payload + offsets[s + 1]);
+  d.underflow = false;
+  {
+    const uint32_t lo = d.next(), hi = d.next();
+    d.x = (uint64_t)lo | ((uint64_t)hi << 32);
+  }
+  const size_t base = (size_t)c * L + k;
+  for (int i = 0; i < count; ++i) {
+    const size_t pos = base + (size_t)i * spc;
+    const int ci = index_is_channel ? c : (int)idx[pos];
+    const int32_t* row = cdf + (size_t)ci * cdf_stride;
+    const int32_t n_entries = cdf_len[ci];
+    const int32_t max_value = n_entries - 2;
+    const uint32_t cum = (uint32_t)(d.x & 0xffffu);
+    // last v in [0, n_entries-1) with row[v] <= cum  (the reference searches linearly, rans_interface.cpp:246-250)
+    int lo = 0, hi = n_entries - 1;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if ((uint32_t)row[mid] <= cum) lo = mid; else hi = mid;
+    }
+    const uint32_t start = (uint32_t)row[lo];
+    const uint32_t freq = (uint32_t)row[lo + 1] - start;
+    d.x = (uint64_t)freq * (d.x >> RANS_PRECISION) + cum - start;
+    if (d.x < RANS_L) d.x = (d.x << 32) | d.next();
+    int32_t value = lo;
+    if (value == max_value) {  // bypass, rans_interface.cpp:256-278
+      int32_t val = (int32_t)d.get_bits(RANS_BYPASS_BITS);
+      int32_t nb = val;
+      while (val == RANS_BYPASS_MAX && !d.underflow) {
+        val = (int32_t)d.get_bits(RANS_BYPASS_BITS);
+        nb += val;
+      }
+      uint32_t raw = 0;
+      for (int32_t j = 0; j < nb; ++j) {
+        val = (int32_t)d.get_bits(RANS_BYPASS_BITS);
+        if (j < 8) raw |= (uint32_t)val << (j * RANS_BYPASS_BITS);
+        if (d.underflow) break;
+      }
+      value = (int32_t)(raw >> 1);
+      if (raw & 1u) value = -value - 1; else value += max_value;
+    }
+    const int32_t out = value + offset[ci];
+    if (sym_out != nullptr) sym_out[pos] = out;
+    if (val_out != nullptr) val_out[pos] = __fadd_rn((float)out, (mu != nullptr) ? mu[pos] : median[c]);
+  }
+  if (d.underflow) atomicExch(err, 2);
+}
+
+void rans_decode(cudaStream_t st, const uint8_t* payload, const uint32_t* offsets, const uint8_t* idx,
+                 bool index_is_channel, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len,
+                 const int32_t* offset, int n_channels, int L, int spc, int32_t* sym_out, const float* mu,
+                 const float* median, float* val_out, int* err) {
+  const int n_streams = n_channels * spc;
+  if (n_streams == 0) return;
+  rans_decode_kernel<<<(n_streams + 127) / 128, 128, 0, st>>>(payload, offsets, idx, index_is_channel ? 1 : 0, cdf,
+                                                              cdf_stride, cdf_len, offset, n_channels, L, spc, sym_out,
+                                                              mu, median, val_out, err);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+void scan_lengths(cudaStream_t st, const uint32_t* lengths, int n, uint32_t* offsets) {
+  scan_lengths_kernel<<<1, 1024, 0, st>>>(lengths, n, offsets);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+}  // namespace cra5

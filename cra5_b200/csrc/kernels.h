@@ -22,4 +22,34 @@ void gemm_simt_check(cudaStream_t st, const __nv_bfloat16* A, int lda, const __n
 void attention_tc(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* Vt,
                   __nv_bfloat16* out, int ldo, int heads, int rows_total, int seg_len);
 
+void attention_simt(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* Vt,
+                    __nv_bfloat16* out, int ldo, int heads, int hd, int rows_total, int seg_len);
+
+// elementwise.cu
+struct WinMap;
+void frame_to_patches(cudaStream_t st, const float* x, __nv_bfloat16* out, const float* mean, const float* std_,
+                      int C, int H, int W, int Wp, int pw, int cs_pad);
+void layernorm_bf16(cudaStream_t st, const float* x, const float* gamma, const float* beta, float eps,
+                    __nv_bfloat16* out, int rows_out, int D, const WinMap& wm);
+void im2col_latent(cudaStream_t st, const float* y, __nv_bfloat16* A, int C, int Hy, int Wy, int p1, int p2, int lda);
+void transpose_cast(cudaStream_t st, const float* in, __nv_bfloat16* out, int C, int T, int ldo);
+void cast_bf16(cudaStream_t st, const float* in, __nv_bfloat16* out, size_t n);
+void affine_channels(cudaStream_t st, const float* in, float* out, const float* a, const float* b, size_t hw, int C,
+                     int forward);
+
+// entropy.cu
+void gc_quantize_index(cudaStream_t st, const float* y, const float* sigma, const float* mu, const float* scale_table,
+                       int levels, float bound, int32_t* sym, uint8_t* idx, float* y_hat, size_t n);
+void eb_quantize(cudaStream_t st, const float* z, const float* median, int L, int32_t* sym, float* z_hat, size_t n);
+void dequantize(cudaStream_t st, const int32_t* sym, const float* mu, const float* median, int L, float* out,
+                size_t n);
+void rans_encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx, bool index_is_channel, const int32_t* cdf,
+                 int cdf_stride, const int32_t* cdf_len, const int32_t* offset, int n_channels, int L, int spc,
+                 uint32_t* scratch, int cap_words, uint32_t* lengths, uint32_t* offsets, uint8_t* payload, int* err);
+void rans_decode(cudaStream_t st, const uint8_t* payload, const uint32_t* offsets, const uint8_t* idx,
+                 bool index_is_channel, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len,
+                 const int32_t* offset, int n_channels, int L, int spc, int32_t* sym_out, const float* mu,
+                 const float* median, float* val_out, int* err);
+void scan_lengths(cudaStream_t st, const uint32_t* lengths, int n, uint32_t* offsets);
+
 }  // namespace cra5

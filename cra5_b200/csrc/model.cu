@@ -1,0 +1,510 @@
+// model.cu -- VAEformer encode / entropy-code / decode as kernel launches (see model.h).
+#include "model.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "coder.h"
+#include "host_util.h"
+#include "kernels.h"
+
+namespace cra5 {
+
+static int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+Model::Model(const cra5_config& c) : cfg_(c) {
+  require_sm100();
+  CRA5_CHECK(c.in_chans > 0 && c.dim > 0 && c.depth >= 2 && c.num_heads > 0, ERR_INVALID, "config: sizes");
+  CRA5_CHECK(c.dim % c.num_heads == 0 && c.hyper_dim % c.hyper_heads == 0, ERR_INVALID,
+             "config: width must be divisible by heads");
+  CRA5_CHECK(c.dim % 8 == 0 && c.hyper_dim % 8 == 0 && c.latent_chans % 8 == 0 && c.z_chans % 8 == 0, ERR_INVALID,
+             "unsupported geometry: widths must be multiples of 8");
+  CRA5_CHECK(c.patch_w == c.stride_w, ERR_INVALID, "unsupported geometry: horizontal patch overlap");
+  CRA5_CHECK(c.stride_h <= c.patch_h && c.patch_h <= 2 * c.stride_h, ERR_INVALID,
+             "unsupported geometry: vertical patch size must be in [stride, 2*stride]");
+  CRA5_CHECK(c.n_windows >= 1 && c.n_windows <= 4 && c.interval >= 1, ERR_INVALID, "config: windows");
+  Hg = (c.img_h - c.patch_h) / c.stride_h + 1;
+  Wg = (c.img_w - c.patch_w) / c.stride_w + 1;
+  T = Hg * Wg;
+  CRA5_CHECK(Hg % c.hyper_patch_h == 0 && Wg % c.hyper_patch_w == 0, ERR_INVALID,
+             "unsupported geometry: token grid not divisible by the hyperprior patch");
+  Hh = Hg / c.hyper_patch_h;
+  Wh = Wg / c.hyper_patch_w;
+  Th = Hh * Wh;
+  hd = c.dim / c.num_heads;
+  hdh = c.hyper_dim / c.hyper_heads;
+  CRA5_CHECK(hd == 64, ERR_INVALID, "unsupported geometry: trunk head_dim must be 64 (tcgen05 attention tile)");
+  // window-partitioned row counts
+  Tpad = T;
+  for (int i = 0; i < c.n_windows; ++i) {
+    const int rows = ceil_div(Hg, c.window_h[i]) * c.window_h[i] * ceil_div(Wg, c.window_w[i]) * c.window_w[i];
+    CRA5_CHECK(rows % 8 == 0, ERR_INVALID, "unsupported geometry: padded window rows must be a multiple of 8");
+    Tpad = std::max(Tpad, rows);
+  }
+  CRA5_CHECK(T % 8 == 0, ERR_INVALID, "unsupported geometry: token count must be a multiple of 8");
+  // patch-embed implicit GEMM
+  const int CS = c.in_chans * c.patch_w;
+  kpr = ceil_div(CS, GEMM_BK);
+  cs_pad = (int)align_up((size_t)CS, 8);
+  box_rows = 0;
+  for (int b = 128; b >= 8; b >>= 1)
+    if (Wg % b == 0) { box_rows = b; break; }
+  CRA5_CHECK(box_rows != 0, ERR_INVALID, "unsupported geometry: patches per row must be a multiple of 8");
+  nB = c.patch_h - c.stride_h;
+  nA = c.stride_h - nB;
+  spc_y_ = c.streams_per_channel_y > 0 ? c.streams_per_channel_y : 8;
+  spc_z_ = c.streams_per_channel_z > 0 ? c.streams_per_channel_z : 1;
+  CRA5_CHECK(spc_y_ <= CR5B_MAX_SPC && spc_z_ <= CR5B_MAX_SPC, ERR_INVALID, "streams per channel must be <= 64");
+
+  // ---------------- workspace
+  const int D = c.dim, Dh = c.hyper_dim, mlp = c.mlp_ratio, lat = c.latent_chans, zc = c.z_chans;
+  const int hidden = std::max(1, (int)sqrt((double)(Dh / zc))) * zc;
+  const size_t kh_max = std::max<size_t>({(size_t)lat * c.hyper_patch_h * c.hyper_patch_w, (size_t)Dh, (size_t)hidden,
+                                          (size_t)zc});
+  auto trunk_bytes = [&](int T_, int Tp, int D_, int mlp_) {
+    return align_up((size_t)T_ * D_ * 4, 256) + 5 * align_up((size_t)Tp * D_ * 2, 256) +
+           align_up((size_t)T_ * mlp_ * D_ * 2, 256);
+  };
+  size_t total = 0;
+  total += trunk_bytes(T, Tpad, D, mlp) + trunk_bytes(Th, Th, Dh, std::max(mlp, ceil_div(hidden, Dh)));
+  total += 2 * align_up((size_t)T * D * 4, 256) + align_up((size_t)T * 2 * D * 2, 256);
+  total += align_up((size_t)c.img_h * Wg * cs_pad * 2, 256);
+  total += 2 * align_up((size_t)lat * T * 4, 256) + align_up((size_t)2 * lat * T * 4, 256) +
+           align_up((size_t)T * lat * 2, 256);
+  total += 2 * align_up((size_t)zc * Th * 4, 256) + align_up((size_t)Th * zc * 2, 256) +
+           align_up((size_t)Th * kh_max * 2, 256);
+  total += align_up((size_t)lat * T * 4, 256) + align_up((size_t)zc * Th * 4, 256) + align_up((size_t)lat * T, 256);
+  total += 4096;
+  ws_bytes_ = total;
+  CRA5_CUDA(cudaMalloc(&ws_, ws_bytes_));
+  CRA5_CUDA(cudaMemset(ws_, 0, ws_bytes_));
+  auto trunk_alloc = [&](TrunkBuffers& tb, int T_, int Tp, int D_, int mlp_) {
+    tb.x = (float*)alloc((size_t)T_ * D_ * 4);
+    tb.a = (__nv_bfloat16*)alloc((size_t)Tp * D_ * 2);
+    tb.q = (__nv_bfloat16*)alloc((size_t)Tp * D_ * 2);
+    tb.k = (__nv_bfloat16*)alloc((size_t)Tp * D_ * 2);
+    tb.vt = (__nv_bfloat16*)alloc((size_t)Tp * D_ * 2);
+    tb.o = (__nv_bfloat16*)alloc((size_t)Tp * D_ * 2);
+    tb.h = (__nv_bfloat16*)alloc((size_t)T_ * mlp_ * D_ * 2);
+  };
+  trunk_alloc(main_, T, Tpad, D, mlp);
+  trunk_alloc(hyper_, Th, Th, Dh, std::max(mlp, ceil_div(hidden, Dh)));
+  x1_ = (float*)alloc((size_t)T * D * 4);
+  x2_ = (float*)alloc((size_t)T * D * 4);
+  cat_ = (__nv_bfloat16*)alloc((size_t)T * 2 * D * 2);
+  patches_ = (__nv_bfloat16*)alloc((size_t)c.img_h * Wg * cs_pad * 2);
+  y_ = (float*)alloc((size_t)lat * T * 4);
+  yhat_ = (float*)alloc((size_t)lat * T * 4);
+  params_ = (float*)alloc((size_t)2 * lat * T * 4);
+  ytok_ = (__nv_bfloat16*)alloc((size_t)T * lat * 2);
+  z_ = (float*)alloc((size_t)zc * Th * 4);
+  zhat_ = (float*)alloc((size_t)zc * Th * 4);
+  ztok_ = (__nv_bfloat16*)alloc((size_t)Th * zc * 2);
+  ah_ = (__nv_bfloat16*)alloc((size_t)Th * kh_max * 2);
+  ysym_ = (int32_t*)alloc((size_t)lat * T * 4);
+  zsym_ = (int32_t*)alloc((size_t)zc * Th * 4);
+  yidx_ = (uint8_t*)alloc((size_t)lat * T);
+  coder_ = new RansCoder((size_t)lat * T, std::max(lat, zc));
+  host_y_cap_ = RansCoder::max_container_bytes((size_t)lat * T, lat * CR5B_MAX_SPC);
+  host_z_cap_ = RansCoder::max_container_bytes((size_t)zc * Th, zc * CR5B_MAX_SPC);
+  CRA5_CUDA(cudaMallocHost(&host_y_, host_y_cap_));
+  CRA5_CUDA(cudaMallocHost(&host_z_, host_z_cap_));
+}
+
+Model::~Model() {
+  delete coder_;
+  cudaFree(ws_);
+  cudaFreeHost(host_y_);
+  cudaFreeHost(host_z_);
+}
+
+void* Model::alloc(size_t bytes) {
+  const size_t off = ws_used_;
+  ws_used_ += align_up(bytes, 256);
+  CRA5_CHECK(ws_used_ <= ws_bytes_, ERR_INTERNAL, "workspace sizing");
+  return ws_ + off;
+}
+
+void Model::set_tensor(const std::string& name, const void* ptr, int dtype, int64_t numel) {
+  CRA5_CHECK(ptr != nullptr && numel > 0, ERR_INVALID, "set_tensor: null tensor '" + name + "'");
+  CRA5_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, ERR_INVALID, "set_tensor: '" + name + "' must be 16-byte aligned");
+  tensors_[name] = TensorRef{ptr, dtype, numel};
+  finalized_ = false;
+}
+
+void Model::set_cdf(int which, const int32_t* cdf, const int32_t* len, const int32_t* off, int rows, int cols) {
+  CRA5_CHECK(which == 0 || which == 1, ERR_INVALID, "set_cdf: which must be 0 (EntropyBottleneck) or 1 (GaussianConditional)");
+  CRA5_CHECK(cdf && len && off && rows > 0 && cols >= 3, ERR_INVALID, "set_cdf: invalid CDF size");
+  CdfTable& t = which == 0 ? eb_ : gc_;
+  if (which == 0) CRA5_CHECK(rows == cfg_.z_chans, ERR_INVALID, "set_cdf: EntropyBottleneck needs one row per z channel");
+  if (which == 1) CRA5_CHECK(rows <= 256, ERR_INVALID, "set_cdf: at most 256 scale levels");
+  t.cdf = cdf; t.length = len; t.offset = off; t.rows = rows; t.cols = cols;
+}
+
+void Model::set_coder(int spc_y, int spc_z) {
+  CRA5_CHECK(spc_y >= 1 && spc_y <= CR5B_MAX_SPC && spc_z >= 1 && spc_z <= CR5B_MAX_SPC, ERR_INVALID,
+             "streams per channel must be in [1, 64]");
+  spc_y_ = spc_y;
+  spc_z_ = spc_z;
+}
+
+const void* Model::need(const std::string& name, int dtype, int64_t numel) const {
+  auto it = tensors_.find(name);
+  CRA5_CHECK(it != tensors_.end(), ERR_STATE, "missing parameter '" + name + "' (load_state_dict incomplete)");
+  CRA5_CHECK(it->second.dtype == dtype, ERR_INVALID, "parameter '" + name + "' has the wrong dtype");
+  CRA5_CHECK(it->second.numel == numel, ERR_INVALID,
+             "size mismatch for '" + name + "': expected " + std::to_string(numel) + " elements, got " +
+                 std::to_string(it->second.numel));
+  return it->second.ptr;
+}
+
+BlockWeights Model::block_weights(const std::string& p, int D, int mlp) const {
+  BlockWeights w;
+  auto f = [&](const std::string& n, int64_t ne) { return (const float*)need(p + n, CRA5_DT_F32, ne); };
+  auto b = [&](const std::string& n, int64_t ne) { return (const __nv_bfloat16*)need(p + n, CRA5_DT_BF16, ne); };
+  w.ln1_g = f(".norm1.weight", D); w.ln1_b = f(".norm1.bias", D);
+  w.ln2_g = f(".norm2.weight", D); w.ln2_b = f(".norm2.bias", D);
+  w.qkv_w = b(".attn.qkv.weight", (int64_t)3 * D * D); w.qkv_b = f(".attn.qkv.bias", 3 * D);
+  w.proj_w = b(".attn.proj.weight", (int64_t)D * D); w.proj_b = f(".attn.proj.bias", D);
+  w.fc1_w = b(".mlp.fc1.weight", (int64_t)mlp * D * D); w.fc1_b = f(".mlp.fc1.bias", mlp * D);
+  w.fc2_w = b(".mlp.fc2.weight", (int64_t)mlp * D * D); w.fc2_b = f(".mlp.fc2.bias", D);
+  return w;
+}
+
+void Model::finalize() {
+  if (finalized_) return;
+  const cra5_config& c = cfg_;
+  const int n_enc = c.depth / 2 + 1, n_dec = c.depth - c.depth / 2;
+  ga_.clear(); gs_.clear(); ha_.clear(); hs_.clear();
+  for (int i = 0; i < n_enc; ++i) ga_.push_back(block_weights("g_a.blocks." + std::to_string(i), c.dim, c.mlp_ratio));
+  for (int i = 0; i < n_dec; ++i) gs_.push_back(block_weights("g_s.blocks." + std::to_string(i), c.dim, c.mlp_ratio));
+  for (int i = 0; i < c.hyper_depth / 2; ++i)
+    ha_.push_back(block_weights("h_a.blocks." + std::to_string(i), c.hyper_dim, c.mlp_ratio));
+  for (int i = 0; i < c.hyper_depth - c.hyper_depth / 2; ++i)
+    hs_.push_back(block_weights("h_s.blocks." + std::to_string(i), c.hyper_dim, c.mlp_ratio));
+  finalized_ = true;
+}
+
+// window (wh, ww) partition of the Hg x Wg grid, zero padded to whole windows (vit_nlc.py:229-237)
+WinMap Model::make_winmap(int wh, int ww) const {
+  WinMap m{};
+  if (wh <= 0) return m;  // global block
+  m.enabled = 1;
+  m.H = Hg; m.W = Wg; m.wh = wh; m.ww = ww;
+  m.nWr = ceil_div(Hg, wh);
+  m.nWc = ceil_div(Wg, ww);
+  return m;
+}
+
+// Block.forward (vit_nlc.py:282-287): x_out = x_in + attn(LN1(x_in)); x_out += mlp(LN2(x_out))
+void Model::run_block(cudaStream_t st, const BlockWeights& w, const TrunkBuffers& tb, const float* x_in, float* x_out,
+                      int T_, int D, int heads, int mlp, int win_h, int win_w, __nv_bfloat16* cat_out, int cat_col0,
+                      int cat_ld) {
+  const int hd_ = D / heads;
+  WinMap wm = (T_ == T) ? make_winmap(win_h, win_w) : WinMap{};
+  const int rows = wm.enabled ? wm.nWr * wm.nWc * wm.wh * wm.ww : T_;
+  const int seg = wm.enabled ? wm.wh * wm.ww : T_;
+  layernorm_bf16(st, x_in, w.ln1_g, w.ln1_b, cfg_.ln_eps, tb.a, rows, D, wm);
+  {
+    EpiParams e{};
+    e.bias = w.qkv_b;
+    e.q = tb.q; e.k = tb.k; e.vt = tb.vt;
+    e.D = D; e.hd = hd_; e.rows_total = rows;
+    e.qscale = 1.0f / sqrtf((float)hd_);
+    gemm_plain(st, EPI_QKV, tb.a, D, w.qkv_w, D, rows, 3 * D, D, e);
+  }
+  if (hd_ == 64)
+    attention_tc(st, tb.q, tb.k, tb.vt, tb.o, D, heads, rows, seg);
+  else
+    attention_simt(st, tb.q, tb.k, tb.vt, tb.o, D, heads, hd_, rows, seg);
+  {
+    EpiParams e{};
+    e.bias = w.proj_b;
+    e.resid = x_in; e.out_f32 = x_out; e.ldo = D; e.wm = wm;
+    gemm_plain(st, EPI_RESID, tb.o, D, w.proj_w, D, rows, D, D, e);
+  }
+  layernorm_bf16(st, x_out, w.ln2_g, w.ln2_b, cfg_.ln_eps, tb.a, T_, D, WinMap{});
+  {
+    EpiParams e{};
+    e.bias = w.fc1_b;
+    e.out_bf16 = tb.h; e.ldo = mlp * D;
+    gemm_plain(st, EPI_GELU_BF16, tb.a, D, w.fc1_w, D, T_, mlp * D, D, e);
+  }
+  {
+    EpiParams e{};
+    e.bias = w.fc2_b;
+    e.resid = x_out; e.out_f32 = x_out; e.ldo = D;
+    e.out_bf16 = cat_out; e.bf16_col0 = cat_col0; e.ld_bf16 = cat_ld;
+    gemm_plain(st, EPI_RESID, tb.h, mlp * D, w.fc2_w, mlp * D, T_, D, mlp * D, e);
+  }
+}
+
+static void window_of(const cra5_config& c, int abs_block, int* wh, int* ww) {
+  // vit_nlc.py:402-407 / :614-619: global every `interval`-th block, else window_size[min(i % interval, n-1)]
+  if ((abs_block + 1) % c.interval == 0) { *wh = 0; *ww = 0; return; }
+  const int which = std::min(abs_block % c.interval, c.n_windows - 1);
+  *wh = c.window_h[which];
+  *ww = c.window_w[which];
+}
+
+// ViT_Encoder.forward + quant_conv + mode(): x -> y  (vit_nlc.py:458-486, vaeformer.py:272-283)
+void Model::encode_to_latent(const float* x, float* y, const float* mean, const float* std_, cudaStream_t st) {
+  finalize();
+  const cra5_config& c = cfg_;
+  const int D = c.dim, CS = c.in_chans * c.patch_w;
+  CRA5_CHECK((mean == nullptr) == (std_ == nullptr), ERR_INVALID, "mean and std must be given together");
+  frame_to_patches(st, x, patches_, mean, std_, c.in_chans, c.img_h, c.img_w, Wg, c.patch_w, cs_pad);
+  {
+    // implicit-GEMM patch embedding: K ordered (kernel row r, channel, column s), zero padded per r to kpr*64
+    const int Kp = c.patch_h * kpr * GEMM_BK;
+    const __nv_bfloat16* Wpe = (const __nv_bfloat16*)need("g_a.patch_embed.proj.weight", CRA5_DT_BF16, (int64_t)D * Kp);
+    uint64_t dims[3] = {(uint64_t)CS, (uint64_t)Wg, (uint64_t)c.img_h};
+    uint64_t strides[2] = {(uint64_t)cs_pad * 2, (uint64_t)Wg * cs_pad * 2};
+    uint32_t box[3] = {GEMM_BK, (uint32_t)box_rows, 1};
+    CUtensorMap tmA = make_tmap_bf16(patches_, 3, dims, strides, box, true);
+    const int bn = gemm_pick_bn(D);
+    CUtensorMap tmB = make_tmap_bf16_2d(Wpe, (uint64_t)Kp, (uint64_t)D, (uint64_t)Kp * 2, GEMM_BK, bn);
+    GemmShape shp{};
+    shp.M = T; shp.N = D; shp.K = Kp; shp.a_mode = A_PATCH;
+    shp.pe_kpr = kpr; shp.pe_box_rows = box_rows; shp.pe_Wp = Wg; shp.pe_sh = c.stride_h;
+    EpiParams e{};
+    e.bias = (const float*)need("g_a.patch_embed.proj.bias", CRA5_DT_F32, D);
+    e.add = (const float*)need("g_a.pos_embed", CRA5_DT_F32, (int64_t)T * D);
+    e.lda = D;
+    e.out_f32 = main_.x; e.ldo = D;
+    launch_gemm(st, bn, EPI_F32, tmA, tmB, shp, e);
+  }
+  taps_["tokens"] = TensorRef{main_.x, CRA5_DT_F32, (int64_t)T * D};
+  const int n = (int)ga_.size();
+  int wh, ww;
+  for (int i = 0; i < n - 2; ++i) {
+    window_of(c, i, &wh, &ww);
+    run_block(st, ga_[i], main_, main_.x, main_.x, T, D, c.num_heads, c.mlp_ratio, wh, ww, nullptr, 0, 0);
+  }
+  // the last two blocks share their input and window setting; outputs are concatenated (vit_nlc.py:467-472)
+  window_of(c, n - 2, &wh, &ww);
+  run_block(st, ga_[n - 2], main_, main_.x, x1_, T, D, c.num_heads, c.mlp_ratio, wh, ww, cat_, 0, 2 * D);
+  run_block(st, ga_[n - 1], main_, main_.x, x2_, T, D, c.num_heads, c.mlp_ratio, wh, ww, cat_, D, 2 * D);
+  {
+    // quant_conv 1x1, only the `mean` half of the moments is ever used (distributions.py:32,71-72)
+    const int lat = c.latent_chans;
+    EpiParams e{};
+    e.bias = (const float*)need("quant_conv.bias", CRA5_DT_F32, lat);
+    e.out_f32 = y; e.ldo = T;
+    gemm_plain(st, EPI_T_F32, cat_, 2 * D, (const __nv_bfloat16*)need("quant_conv.weight", CRA5_DT_BF16, (int64_t)lat * 2 * D),
+               2 * D, T, lat, 2 * D, e);
+  }
+  taps_["y"] = TensorRef{y, CRA5_DT_F32, (int64_t)c.latent_chans * T};
+}
+
+// HyperpriorEncoder: y (latent, Hg, Wg) -> z_ (zc, Hh, Wh)   (vit_nlc.py:488-551 via :477-486)
+void Model::run_h_a(cudaStream_t st, const float* y) {
+  finalize();
+  const cra5_config& c = cfg_;
+  const int Dh = c.hyper_dim, lat = c.latent_chans, zc = c.z_chans;
+  const int Kc = lat * c.hyper_patch_h * c.hyper_patch_w;
+  const int hidden = std::max(1, (int)sqrt((double)(Dh / zc))) * zc;
+  im2col_latent(st, y, ah_, lat, Hg, Wg, c.hyper_patch_h, c.hyper_patch_w, Kc);
+  {
+    EpiParams e{};
+    e.bias = (const float*)need("h_a.patch_embed.proj.bias", CRA5_DT_F32, Dh);
+    e.add = (const float*)need("h_a.pos_embed", CRA5_DT_F32, (int64_t)Th * Dh);
+    e.lda = Dh;
+    e.out_f32 = hyper_.x; e.ldo = Dh;
+    gemm_plain(st, EPI_F32, ah_, Kc, (const __nv_bfloat16*)need("h_a.patch_embed.proj.weight", CRA5_DT_BF16, (int64_t)Dh * Kc),
+               Kc, Th, Dh, Kc, e);
+  }
+  for (size_t i = 0; i < ha_.size(); ++i)
+    run_block(st, ha_[i], hyper_, hyper_.x, hyper_.x, Th, Dh, c.hyper_heads, c.mlp_ratio, 0, 0, nullptr, 0, 0);
+  // quan_mlp (vit_nlc.py:544-546): fc1 -> GELU -> fc2, no norm in front
+  cast_bf16(st, hyper_.x, hyper_.a, (size_t)Th * Dh);
+  {
+    EpiParams e{};
+    e.bias = (const float*)need("h_a.quan_mlp.fc1.bias", CRA5_DT_F32, hidden);
+    e.out_bf16 = hyper_.h; e.ldo = hidden;
+    gemm_plain(st, EPI_GELU_BF16, hyper_.a, Dh, (const __nv_bfloat16*)need("h_a.quan_mlp.fc1.weight", CRA5_DT_BF16, (int64_t)hidden * Dh),
+               Dh, Th, hidden, Dh, e);
+  }
+  {
+    EpiParams e{};
+    e.bias = (const float*)need("h_a.quan_mlp.fc2.bias", CRA5_DT_F32, zc);
+    e.out_f32 = z_; e.ldo = Th;
+    gemm_plain(st, EPI_T_F32, hyper_.h, hidden, (const __nv_bfloat16*)need("h_a.quan_mlp.fc2.weight", CRA5_DT_BF16, (int64_t)zc * hidden),
+               hidden, Th, zc, hidden, e);
+  }
+  taps_["z"] = TensorRef{z_, CRA5_DT_F32, (int64_t)zc * Th};
+}
+
+// HyperpriorDecoder: z_hat (zc, Hh, Wh) -> params_ = [sigma (latent) | mu (latent)] x (Hg, Wg)  (vit_nlc.py:696-748)
+void Model::run_h_s(cudaStream_t st, const float* z_hat) {
+  finalize();
+  const cra5_config& c = cfg_;
+  const int Dh = c.hyper_dim, lat = c.latent_chans, zc = c.z_chans;
+  const int hidden = std::max(1, (int)sqrt((double)(Dh / zc))) * zc;
+  transpose_cast(st, z_hat, ztok_, zc, Th, zc);
+  {
+    EpiParams e{};
+    e.bias = (const float*)need("h_s.post_quan_mlp.fc1.bias", CRA5_DT_F32, hidden);
+    e.out_bf16 = hyper_.h; e.ldo = hidden;
+    gemm_plain(st, EPI_GELU_BF16, ztok_, zc, (const __nv_bfloat16*)need("h_s.post_quan_mlp.fc1.weight", CRA5_DT_BF16, (int64_t)hidden * zc),
+               zc, Th, hidden, zc, e);
+  }
+  {
+    EpiParams e{};
+    e.bias = (const float*)need("h_s.post_quan_mlp.fc2.bias", CRA5_DT_F32, Dh);
+    e.out_f32 = hyper_.x; e.ldo = Dh;
+    gemm_plain(st, EPI_F32, hyper_.h, hidden, (const __nv_bfloat16*)need("h_s.post_quan_mlp.fc2.weight", CRA5_DT_BF16, (int64_t)Dh * hidden),
+               hidden, Th, Dh, hidden, e);
+  }
+  for (size_t i = 0; i < hs_.size(); ++i)
+    run_block(st, hs_[i], hyper_, hyper_.x, hyper_.x, Th, Dh, c.hyper_heads, c.mlp_ratio, 0, 0, nullptr, 0, 0);
+  layernorm_bf16(st, hyper_.x, (const float*)need("h_s.norm.weight", CRA5_DT_F32, Dh),
+                 (const float*)need("h_s.norm.bias", CRA5_DT_F32, Dh), c.ln_eps, hyper_.a, Th, Dh, WinMap{});
+  {
+    // Linear(Dh, 2*latent*p1*p2, bias=False) + rearrange '(p1 p2 c)' (vit_nlc.py:741, 671-680)
+    const int Nf = 2 * lat * c.hyper_patch_h * c.hyper_patch_w;
+    EpiParams e{};
+    e.out_f32 = params_; e.ldo = T;
+    e.ps_P1 = c.hyper_patch_h; e.ps_P2 = c.hyper_patch_w; e.ps_C = 2 * lat; e.ps_Wh = Wh;
+    gemm_plain(st, EPI_PIXSHUF, hyper_.a, Dh, (const __nv_bfloat16*)need("h_s.final.weight", CRA5_DT_BF16, (int64_t)Nf * Dh), Dh, Th,
+               Nf, Dh, e);
+  }
+  taps_["scales"] = TensorRef{params_, CRA5_DT_F32, (int64_t)lat * T};
+  taps_["means"] = TensorRef{params_ + (size_t)lat * T, CRA5_DT_F32, (int64_t)lat * T};
+}
+
+static const float* scale_table_of(const Model* m, const std::map<std::string, TensorRef>& t, int rows) {
+  auto it = t.find("gaussian_conditional.scale_table");
+  CRA5_CHECK(it != t.end(), ERR_STATE, "Uninitialized CDFs. Run update() first");
+  CRA5_CHECK(it->second.dtype == CRA5_DT_F32 && it->second.numel == rows, ERR_INVALID,
+             "scale_table does not match the GaussianConditional CDF rows");
+  (void)m;
+  return (const float*)it->second.ptr;
+}
+
+constexpr float SCALE_BOUND = 0.11f;  // entropy_models.py:560
+
+// tail of VAEformer.encode_latent(type='quantized') (vaeformer.py:284-290), eval mode = "dequantize"
+void Model::latent_quantized(const float* y, float* y_hat, cudaStream_t st) {
+  const cra5_config& c = cfg_;
+  CRA5_CHECK(gc_.ready(), ERR_STATE, "Uninitialized CDFs. Run update() first");
+  const float* med = (const float*)need("entropy_bottleneck.medians", CRA5_DT_F32, c.z_chans);
+  run_h_a(st, y);
+  eb_quantize(st, z_, med, Th, nullptr, zhat_, (size_t)c.z_chans * Th);
+  run_h_s(st, zhat_);
+  gc_quantize_index(st, y, nullptr, params_ + (size_t)c.latent_chans * T, scale_table_of(this, tensors_, gc_.rows),
+                    gc_.rows, SCALE_BOUND, nullptr, nullptr, y_hat, (size_t)c.latent_chans * T);
+}
+
+// VAEformer.compress_from_latent (vaeformer.py:334-348)
+void Model::latent_to_bin(const float* y, const uint8_t** y_bytes, size_t* y_len, const uint8_t** z_bytes,
+                          size_t* z_len, cudaStream_t st) {
+  const cra5_config& c = cfg_;
+  CRA5_CHECK(eb_.ready() && gc_.ready(), ERR_STATE, "Uninitialized CDFs. Run update() first");
+  const int lat = c.latent_chans, zc = c.z_chans;
+  const float* med = (const float*)need("entropy_bottleneck.medians", CRA5_DT_F32, zc);
+  const float* table = scale_table_of(this, tensors_, gc_.rows);
+  run_h_a(st, y);
+  // z: symbols + the z_hat the decoder will see (the reference decodes its own z string, vaeformer.py:340)
+  eb_quantize(st, z_, med, Th, zsym_, zhat_, (size_t)zc * Th);
+  taps_["z_symbols"] = TensorRef{zsym_, CRA5_DT_I32, (int64_t)zc * Th};
+  taps_["z_hat"] = TensorRef{zhat_, CRA5_DT_F32, (int64_t)zc * Th};
+  run_h_s(st, zhat_);
+  gc_quantize_index(st, y, params_, params_ + (size_t)lat * T, table, gc_.rows, SCALE_BOUND, ysym_, yidx_, nullptr,
+                    (size_t)lat * T);
+  taps_["y_symbols"] = TensorRef{ysym_, CRA5_DT_I32, (int64_t)lat * T};
+  taps_["y_indexes"] = TensorRef{yidx_, CRA5_DT_U8, (int64_t)lat * T};
+  *z_len = coder_->encode(st, zsym_, nullptr, eb_, zc, Th, spc_z_, host_z_, host_z_cap_);
+  *y_len = coder_->encode(st, ysym_, yidx_, gc_, lat, T, spc_y_, host_y_, host_y_cap_);
+  *y_bytes = host_y_;
+  *z_bytes = host_z_;
+}
+
+// VAEformer.decompress(return_format='latent') (vaeformer.py:378-391)
+void Model::bin_to_latent(const uint8_t* y_bytes, size_t y_len, const uint8_t* z_bytes, size_t z_len, int z_h, int z_w,
+                          float* y_hat, cudaStream_t st) {
+  const cra5_config& c = cfg_;
+  CRA5_CHECK(eb_.ready() && gc_.ready(), ERR_STATE, "Uninitialized CDFs. Run update() first");
+  CRA5_CHECK(z_h == Hh && z_w == Wh, ERR_INVALID, "z shape does not match the model geometry");
+  const int lat = c.latent_chans, zc = c.z_chans;
+  const float* med = (const float*)need("entropy_bottleneck.medians", CRA5_DT_F32, zc);
+  const float* table = scale_table_of(this, tensors_, gc_.rows);
+  coder_->decode(st, z_bytes, z_len, nullptr, eb_, zc, Th, zsym_, nullptr, med, zhat_);
+  taps_["z_symbols"] = TensorRef{zsym_, CRA5_DT_I32, (int64_t)zc * Th};
+  taps_["z_hat"] = TensorRef{zhat_, CRA5_DT_F32, (int64_t)zc * Th};
+  run_h_s(st, zhat_);
+  gc_quantize_index(st, nullptr, params_, nullptr, table, gc_.rows, SCALE_BOUND, nullptr, yidx_, nullptr, (size_t)lat * T);
+  coder_->decode(st, y_bytes, y_len, yidx_, gc_, lat, T, ysym_, params_ + (size_t)lat * T, nullptr, y_hat);
+  taps_["y_symbols"] = TensorRef{ysym_, CRA5_DT_I32, (int64_t)lat * T};
+  taps_["y_indexes"] = TensorRef{yidx_, CRA5_DT_U8, (int64_t)lat * T};
+}
+
+// VAEformer.decode_latent (vaeformer.py:294-300): post_quant_conv + ViT_Decoder.forward (vit_nlc.py:682-693)
+void Model::latent_to_reconstruction(const float* y_hat, float* x_hat, cudaStream_t st) {
+  finalize();
+  const cra5_config& c = cfg_;
+  const int D = c.dim, lat = c.latent_chans, CS = c.in_chans * c.patch_w;
+  transpose_cast(st, y_hat, ytok_, lat, T, lat);
+  {
+    EpiParams e{};
+    e.bias = (const float*)need("post_quant_conv.bias", CRA5_DT_F32, D);
+    e.out_f32 = main_.x; e.ldo = D;
+    gemm_plain(st, EPI_F32, ytok_, lat, (const __nv_bfloat16*)need("post_quant_conv.weight", CRA5_DT_BF16, (int64_t)D * lat), lat, T,
+               D, lat, e);
+  }
+  const int n = (int)gs_.size();
+  for (int i = 0; i < n; ++i) {
+    int wh, ww;
+    window_of(c, c.depth / 2 + i, &wh, &ww);
+    run_block(st, gs_[i], main_, main_.x, main_.x, T, D, c.num_heads, c.mlp_ratio, wh, ww, nullptr, 0, 0);
+  }
+  layernorm_bf16(st, main_.x, (const float*)need("g_s.norm.weight", CRA5_DT_F32, D),
+                 (const float*)need("g_s.norm.bias", CRA5_DT_F32, D), c.ln_eps, main_.a, T, D, WinMap{});
+  const bool conv_head = (c.img_h == 721 && c.img_w == 1440);  // vit_nlc.py:628
+  if (conv_head) {
+    // ConvTranspose2d(k=(ph,pw), s=(sh,pw)) as two GEMMs with a scatter epilogue, no atomics:
+    //  class A: kernel rows r in [nB, sh) touch exactly one patch row  -> K = D
+    //  class B: output rows sh*i' + r', r' < nB receive kernel row r' of patch i' and row r'+sh of patch i'-1 -> K = 2D
+    EpiParams e{};
+    e.out_f32 = x_hat;
+    e.ct_CS = CS; e.ct_pw = c.patch_w; e.ct_sh = c.stride_h; e.ct_Wp = Wg; e.ct_Himg = c.img_h; e.ct_Wimg = c.img_w;
+    if (nA > 0) {
+      e.ct_r0 = nB;
+      gemm_plain(st, EPI_CONVT, main_.a, D, (const __nv_bfloat16*)need("g_s.final.A", CRA5_DT_BF16, (int64_t)nA * CS * D), D, T,
+                 nA * CS, D, e);
+    }
+    if (nB > 0) {
+      e.ct_r0 = 0;
+      const int M2 = (Hg + 1) * Wg, N2 = nB * CS, K2 = 2 * D;
+      const __nv_bfloat16* Wb = (const __nv_bfloat16*)need("g_s.final.B", CRA5_DT_BF16, (int64_t)N2 * K2);
+      CRA5_CHECK(D % GEMM_BK == 0, ERR_INVALID, "unsupported geometry: width must be a multiple of 64 for the conv head");
+      const int bn = gemm_pick_bn(N2);
+      CUtensorMap tmA = make_tmap_bf16_2d(main_.a, (uint64_t)D, (uint64_t)T, (uint64_t)D * 2, GEMM_BK, GEMM_BM);
+      CUtensorMap tmB = make_tmap_bf16_2d(Wb, (uint64_t)K2, (uint64_t)N2, (uint64_t)K2 * 2, GEMM_BK, bn);
+      GemmShape shp{};
+      shp.M = M2; shp.N = N2; shp.K = K2; shp.a_mode = A_CONCAT; shp.cc_D = D; shp.cc_shift = Wg;
+      launch_gemm(st, bn, EPI_CONVT, tmA, tmB, shp, e);
+    }
+  } else {
+    // Linear(D, C*p1*p2, bias=False) + rearrange 'b h w (p1 p2 c) -> b c (h p1) (w p2)' (vit_nlc.py:632, 671-680)
+    const int Nf = c.in_chans * c.patch_h * c.patch_w;
+    EpiParams e{};
+    e.out_f32 = x_hat; e.ldo = (Hg * c.patch_h) * (Wg * c.patch_w);
+    e.ps_P1 = c.patch_h; e.ps_P2 = c.patch_w; e.ps_C = c.in_chans; e.ps_Wh = Wg;
+    gemm_plain(st, EPI_PIXSHUF, main_.a, D, (const __nv_bfloat16*)need("g_s.final.weight", CRA5_DT_BF16, (int64_t)Nf * D), D, T, Nf,
+               D, e);
+  }
+}
+
+const void* Model::tap(const std::string& name, int64_t* numel, int* dtype) const {
+  auto it = taps_.find(name);
+  CRA5_CHECK(it != taps_.end(), ERR_INVALID, "no such tap: " + name);
+  *numel = it->second.numel;
+  *dtype = it->second.dtype;
+  return it->second.ptr;
+}
+
+}  // namespace cra5

@@ -1,0 +1,117 @@
+// model.h -- the VAEformer codec as a sequence of sm_100a kernel launches over library-owned workspaces.
+// Host-side mirror of cra5/models/vaeformer/vaeformer.py:272-400 (encode_latent / decode_latent /
+// compress_from_latent / decompress). One Model per (GPU, stream); no global state.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/cra5_b200.h"
+#include "gemm_tc.cuh"
+
+namespace cra5 {
+
+struct TensorRef {
+  const void* ptr = nullptr;
+  int dtype = 0;  // CRA5_DT_*
+  int64_t numel = 0;
+};
+
+struct BlockWeights {
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *qkv_b, *proj_b, *fc1_b, *fc2_b;
+  const __nv_bfloat16 *qkv_w, *proj_w, *fc1_w, *fc2_w;
+};
+
+struct CdfTable {
+  const int32_t* cdf = nullptr;     // [rows][cols] device
+  const int32_t* length = nullptr;  // [rows] device
+  const int32_t* offset = nullptr;  // [rows] device
+  int rows = 0, cols = 0;
+  bool ready() const { return cdf != nullptr && rows > 0; }
+};
+
+// Scratch for one transformer trunk (main or hyper)
+class RansCoder;
+
+struct TrunkBuffers {
+  float* x;                 // [T][D] residual stream
+  __nv_bfloat16* a;         // [Tpad][D] LayerNorm output (attention order) / generic bf16 A operand
+  __nv_bfloat16 *q, *k, *vt;  // [heads][Tpad][hd], [heads][hd][Tpad]
+  __nv_bfloat16* o;         // [Tpad][D] attention output
+  __nv_bfloat16* h;         // [T][mlp*D]
+};
+
+class Model {
+ public:
+  explicit Model(const cra5_config& cfg);
+  ~Model();
+  Model(const Model&) = delete;
+
+  void set_tensor(const std::string& name, const void* ptr, int dtype, int64_t numel);
+  void set_cdf(int which, const int32_t* cdf, const int32_t* len, const int32_t* off, int rows, int cols);
+  void set_coder(int spc_y, int spc_z);
+
+  // hot path (all pointers device, fp32)
+  void encode_to_latent(const float* x, float* y, const float* mean, const float* std_, cudaStream_t st);
+  void latent_to_reconstruction(const float* y_hat, float* x_hat, cudaStream_t st);
+  void latent_quantized(const float* y, float* y_hat, cudaStream_t st);  // encode_latent(type='quantized') tail
+  // entropy stage; returns pinned host buffers owned by the model, valid until the next call
+  void latent_to_bin(const float* y, const uint8_t** y_bytes, size_t* y_len, const uint8_t** z_bytes, size_t* z_len,
+                     cudaStream_t st);
+  void bin_to_latent(const uint8_t* y_bytes, size_t y_len, const uint8_t* z_bytes, size_t z_len, int z_h, int z_w,
+                     float* y_hat, cudaStream_t st);
+  // debug taps for the parity tests (device pointers into the workspace, valid until the next call)
+  const void* tap(const std::string& name, int64_t* numel, int* dtype) const;
+
+  const cra5_config& config() const { return cfg_; }
+  size_t workspace_bytes() const { return ws_bytes_; }
+  // geometry
+  int Hg, Wg, T;        // token grid of the main trunk
+  int Hh, Wh, Th;       // hyper grid
+  int Tpad;             // max rows of any window-partitioned order
+  int hd, hdh;          // head dims
+  int kpr, cs_pad, box_rows;  // patch-embed implicit-GEMM geometry
+  int nA, nB;           // ConvTranspose kernel-row classes (non-overlapping rows, overlapping rows)
+
+ private:
+  void finalize();  // resolve tensor pointers (first use)
+  const void* need(const std::string& name, int dtype, int64_t numel) const;
+  BlockWeights block_weights(const std::string& prefix, int D, int mlp) const;
+  WinMap make_winmap(int block_window_h, int block_window_w) const;
+  void run_block(cudaStream_t st, const BlockWeights& w, const TrunkBuffers& tb, const float* x_in, float* x_out, int T_,
+                 int D, int heads, int mlp, int win_h, int win_w, __nv_bfloat16* cat_out, int cat_col0, int cat_ld);
+  void run_h_a(cudaStream_t st, const float* y);     // -> z_
+  void run_h_s(cudaStream_t st, const float* z_hat); // -> params_ (sigma | mu)
+  void* alloc(size_t bytes);
+
+  cra5_config cfg_;
+  std::map<std::string, TensorRef> tensors_;
+  bool finalized_ = false;
+  std::vector<BlockWeights> ga_, gs_, ha_, hs_;
+  CdfTable eb_, gc_;
+  int spc_y_, spc_z_;
+
+  uint8_t* ws_ = nullptr;
+  size_t ws_bytes_ = 0, ws_used_ = 0;
+  TrunkBuffers main_, hyper_;
+  float *x1_, *x2_;                 // outputs of the two parallel head blocks
+  __nv_bfloat16* cat_;              // [T][2D] bf16 (mean || logvar tokens)
+  __nv_bfloat16* patches_;          // [Himg][Wg][cs_pad] bf16
+  float *y_, *yhat_, *params_;      // [latent][T], [latent][T], [2*latent][T]
+  __nv_bfloat16* ytok_;             // [T][latent]
+  float *z_, *zhat_;                // [zc][Th]
+  __nv_bfloat16* ztok_;             // [Th][zc]
+  __nv_bfloat16* ah_;               // hyper im2col / generic A operand [Th][max K]
+  int32_t *ysym_, *zsym_;
+  uint8_t* yidx_;
+  RansCoder* coder_ = nullptr;
+  uint8_t *host_y_ = nullptr, *host_z_ = nullptr;  // pinned output containers
+  size_t host_y_cap_ = 0, host_z_cap_ = 0;
+  std::map<std::string, TensorRef> taps_;
+};
+
+}  // namespace cra5

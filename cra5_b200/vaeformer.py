@@ -1,0 +1,411 @@
+"""Host-side mirror of the reference's `VAEformer` codec object (cra5/models/vaeformer/vaeformer.py:70-404).
+
+Same method names, argument meaning and error behaviour; every tensor operation is a call into libcra5b200.so
+(hand-written sm_100a kernels) through the C ABI in include/cra5_b200.h. torch is used for device memory, streams
+and one-time weight repacking only. There is no CPU execution path: constructing a model without a CUDA device or
+without the built library raises.
+
+Repacked parameter names handed to the library (besides the reference's own state-dict names):
+  g_a.patch_embed.proj.weight  bf16 [D][ph * ceil(C*pw/64)*64]   K ordered (kernel row, channel, column), zero padded
+  g_s.final.A / g_s.final.B    bf16 ConvTranspose2d weight split by kernel-row class (see csrc/model.cu)
+  quant_conv.weight / .bias    only the `mean` half of the moments (distributions.py:32,71-72)
+  entropy_bottleneck.medians   fp32 [z_chans] = quantiles[:, 0, 1]
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from collections import OrderedDict
+from typing import Optional
+
+import torch
+
+from . import _lib, config as C, entropy_tables as ET
+
+_DT = {torch.float32: 0, torch.bfloat16: 1, torch.int32: 2, torch.uint8: 3}
+
+
+class _CConfig(ctypes.Structure):
+    _fields_ = [("in_chans", ctypes.c_int32), ("img_h", ctypes.c_int32), ("img_w", ctypes.c_int32),
+                ("patch_h", ctypes.c_int32), ("patch_w", ctypes.c_int32), ("stride_h", ctypes.c_int32),
+                ("stride_w", ctypes.c_int32), ("dim", ctypes.c_int32), ("depth", ctypes.c_int32),
+                ("num_heads", ctypes.c_int32), ("mlp_ratio", ctypes.c_int32), ("n_windows", ctypes.c_int32),
+                ("window_h", ctypes.c_int32 * 4), ("window_w", ctypes.c_int32 * 4), ("interval", ctypes.c_int32),
+                ("latent_chans", ctypes.c_int32), ("z_chans", ctypes.c_int32), ("hyper_dim", ctypes.c_int32),
+                ("hyper_depth", ctypes.c_int32), ("hyper_heads", ctypes.c_int32), ("hyper_patch_h", ctypes.c_int32),
+                ("hyper_patch_w", ctypes.c_int32), ("ln_eps", ctypes.c_float),
+                ("streams_per_channel_y", ctypes.c_int32), ("streams_per_channel_z", ctypes.c_int32)]
+
+
+def _c_config(cfg: C.VaeformerConfig, spc_y: int, spc_z: int) -> _CConfig:
+    if len(cfg.window_sizes) > 4:
+        raise ValueError("at most 4 window sizes are supported")
+    c = _CConfig()
+    c.in_chans = cfg.in_chans
+    c.img_h, c.img_w = cfg.img_size
+    c.patch_h, c.patch_w = cfg.patch_size
+    c.stride_h, c.stride_w = cfg.patch_stride
+    c.dim, c.depth, c.num_heads, c.mlp_ratio = cfg.dim, cfg.depth, cfg.num_heads, cfg.mlp_ratio
+    c.n_windows = len(cfg.window_sizes)
+    for i, (h, w) in enumerate(cfg.window_sizes):
+        c.window_h[i], c.window_w[i] = h, w
+    c.interval = cfg.interval
+    c.latent_chans, c.z_chans = cfg.latent_chans, cfg.z_chans
+    c.hyper_dim, c.hyper_depth, c.hyper_heads = cfg.hyper_dim, cfg.hyper_depth, cfg.hyper_heads
+    c.hyper_patch_h, c.hyper_patch_w = cfg.hyper_patch
+    c.ln_eps = cfg.ln_eps
+    c.streams_per_channel_y, c.streams_per_channel_z = spc_y, spc_z
+    return c
+
+
+def init_state_dict(cfg: C.VaeformerConfig, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """random initialisation with the reference's distributions: trunc_normal(0.02) Linear weights, zero biases, unit
+    LayerNorm, proj/fc2 rescaled by 1/sqrt(2*layer) (vit_nlc.py:438-453), default Conv2d init for the conv layers,
+    EntropyBottleneck as in entropy_models.py:364-385. (Values differ from a reference-side `torch.manual_seed` run;
+    only the distributions are the same.)"""
+    import numpy as np
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    for key, shape in C.param_shapes(cfg).items():
+        if key.startswith("entropy_bottleneck."):
+            continue
+        if ".norm" in key:
+            sd[key] = torch.ones(shape) if key.endswith("weight") else torch.zeros(shape)
+        elif key.endswith("pos_embed"):
+            sd[key] = torch.randn(shape, generator=g) * 0.02
+        elif len(shape) == 4:  # Conv2d / ConvTranspose2d default: U(-1/sqrt(fan_in), 1/sqrt(fan_in))
+            fan_in = shape[1] * shape[2] * shape[3] if "final" not in key else shape[0] * shape[2] * shape[3]
+            sd[key] = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan_in)
+        elif key.endswith("bias"):
+            if key.startswith(("quant_conv", "post_quant_conv", "g_a.patch_embed", "h_a.patch_embed")):
+                fan_in = {"quant_conv": 2 * cfg.dim, "post_quant_conv": cfg.latent_chans}.get(key.split(".")[0], 64)
+                sd[key] = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan_in)
+            else:
+                sd[key] = torch.zeros(shape)
+        else:
+            w = torch.nn.init.trunc_normal_(torch.empty(shape), std=0.02, generator=g)
+            parts = key.split(".")
+            if parts[1] == "blocks" and (key.endswith("attn.proj.weight") or key.endswith("mlp.fc2.weight")):
+                w = w / math.sqrt(2.0 * (int(parts[2]) + 1))
+            sd[key] = w
+    filt = (1,) + C.EB_FILTERS + (1,)
+    scale = 10.0 ** (1 / (len(C.EB_FILTERS) + 1))
+    shapes = C.param_shapes(cfg)
+    for i in range(len(C.EB_FILTERS) + 1):
+        init = float(np.log(np.expm1(1 / scale / filt[i + 1])))
+        sd[f"entropy_bottleneck._matrix{i}"] = torch.full(shapes[f"entropy_bottleneck._matrix{i}"], init)
+        sd[f"entropy_bottleneck._bias{i}"] = torch.rand(shapes[f"entropy_bottleneck._bias{i}"], generator=g) - 0.5
+        if i < len(C.EB_FILTERS):
+            sd[f"entropy_bottleneck._factor{i}"] = torch.zeros(shapes[f"entropy_bottleneck._factor{i}"])
+    sd["entropy_bottleneck.quantiles"] = torch.tensor([-10.0, 0.0, 10.0]).repeat(cfg.z_chans, 1, 1)
+    return OrderedDict((k, sd[k]) for k in shapes)
+
+
+class VAEformer:
+    """Drop-in for the reference `VAEformer` on the inference path.
+
+    `VAEformer(268)` reproduces the hard-coded shipped variant (vaeformer.py:93-142); other geometries pass a
+    `VaeformerConfig` via `cfg=`.
+    """
+
+    def __init__(self, model_version: int = 268, cfg: Optional[C.VaeformerConfig] = None, device="cuda",
+                 streams_per_channel=(8, 1), init_seed: Optional[int] = 0, **kwargs):
+        if cfg is None:
+            if model_version != 268:
+                # the reference dies on `Encoder(**None)` here (vaeformer.py:150); say why instead
+                raise ValueError(f'model_version {model_version} has no built-in configuration; pass cfg=')
+            cfg = C.cra5_268()
+        self.cfg = cfg.validate()
+        if not torch.cuda.is_available():
+            raise RuntimeError("cra5_b200 needs a CUDA device (sm_100a); there is no CPU execution path")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("cra5_b200 models live on a CUDA device")
+        self._spc = tuple(streams_per_channel)
+        self._handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            cc = _c_config(self.cfg, *self._spc)
+            _lib.check(_lib.lib.cra5_model_create(ctypes.byref(cc), ctypes.byref(self._handle)))
+        self._dev = {}      # name -> device tensor handed to the library (kept alive here)
+        self._sd = None     # fp32 CPU copy in reference layout (for state_dict())
+        self._cdf = {"entropy_bottleneck": None, "gaussian_conditional": None}
+        self.scale_table = torch.empty(0)
+        self.training = False
+        if init_seed is not None:
+            self.load_state_dict(init_state_dict(self.cfg, init_seed))
+
+    # ------------------------------------------------------------------ nn.Module look-alikes
+    def eval(self):
+        self.training = False
+        return self
+
+    def to(self, device):
+        if torch.device(device).type != "cuda":
+            raise RuntimeError("cra5_b200 models live on a CUDA device")
+        if torch.device(device) != self.device and torch.device(device).index not in (None, self.device.index):
+            raise RuntimeError("moving a cra5_b200 model between GPUs is not supported; construct it on the target GPU")
+        return self
+
+    def cuda(self):
+        return self
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) and self._handle.value:
+                _lib.lib.cra5_model_destroy(self._handle)
+                self._handle = ctypes.c_void_p()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ parameters
+    def _set(self, name: str, t: torch.Tensor):
+        t = t.detach().to(self.device).contiguous()
+        self._dev[name] = t
+        _lib.check(_lib.lib.cra5_model_set_tensor(self._handle, name.encode(), _lib.ptr(t), _DT[t.dtype],
+                                                  ctypes.c_int64(t.numel())))
+
+    @classmethod
+    def from_state_dict(cls, state_dict, device="cuda", **kw):
+        """VAEformer.from_state_dict, vaeformer.py:168-185: strips the 'backbone.' prefix, drops 'kl_loss.logvar'."""
+        sd = OrderedDict((k.replace("backbone.", ""), v) for k, v in state_dict.items() if "kl_loss.logvar" not in k)
+        cfg = kw.pop("cfg", None) or C.config_from_state_dict(sd)
+        net = cls(268, cfg=cfg, device=device, init_seed=None, **kw)
+        net.load_state_dict(sd)
+        return net
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        """CompressionModel.load_state_dict, models/base.py:69-89: float parameters by name; CDF buffers shipped in the
+        checkpoint are honoured (no recomputation) when present and non-empty."""
+        cfg = self.cfg
+        shapes = C.param_shapes(cfg)
+        sd = {k: v for k, v in state_dict.items()}
+        missing = [k for k in shapes if k not in sd]
+        unexpected = [k for k in sd if k not in shapes and k not in C.BUFFER_KEYS]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict: missing keys {missing[:5]}{'...' if len(missing) > 5 else ''}, "
+                               f"unexpected keys {unexpected[:5]}")
+        for k, shape in shapes.items():
+            if k in sd and tuple(sd[k].shape) != tuple(shape):
+                raise RuntimeError(f"size mismatch for {k}: copying a param with shape {tuple(sd[k].shape)} from "
+                                   f"checkpoint, the shape in current model is {tuple(shape)}")
+        self._sd = OrderedDict((k, sd[k].detach().float().cpu().clone()) for k in shapes if k in sd)
+        with torch.cuda.device(self.device):
+            self._upload()
+            # CDF buffers travelling inside a checkpoint (checkpoint row)
+            for mod in ("entropy_bottleneck", "gaussian_conditional"):
+                q = sd.get(f"{mod}._quantized_cdf")
+                if q is not None and q.numel() > 0:
+                    tabs = ET.CdfTables(q.int().cpu(), sd[f"{mod}._cdf_length"].int().cpu().reshape(-1),
+                                        sd[f"{mod}._offset"].int().cpu().reshape(-1))
+                    st = sd.get("gaussian_conditional.scale_table") if mod == "gaussian_conditional" else None
+                    self._install_tables(mod, tabs, st)
+        return self
+
+    def _upload(self):
+        cfg, sd = self.cfg, self._sd
+        D, Cc = cfg.dim, cfg.in_chans
+        ph, pw = cfg.patch_size
+        sh = cfg.patch_stride[0]
+        dev = self.device
+
+        def bf(t):
+            return t.to(dev).to(torch.bfloat16).contiguous()
+
+        for k, v in sd.items():
+            if k.startswith("entropy_bottleneck."):
+                continue
+            if k in ("g_a.patch_embed.proj.weight", "g_s.final.weight", "quant_conv.weight", "quant_conv.bias",
+                     "post_quant_conv.weight", "h_a.patch_embed.proj.weight"):
+                continue
+            if v.dim() == 2:          # nn.Linear weights feed tensor-core GEMMs
+                self._set(k, bf(v))
+            elif k.endswith("pos_embed"):
+                self._set(k, v.reshape(-1, v.shape[-1]).float())
+            else:                     # biases, LayerNorm affine
+                self._set(k, v.float())
+        # patch-embed conv as an implicit GEMM: [D][C][ph][pw] -> [D][ph][C*pw] padded to whole 64-wide K blocks
+        w = sd["g_a.patch_embed.proj.weight"].to(dev)
+        kpr = (Cc * pw + 63) // 64
+        w = w.permute(0, 2, 1, 3).reshape(D, ph, Cc * pw)
+        wp = torch.zeros(D, ph, kpr * 64, device=dev)
+        wp[:, :, : Cc * pw] = w
+        self._set("g_a.patch_embed.proj.weight", bf(wp.reshape(D, ph * kpr * 64)))
+        # reconstruction head
+        wf = sd["g_s.final.weight"].to(dev)
+        if cfg.conv_head:
+            P = wf.permute(2, 1, 3, 0).contiguous()          # [ph][C][pw][D]
+            nB = ph - sh
+            if sh - nB > 0:
+                self._set("g_s.final.A", bf(P[nB:sh].reshape(-1, D)))
+            if nB > 0:
+                self._set("g_s.final.B", bf(torch.cat([P[:nB], P[sh:sh + nB]], dim=-1).reshape(-1, 2 * D)))
+        else:
+            self._set("g_s.final.weight", bf(wf))
+        lat = cfg.latent_chans
+        self._set("quant_conv.weight", bf(sd["quant_conv.weight"][:lat].reshape(lat, 2 * D)))
+        self._set("quant_conv.bias", sd["quant_conv.bias"][:lat].float())
+        self._set("post_quant_conv.weight", bf(sd["post_quant_conv.weight"].reshape(D, lat)))
+        self._set("h_a.patch_embed.proj.weight", bf(sd["h_a.patch_embed.proj.weight"].reshape(cfg.hyper_dim, -1)))
+        self._set("entropy_bottleneck.medians", sd["entropy_bottleneck.quantiles"][:, 0, 1].float())
+
+    def state_dict(self):
+        out = OrderedDict(self._sd)
+        for mod in ("entropy_bottleneck", "gaussian_conditional"):
+            t = self._cdf[mod]
+            out[f"{mod}._quantized_cdf"] = t.quantized_cdf.clone() if t else torch.IntTensor()
+            out[f"{mod}._cdf_length"] = t.cdf_length.clone() if t else torch.IntTensor()
+            out[f"{mod}._offset"] = t.offset.clone() if t else torch.IntTensor()
+        out["gaussian_conditional.scale_table"] = self.scale_table.clone()
+        return out
+
+    # ------------------------------------------------------------------ CDF tables
+    def _install_tables(self, mod: str, tabs: ET.CdfTables, scale_table=None):
+        which = 0 if mod == "entropy_bottleneck" else 1
+        if tabs.quantized_cdf.dim() != 2:
+            raise ValueError(f"Invalid CDF size {tuple(tabs.quantized_cdf.size())}")
+        d = {k: getattr(tabs, k).int().to(self.device).contiguous() for k in ("quantized_cdf", "cdf_length", "offset")}
+        self._dev[f"{mod}.tables"] = d
+        self._cdf[mod] = tabs
+        _lib.check(_lib.lib.cra5_model_set_cdf(self._handle, which, _lib.ptr(d["quantized_cdf"]), _lib.ptr(d["cdf_length"]),
+                                               _lib.ptr(d["offset"]), d["quantized_cdf"].shape[0], d["quantized_cdf"].shape[1]))
+        if which == 1 and scale_table is not None:
+            self.scale_table = scale_table.detach().float().cpu()
+            self._set("gaussian_conditional.scale_table", self.scale_table)
+
+    def update(self, scale_table=None, force: bool = False) -> bool:
+        """CompressionModel.update, models/base.py:91-115"""
+        updated = False
+        with torch.cuda.device(self.device):
+            if self._cdf["entropy_bottleneck"] is None or force:
+                self._install_tables("entropy_bottleneck", ET.entropy_bottleneck_tables(self._sd))
+                updated = True
+            if self._cdf["gaussian_conditional"] is None or force:
+                st = ET.get_scale_table() if scale_table is None else torch.as_tensor(scale_table, dtype=torch.float32)
+                self._install_tables("gaussian_conditional", ET.gaussian_conditional_tables(st), st)
+                updated = True
+        return updated
+
+    def set_coder(self, streams_per_channel_y: int = 8, streams_per_channel_z: int = 1):
+        _lib.check(_lib.lib.cra5_model_set_coder(self._handle, streams_per_channel_y, streams_per_channel_z))
+        self._spc = (streams_per_channel_y, streams_per_channel_z)
+
+    # ------------------------------------------------------------------ helpers
+    def _check_x(self, x):
+        cfg = self.cfg
+        if x.dim() != 4 or tuple(x.shape[1:]) != (cfg.in_chans, *cfg.img_size):
+            raise ValueError(f"expected input of shape (B, {cfg.in_chans}, {cfg.img_size[0]}, {cfg.img_size[1]}), "
+                             f"got {tuple(x.shape)}")
+        return x.to(self.device, torch.float32).contiguous()
+
+    def _latent_shape(self, B=1):
+        return (B, self.cfg.latent_chans, *self.cfg.grid)
+
+    def _check_y(self, y):
+        if y.dim() != 4 or tuple(y.shape[1:]) != self._latent_shape()[1:]:
+            raise ValueError(f"expected latent of shape {self._latent_shape('B')}, got {tuple(y.shape)}")
+        return y.to(self.device, torch.float32).contiguous()
+
+    def _require_cdfs(self):
+        if self._cdf["entropy_bottleneck"] is None or self._cdf["gaussian_conditional"] is None:
+            raise ValueError("Uninitialized CDFs. Run update() first")
+
+    # ------------------------------------------------------------------ the codec (vaeformer.py:272-400)
+    def encode_latent(self, x, type="quantized", mean=None, std=None):
+        """-> (y, y_hat, y_likelihoods). With type='float' the last two are None. `mean`/`std` (C,) optionally fuse the
+        input normalisation into the first kernel (additive extension)."""
+        x = self._check_x(x)
+        y = torch.empty(self._latent_shape(x.shape[0]), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            s = _lib.stream_ptr()
+            for b in range(x.shape[0]):
+                _lib.check(_lib.lib.cra5_encode_to_latent(self._handle, _lib.ptr(x[b]), _lib.ptr(y[b]), _lib.ptr(mean),
+                                                          _lib.ptr(std), s))
+            if type != "quantized":
+                return y, None, None
+            self._require_cdfs()
+            y_hat = torch.empty_like(y)
+            for b in range(x.shape[0]):
+                _lib.check(_lib.lib.cra5_latent_quantized(self._handle, _lib.ptr(y[b]), _lib.ptr(y_hat[b]), s))
+        return y, y_hat, None
+
+    def decode_latent(self, y, type="quantized"):
+        y = self._check_y(y)
+        cfg = self.cfg
+        x_hat = torch.empty((y.shape[0], cfg.in_chans, *cfg.img_size), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            s = _lib.stream_ptr()
+            for b in range(y.shape[0]):
+                _lib.check(_lib.lib.cra5_latent_to_reconstruction(self._handle, _lib.ptr(y[b]), _lib.ptr(x_hat[b]), s))
+        return x_hat
+
+    def compress_from_latent(self, y):
+        self._require_cdfs()
+        y = self._check_y(y)
+        y_strings, z_strings = [], []
+        yb, zb = ctypes.c_void_p(), ctypes.c_void_p()
+        yl, zl = ctypes.c_uint64(), ctypes.c_uint64()
+        with torch.cuda.device(self.device):
+            s = _lib.stream_ptr()
+            for b in range(y.shape[0]):
+                _lib.check(_lib.lib.cra5_latent_to_bin(self._handle, _lib.ptr(y[b]), ctypes.byref(yb), ctypes.byref(yl),
+                                                       ctypes.byref(zb), ctypes.byref(zl), s))
+                y_strings.append(ctypes.string_at(yb.value, yl.value))
+                z_strings.append(ctypes.string_at(zb.value, zl.value))
+        return {"strings": [y_strings, z_strings], "z_shape": torch.Size(self.cfg.hyper_grid)}
+
+    def compress(self, x):
+        y, _, _ = self.encode_latent(x, type="float")
+        return self.compress_from_latent(y)
+
+    def decompress(self, strings, shape, return_format: str = "reconstructed"):
+        assert isinstance(strings, list) and len(strings) == 2
+        self._require_cdfs()
+        if not isinstance(strings[0], (tuple, list)) or not isinstance(strings[1], (tuple, list)):
+            raise ValueError("Invalid `strings` parameter type.")
+        if len(strings[0]) != len(strings[1]):
+            raise ValueError("Invalid strings or indexes parameters")
+        B = len(strings[0])
+        y_hat = torch.empty(self._latent_shape(B), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            s = _lib.stream_ptr()
+            for b in range(B):
+                ys, zs = bytes(strings[0][b]), bytes(strings[1][b])
+                _lib.check(_lib.lib.cra5_bin_to_latent(self._handle, ys, ctypes.c_uint64(len(ys)), zs,
+                                                       ctypes.c_uint64(len(zs)), int(shape[0]), int(shape[1]),
+                                                       _lib.ptr(y_hat[b]), s))
+        if return_format == "latent":
+            return y_hat
+        return {"x_hat": self.decode_latent(y_hat)}
+
+    def forward(self, x):
+        """eval-mode forward (vaeformer.py:302-333) without the likelihood tensors (rate estimation: SURVEY 8f-3)."""
+        y, y_hat, _ = self.encode_latent(x, type="quantized")
+        return {"x_hat": self.decode_latent(y_hat), "likelihoods": {"y": None, "z": None}, "posterior": None}
+
+    __call__ = forward
+
+    def prediction(self, inputs):
+        """vaeformer.py:254-269 (the reference version reads a non-existent key and cannot run; this one can)"""
+        import time
+        torch.cuda.synchronize(self.device)
+        t1 = time.time()
+        out = self.compress(inputs)
+        torch.cuda.synchronize(self.device)
+        t2 = time.time()
+        x_hat = self.decompress(out["strings"], out["z_shape"])
+        torch.cuda.synchronize(self.device)
+        t3 = time.time()
+        return {**x_hat, "strings": out["strings"], "z_shape": out["z_shape"], "x_shape": inputs.shape,
+                "encoding_time": (t2 - t1) / inputs.size(0), "decoding_time": (t3 - t2) / inputs.size(0)}
+
+    # ------------------------------------------------------------------ test hooks
+    def tap(self, name: str) -> torch.Tensor:
+        """copy of an intermediate of the last call (parity tests)"""
+        p, n, dt = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int()
+        _lib.check(_lib.lib.cra5_model_tap(self._handle, name.encode(), ctypes.byref(p), ctypes.byref(n), ctypes.byref(dt)))
+        dtype = {v: k for k, v in _DT.items()}[dt.value]
+        out = torch.empty(n.value, dtype=dtype, device=self.device)
+        _lib.check(_lib.lib.cra5_model_tap_read(self._handle, name.encode(), _lib.ptr(out),
+                                                ctypes.c_uint64(out.numel() * out.element_size()), _lib.stream_ptr()))
+        torch.cuda.synchronize(self.device)
+        return out

@@ -61,6 +61,126 @@ CRA5_API int cra5_op_gemm_check(const void* A_dev, int lda, const void* B_dev, i
 CRA5_API int cra5_op_attention(const void* Q_dev, const void* K_dev, const void* Vt_dev, void* out_dev, int ldo, int heads,
                       int rows_total, int seg_len, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Host utilities (run once per model, like the reference's C++ helpers)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* float pmf -> strictly increasing uint32 CDF with cdf[n] == 1 << precision. Replaces
+ * compressai._CXX.pmf_to_quantized_cdf (cpp_exts/ops/ops.cpp:40-109, bound at :111-118; caller
+ * entropy_models.py:89-92). `cdf_out` holds n + 1 entries. CRA5_ERR_INVALID for negative / non-finite / all-zero
+ * pmf (the reference raises ValueError through std::domain_error). */
+CRA5_API int cra5_pmf_to_quantized_cdf(const float* pmf, int n, int precision, uint32_t* cdf_out);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Model handle
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct cra5_config {
+  int32_t in_chans;          /* vaeformer.py:106 */
+  int32_t img_h, img_w;      /* vaeformer.py:119 */
+  int32_t patch_h, patch_w;  /* vaeformer.py:104 */
+  int32_t stride_h, stride_w;/* vaeformer.py:105 */
+  int32_t dim, depth, num_heads, mlp_ratio; /* vit_nlc.py:1009-1015 */
+  int32_t n_windows;         /* vaeformer.py:112 */
+  int32_t window_h[4], window_w[4];
+  int32_t interval;          /* vaeformer.py:113 */
+  int32_t latent_chans;      /* vaeformer.py:94 */
+  int32_t z_chans;           /* vaeformer.py:95 */
+  int32_t hyper_dim, hyper_depth, hyper_heads; /* vaeformer.py:129-131 */
+  int32_t hyper_patch_h, hyper_patch_w;        /* vaeformer.py:124 */
+  float ln_eps;              /* vit_nlc.py:381 */
+  int32_t streams_per_channel_y; /* chunk-parallel coder: interleaved rANS sub-streams per latent channel */
+  int32_t streams_per_channel_z;
+} cra5_config;
+
+typedef struct cra5_model cra5_model;
+
+#define CRA5_DT_F32 0
+#define CRA5_DT_BF16 1
+#define CRA5_DT_I32 2
+#define CRA5_DT_U8 3
+
+/* Allocates the workspace on the current CUDA device. Replaces VAEformer.__init__ (vaeformer.py:78-166). */
+CRA5_API int cra5_model_create(const cra5_config* cfg, cra5_model** out);
+CRA5_API int cra5_model_destroy(cra5_model* m);
+CRA5_API int cra5_model_workspace_bytes(cra5_model* m, uint64_t* bytes);
+
+/* Hand a parameter to the model by its state-dict name (device pointer, caller keeps it alive). Matmul weights are
+ * bf16, everything else fp32; repacked conv weights use the names documented in cra5_b200/vaeformer.py.
+ * Replaces nn.Module.load_state_dict (models/base.py:69-89). */
+CRA5_API int cra5_model_set_tensor(cra5_model* m, const char* name, const void* dev_ptr, int dtype, int64_t numel);
+
+/* CDF tables as built by update() / shipped in a checkpoint: which = 0 EntropyBottleneck, 1 GaussianConditional.
+ * Device int32 pointers: cdf [rows][cols], cdf_length [rows], offset [rows]
+ * (entropy_models.py:127-129 buffers `_quantized_cdf`, `_cdf_length`, `_offset`). */
+CRA5_API int cra5_model_set_cdf(cra5_model* m, int which, const int32_t* cdf_dev, const int32_t* cdf_length_dev,
+                                const int32_t* offset_dev, int rows, int cols);
+
+/* Interleaved rANS sub-streams per latent channel for y and z (parallelism / rate knob of the CR5B container). */
+CRA5_API int cra5_model_set_coder(cra5_model* m, int streams_per_channel_y, int streams_per_channel_z);
+
+/* x (C,H,W) fp32 -> y (latent, Hg, Wg) fp32. mean/std: optional per-channel (C) device arrays; when given the input
+ * is physical-unit data and (x-mean)/std (cra5_api.normalization, cra5_api.py:264-266) is fused into the first kernel.
+ * Replaces VAEformer.encode_latent(type='float') (vaeformer.py:272-292) = cra5_api.encode_to_latent (:53-71). */
+CRA5_API int cra5_encode_to_latent(cra5_model* m, const float* x_dev, float* y_dev, const float* mean_dev,
+                                   const float* std_dev, void* stream);
+
+/* y -> y_hat = round(y - mu) + mu with (sigma, mu) = h_s(round(h_a(y) - median) + median): the `type='quantized'`
+ * tail of VAEformer.encode_latent (vaeformer.py:284-290). */
+CRA5_API int cra5_latent_quantized(cra5_model* m, const float* y_dev, float* y_hat_dev, void* stream);
+
+/* y -> {y string, z string}. The returned pointers are pinned host buffers owned by the handle, valid until the next
+ * call on it. Replaces VAEformer.compress_from_latent (vaeformer.py:334-348) = cra5_api.latent_to_bin (:73-79), i.e.
+ * h_a, EntropyBottleneck.compress, h_s, build_indexes, GaussianConditional.compress and the C++ coder behind them
+ * (entropy_models.py:239-272 -> compressai.ans RansEncoder.encode_with_indexes, rans_interface.cpp:202-213). */
+CRA5_API int cra5_latent_to_bin(cra5_model* m, const float* y_dev, const uint8_t** y_bytes, uint64_t* y_len,
+                                const uint8_t** z_bytes, uint64_t* z_len, void* stream);
+
+/* {y string, z string} (host memory) -> y_hat (latent, Hg, Wg) fp32 on the device. Replaces
+ * VAEformer.decompress(return_format='latent') (vaeformer.py:378-391) = cra5_api.bin_to_latent (:127-144), i.e.
+ * EntropyBottleneck.decompress, h_s, build_indexes, GaussianConditional.decompress and RansDecoder.decode_with_indexes
+ * (rans_interface.cpp:215-284). */
+CRA5_API int cra5_bin_to_latent(cra5_model* m, const uint8_t* y_bytes, uint64_t y_len, const uint8_t* z_bytes,
+                                uint64_t z_len, int z_h, int z_w, float* y_hat_dev, void* stream);
+
+/* y_hat -> x_hat (C,H,W) fp32, normalised units. Replaces VAEformer.decode_latent (vaeformer.py:294-300) =
+ * cra5_api.latent_to_reconstruction (:146-151). */
+CRA5_API int cra5_latent_to_reconstruction(cra5_model* m, const float* y_hat_dev, float* x_hat_dev, void* stream);
+
+/* per-channel (x - mean)/std (forward != 0) or x*std + mean (forward == 0); in == out allowed.
+ * Replaces cra5_api.normalization / de_normalization (cra5_api.py:264-271). */
+CRA5_API int cra5_normalize(const float* in_dev, float* out_dev, const float* mean_dev, const float* std_dev,
+                            int channels, uint64_t hw, int forward, void* stream);
+
+/* Debug tap for the parity tests: device pointer of an intermediate of the LAST call ("y", "z", "z_hat", "scales",
+ * "means", "y_symbols", "y_indexes", "z_symbols", "tokens"). */
+CRA5_API int cra5_model_tap(cra5_model* m, const char* name, const void** dev_ptr, int64_t* numel, int* dtype);
+
+CRA5_API int cra5_model_tap_read(cra5_model* m, const char* name, void* dst_dev, uint64_t dst_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Entropy-stage operators on caller-provided device buffers (parity tests drive these directly)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* symbols = round_half_even(y - mu), index = scale-table bucket of max(sigma, bound), y_hat = symbols + mu. Any of
+ * y/sym/idx/y_hat may be NULL to skip that part. Replaces EntropyModel.quantize (entropy_models.py:155-184) +
+ * GaussianConditional.build_indexes (:679-685). */
+CRA5_API int cra5_op_gc_quantize(const float* y_dev, const float* sigma_dev, const float* mu_dev,
+                                 const float* scale_table_dev, int levels, float bound, int32_t* sym_dev,
+                                 uint8_t* idx_dev, float* y_hat_dev, uint64_t n, void* stream);
+
+/* Chunk-parallel rANS over a (n_channels, L) int32 symbol tensor. idx_dev NULL => index == channel
+ * (EntropyBottleneck). Writes the container (header, stream lengths, payload) to out_host (capacity out_cap) and its
+ * size to out_len. Each sub-stream is bit-identical to RansEncoder.encode_with_indexes (rans_interface.cpp:202-213)
+ * applied to that sub-stream's symbols. */
+CRA5_API int cra5_op_rans_encode(const int32_t* sym_dev, const uint8_t* idx_dev, const int32_t* cdf_dev, int cdf_cols,
+                                 const int32_t* cdf_length_dev, const int32_t* offset_dev, int n_channels, int L,
+                                 int spc, uint8_t* out_host, uint64_t out_cap, uint64_t* out_len, void* stream);
+
+/* Inverse of cra5_op_rans_encode: container (host) -> int32 symbols (device). */
+CRA5_API int cra5_op_rans_decode(const uint8_t* bytes_host, uint64_t len, const uint8_t* idx_dev,
+                                 const int32_t* cdf_dev, int cdf_cols, const int32_t* cdf_length_dev,
+                                 const int32_t* offset_dev, int n_channels, int L, int32_t* sym_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
