@@ -174,12 +174,31 @@ class cra5_api:
         return (np.array([table[n]["mean"] for n in names], dtype=np.float32),
                 np.array([table[n]["std"] for n in names], dtype=np.float32))
 
+    def _affine(self, data, out, forward):
+        import ctypes
+        from .. import _lib
+        C = data.shape[-3]
+        hw = data.shape[-2] * data.shape[-1]
+        with torch.cuda.device(data.device):
+            for b in range(data.numel() // (C * hw)):
+                src = data.reshape(-1, C, hw)[b]
+                dst = out.reshape(-1, C, hw)[b]
+                _lib.check(_lib.lib.cra5_normalize(_lib.ptr(src), _lib.ptr(dst), _lib.ptr(self.mean), _lib.ptr(self.std),
+                                                   C, ctypes.c_uint64(hw), forward, _lib.stream_ptr()))
+        return out
+
     def normalization(self, data):
-        return (data - self.mean) / self.std
+        """(x - mean_c) / std_c  (cra5_api.py:264-266); on the GPU this is the library's per-channel kernel"""
+        if data.is_cuda and data.dtype == torch.float32 and data.is_contiguous():
+            return self._affine(data, torch.empty_like(data), 1)
+        return (data - self.mean.to(data.device)) / self.std.to(data.device)
 
     def de_normalization(self, data):
-        data *= self.std
-        data += self.mean
+        """in-place x * std_c + mean_c  (cra5_api.py:268-271)"""
+        if data.is_cuda and data.dtype == torch.float32 and data.is_contiguous():
+            return self._affine(data, data, 0)
+        data *= self.std.to(data.device)
+        data += self.mean.to(data.device)
         return data
 
     # ------------------------------------------------------------------ plots (outside the hot path; need matplotlib)

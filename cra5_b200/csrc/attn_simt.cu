@@ -70,6 +70,8 @@ void attention_simt(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16
     configured = smem;
   }
   dim3 grid((seg_len + AS_WARPS - 1) / AS_WARPS, rows_total / seg_len, heads);
+  LaunchScope scope(st, "attn_simt", 4.0 * heads * (double)rows_total * seg_len * hd,
+                    4.0 * 2.0 * heads * (double)rows_total * hd);
   attn_simt_kernel<<<grid, AS_WARPS * 32, smem, st>>>(Q, K, Vt, out, ldo, hd, rows_total, seg_len);
   CRA5_CUDA(cudaGetLastError());
 }

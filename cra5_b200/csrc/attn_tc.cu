@@ -280,6 +280,8 @@ void attention_tc(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* 
   p.out = out;
   p.ldo = ldo;
   dim3 grid((seg_len + AT_BM - 1) / AT_BM, rows_total / seg_len, heads);
+  LaunchScope scope(st, "attn_tc", 4.0 * heads * (double)rows_total * seg_len * AT_HD,
+                    4.0 * 2.0 * heads * (double)rows_total * AT_HD);
   attn_tc_kernel<<<grid, AT_THREADS, AttnSmem::TOTAL, st>>>(tmQ, tmK, tmVt, p);
   CRA5_CUDA(cudaGetLastError());
 }

@@ -8,6 +8,8 @@
 #include "coder.h"
 
 #include <memory>
+#include <algorithm>
+#include <string.h>
 
 namespace cra5 {
 std::string& last_error_slot() {
@@ -183,6 +185,28 @@ int cra5_model_tap(cra5_model* m, const char* name, const void** dev_ptr, int64_
   return guarded([&] {
     MODEL_GUARD(m);
     *dev_ptr = m->impl->tap(name, numel, dtype);
+  });
+}
+
+int cra5_launch_count(uint64_t* count) {
+  return guarded([&] { *count = launch_count(); });
+}
+int cra5_profile_enable(int on) {
+  return guarded([&] {
+    prof_reset();
+    prof_enable(on != 0);
+  });
+}
+int cra5_profile_report(char* buf, uint64_t cap, uint64_t* needed) {
+  return guarded([&] {
+    const std::string js = prof_report_json();
+    if (needed) *needed = js.size() + 1;
+    if (buf != nullptr && cap > 0) {
+      const size_t n = std::min<size_t>(js.size(), cap - 1);
+      memcpy(buf, js.data(), n);
+      buf[n] = 0;
+    }
+    prof_reset();
   });
 }
 

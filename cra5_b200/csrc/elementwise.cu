@@ -51,6 +51,7 @@ void frame_to_patches(cudaStream_t st, const float* x, __nv_bfloat16* out, const
   dim3 grid(Wp / TOK, H, (C + CH - 1) / CH);
   const size_t smem = (size_t)CH * TOK * pw * sizeof(float);
   CRA5_CHECK(smem <= 48 * 1024, ERR_INVALID, "unsupported geometry: patch width too large");
+  LaunchScope scope(st, "frame_to_patches", 0.0, 4.0 * C * H * (double)W + 2.0 * H * (double)Wp * C * pw);
   frame_to_patches_kernel<TOK, CH><<<grid, 256, smem, st>>>(x, out, mean, std_, C, H, W, Wp, pw, cs_pad);
   CRA5_CUDA(cudaGetLastError());
 }
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __rest
 void layernorm_bf16(cudaStream_t st, const float* x, const float* gamma, const float* beta, float eps,
                     __nv_bfloat16* out, int rows_out, int D, const WinMap& wm) {
   const int blocks = (rows_out + 7) / 8;
+  LaunchScope scope(st, "layernorm_bf16", 0.0, 6.0 * rows_out * (double)D);
   if (D <= 128)
     layernorm_bf16_kernel<4><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, rows_out, D, wm);
   else if (D <= 512)
@@ -136,6 +138,7 @@ __global__ void im2col_latent_kernel(const float* __restrict__ y, __nv_bfloat16*
 void im2col_latent(cudaStream_t st, const float* y, __nv_bfloat16* A, int C, int Hy, int Wy, int p1, int p2, int lda) {
   const size_t total = (size_t)(Hy / p1) * (Wy / p2) * C * p1 * p2;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  LaunchScope scope(st, "im2col_latent", 0.0, 6.0 * (double)total);
   im2col_latent_kernel<<<blocks, 256, 0, st>>>(y, A, C, Hy, Wy, p1, p2, lda);
   CRA5_CUDA(cudaGetLastError());
 }
@@ -159,6 +162,7 @@ __global__ void transpose_cast_kernel(const float* __restrict__ in, __nv_bfloat1
 
 void transpose_cast(cudaStream_t st, const float* in, __nv_bfloat16* out, int C, int T, int ldo) {
   dim3 grid((T + 31) / 32, (C + 31) / 32), block(32, 8);
+  LaunchScope scope(st, "transpose_cast", 0.0, 6.0 * C * (double)T);
   transpose_cast_kernel<<<grid, block, 0, st>>>(in, out, C, T, ldo);
   CRA5_CUDA(cudaGetLastError());
 }
@@ -170,6 +174,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
 
 void cast_bf16(cudaStream_t st, const float* in, __nv_bfloat16* out, size_t n) {
   const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+  LaunchScope scope(st, "cast_bf16", 0.0, 6.0 * (double)n);
   cast_bf16_kernel<<<blocks, 256, 0, st>>>(in, out, n);
   CRA5_CUDA(cudaGetLastError());
 }
@@ -192,6 +197,7 @@ __global__ void affine_channels_kernel(const float* __restrict__ in, float* __re
 void affine_channels(cudaStream_t st, const float* in, float* out, const float* a, const float* b, size_t hw, int C,
                      int forward) {
   dim3 grid((unsigned)std::min<size_t>((hw + 1023) / 1024, 64), C);
+  LaunchScope scope(st, "affine_channels", 0.0, 8.0 * C * (double)hw);
   affine_channels_kernel<<<grid, 256, 0, st>>>(in, out, a, b, hw, C, forward);
   CRA5_CUDA(cudaGetLastError());
 }

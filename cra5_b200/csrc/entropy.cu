@@ -80,6 +80,9 @@ void gc_quantize_index(cudaStream_t st, const float* y, const float* sigma, cons
   CRA5_CHECK(levels >= 1 && levels <= 256, ERR_INVALID, "scale table must have 1..256 levels");
   if (n == 0) return;
   const int blocks = (int)std::min<size_t>(((n >> 2) + 255) / 256 + 1, 148 * 8);
+  // algorithmic bytes: read y, sigma, mu (12 B) + write int32 symbol and uint8 index (5 B) per element
+  LaunchScope scope(st, "gc_quantize_index", 0.0,
+                    (double)n * ((y ? 8.0 : 0.0) + (idx ? 5.0 : 0.0) + (sym ? 4.0 : 0.0) + (y_hat ? 4.0 : 0.0)));
   gc_quantize_index_kernel<<<blocks, 256, 0, st>>>(y, sigma, mu, scale_table, levels, bound, sym, idx, y_hat, n);
   CRA5_CUDA(cudaGetLastError());
 }
@@ -98,6 +101,7 @@ __global__ void eb_quantize_kernel(const float* __restrict__ z, const float* __r
 void eb_quantize(cudaStream_t st, const float* z, const float* median, int L, int32_t* sym, float* z_hat, size_t n) {
   if (n == 0) return;
   const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+  LaunchScope scope(st, "eb_quantize", 0.0, (double)n * 12.0);
   eb_quantize_kernel<<<blocks, 256, 0, st>>>(z, median, L, sym, z_hat, n);
   CRA5_CUDA(cudaGetLastError());
 }
@@ -115,6 +119,7 @@ void dequantize(cudaStream_t st, const int32_t* sym, const float* mu, const floa
                 size_t n) {
   if (n == 0) return;
   const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+  LaunchScope scope(st, "dequantize", 0.0, (double)n * 12.0);
   dequantize_kernel<<<blocks, 256, 0, st>>>(sym, mu, median, L, out, n);
   CRA5_CUDA(cudaGetLastError());
 }
@@ -261,12 +266,19 @@ void rans_encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx, bool i
                  uint32_t* scratch, int cap_words, uint32_t* lengths, uint32_t* offsets, uint8_t* payload, int* err) {
   const int n_streams = n_channels * spc;
   if (n_streams == 0) return;
-  rans_encode_kernel<<<(n_streams + 127) / 128, 128, 0, st>>>(sym, idx, index_is_channel ? 1 : 0, cdf, cdf_stride,
-                                                              cdf_len, offset, n_channels, L, spc, scratch, cap_words,
-                                                              lengths, err);
+  {
+    LaunchScope scope(st, "rans_encode", 0.0, (double)n_channels * L * (index_is_channel ? 4.0 : 5.0));
+    rans_encode_kernel<<<(n_streams + 127) / 128, 128, 0, st>>>(sym, idx, index_is_channel ? 1 : 0, cdf, cdf_stride,
+                                                                cdf_len, offset, n_channels, L, spc, scratch,
+                                                                cap_words, lengths, err);
+  }
   CRA5_CUDA(cudaGetLastError());
-  scan_lengths_kernel<<<1, 1024, 0, st>>>(lengths, n_streams, offsets);
+  {
+    LaunchScope scope(st, "scan_lengths", 0.0, 8.0 * n_streams);
+    scan_lengths_kernel<<<1, 1024, 0, st>>>(lengths, n_streams, offsets);
+  }
   CRA5_CUDA(cudaGetLastError());
+  LaunchScope scope(st, "compact_streams", 0.0, 0.0);
   compact_streams_kernel<<<(n_streams * 32 + 255) / 256, 256, 0, st>>>(scratch, cap_words, lengths, offsets, n_streams,
                                                                        payload);
   CRA5_CUDA(cudaGetLastError());
@@ -358,6 +370,7 @@ void rans_decode(cudaStream_t st, const uint8_t* payload, const uint32_t* offset
                  const float* median, float* val_out, int* err) {
   const int n_streams = n_channels * spc;
   if (n_streams == 0) return;
+  LaunchScope scope(st, "rans_decode", 0.0, (double)n_channels * L * (index_is_channel ? 4.0 : 9.0));
   rans_decode_kernel<<<(n_streams + 127) / 128, 128, 0, st>>>(payload, offsets, idx, index_is_channel ? 1 : 0, cdf,
                                                               cdf_stride, cdf_len, offset, n_channels, L, spc, sym_out,
                                                               mu, median, val_out, err);
@@ -365,6 +378,7 @@ void rans_decode(cudaStream_t st, const uint8_t* payload, const uint32_t* offset
 }
 
 void scan_lengths(cudaStream_t st, const uint32_t* lengths, int n, uint32_t* offsets) {
+  LaunchScope scope(st, "scan_lengths", 0.0, 8.0 * n);
   scan_lengths_kernel<<<1, 1024, 0, st>>>(lengths, n, offsets);
   CRA5_CUDA(cudaGetLastError());
 }

@@ -20,6 +20,9 @@ static void launch_one(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMa
   int grid = m_tiles * n_tiles;
   const int sms = device_sm_count();
   if (grid > sms) grid = sms;
+  LaunchScope scope(st, "gemm_tc", 2.0 * shp.M * shp.N * shp.K,
+                    2.0 * ((double)shp.M * shp.K + (double)shp.N * shp.K) +
+                        (double)shp.M * shp.N * ((KIND == EPI_BF16 || KIND == EPI_GELU_BF16 || KIND == EPI_QKV) ? 2.0 : 4.0));
   kern<<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, st>>>(tmA, tmB, shp, epi);
   CRA5_CUDA(cudaGetLastError());
 }
@@ -81,6 +84,7 @@ __global__ void gemm_simt_check_kernel(const __nv_bfloat16* __restrict__ A, int 
 void gemm_simt_check(cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,
                      const float* bias, float* C, int ldc, int M, int N, int K) {
   dim3 block(128), grid((N + 127) / 128, M);
+  LaunchScope scope(st, "gemm_simt_check", 2.0 * M * N * K, 0.0);
   gemm_simt_check_kernel<<<grid, block, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
   CRA5_CUDA(cudaGetLastError());
 }

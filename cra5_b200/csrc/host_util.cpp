@@ -1,6 +1,9 @@
 #include "host_util.h"
 
 #include <mutex>
+#include <map>
+#include <sstream>
+#include <vector>
 
 namespace cra5 {
 
@@ -62,6 +65,93 @@ void require_sm100() {
   CRA5_CUDA(cudaGetDevice(&dev));
   CRA5_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   CRA5_CHECK(major == 10, ERR_CUDA, "cra5_b200 kernels are built for sm_100a only; no such device is current");
+}
+
+// ---------------------------------------------------------------------------------------------- profiler
+namespace {
+struct Rec {
+  std::string name;
+  cudaEvent_t a, b;
+  double flops, bytes;
+};
+struct Prof {
+  bool enabled = false;
+  std::string tag;
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  uint64_t launches = 0;
+};
+Prof& prof() {
+  static thread_local Prof p;
+  return p;
+}
+cudaEvent_t get_event(Prof& p) {
+  if (!p.pool.empty()) {
+    cudaEvent_t e = p.pool.back();
+    p.pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+void count_launch(int n) { prof().launches += (uint64_t)n; }
+uint64_t launch_count() { return prof().launches; }
+void prof_enable(bool on) { prof().enabled = on; }
+bool prof_enabled() { return prof().enabled; }
+void prof_set_tag(const char* tag) { prof().tag = tag ? tag : ""; }
+void prof_reset() {
+  Prof& p = prof();
+  for (auto& r : p.recs) {
+    p.pool.push_back(r.a);
+    p.pool.push_back(r.b);
+  }
+  p.recs.clear();
+}
+
+LaunchScope::LaunchScope(cudaStream_t st, const char* kernel, double flops, double bytes) : st_(st), slot_(-1) {
+  Prof& p = prof();
+  p.launches += 1;
+  if (!p.enabled) return;
+  Rec r;
+  r.name = p.tag.empty() ? std::string(kernel) : std::string(kernel) + ":" + p.tag;
+  r.a = get_event(p);
+  r.b = get_event(p);
+  r.flops = flops;
+  r.bytes = bytes;
+  cudaEventRecord(r.a, st);
+  slot_ = (int)p.recs.size();
+  p.recs.push_back(r);
+}
+LaunchScope::~LaunchScope() {
+  if (slot_ >= 0) cudaEventRecord(prof().recs[slot_].b, st_);
+}
+
+std::string prof_report_json() {
+  Prof& p = prof();
+  cudaDeviceSynchronize();
+  struct Agg { uint64_t n = 0; double ms = 0, flops = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : p.recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    Agg& a = agg[r.name];
+    a.n += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+  }
+  std::ostringstream os;
+  os.precision(9);
+  os << "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    if (!first) os << ", ";
+    first = false;
+    os << "\"" << kv.first << "\": {\"launches\": " << kv.second.n << ", \"ms\": " << kv.second.ms
+       << ", \"flops\": " << kv.second.flops << ", \"bytes\": " << kv.second.bytes << "}";
+  }
+  os << "}";
+  return os.str();
 }
 
 }  // namespace cra5

@@ -50,6 +50,27 @@ inline CUtensorMap make_tmap_bf16_2d(const void* base, uint64_t inner, uint64_t 
 }
 
 int device_sm_count();
+
+// ---- launch accounting + optional per-kernel CUDA-event profiler (bench.py's roofline numbers come from here)
+void count_launch(int n = 1);
+uint64_t launch_count();
+void prof_enable(bool on);
+bool prof_enabled();
+void prof_reset();
+void prof_set_tag(const char* tag);  // call-site label appended to the kernel name ("qkv", "fc1", ...)
+std::string prof_report_json();      // synchronises, then {"name": {"launches": n, "ms": t, "flops": f, "bytes": b}, ...}
+
+// RAII: counts one launch and, when profiling is on, brackets it with CUDA events on its stream
+struct LaunchScope {
+  LaunchScope(cudaStream_t st, const char* kernel, double flops, double bytes);
+  ~LaunchScope();
+  cudaStream_t st_;
+  int slot_;
+};
+struct TagScope {
+  explicit TagScope(const char* tag) { prof_set_tag(tag); }
+  ~TagScope() { prof_set_tag(""); }
+};
 void require_sm100();
 
 }  // namespace cra5

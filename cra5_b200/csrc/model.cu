@@ -214,6 +214,7 @@ void Model::run_block(cudaStream_t st, const BlockWeights& w, const TrunkBuffers
     e.q = tb.q; e.k = tb.k; e.vt = tb.vt;
     e.D = D; e.hd = hd_; e.rows_total = rows;
     e.qscale = 1.0f / sqrtf((float)hd_);
+    TagScope tag_("qkv");
     gemm_plain(st, EPI_QKV, tb.a, D, w.qkv_w, D, rows, 3 * D, D, e);
   }
   if (hd_ == 64)
@@ -224,6 +225,7 @@ void Model::run_block(cudaStream_t st, const BlockWeights& w, const TrunkBuffers
     EpiParams e{};
     e.bias = w.proj_b;
     e.resid = x_in; e.out_f32 = x_out; e.ldo = D; e.wm = wm;
+    TagScope tag_("proj");
     gemm_plain(st, EPI_RESID, tb.o, D, w.proj_w, D, rows, D, D, e);
   }
   layernorm_bf16(st, x_out, w.ln2_g, w.ln2_b, cfg_.ln_eps, tb.a, T_, D, WinMap{});
@@ -231,6 +233,7 @@ void Model::run_block(cudaStream_t st, const BlockWeights& w, const TrunkBuffers
     EpiParams e{};
     e.bias = w.fc1_b;
     e.out_bf16 = tb.h; e.ldo = mlp * D;
+    TagScope tag_("fc1");
     gemm_plain(st, EPI_GELU_BF16, tb.a, D, w.fc1_w, D, T_, mlp * D, D, e);
   }
   {
@@ -238,6 +241,7 @@ void Model::run_block(cudaStream_t st, const BlockWeights& w, const TrunkBuffers
     e.bias = w.fc2_b;
     e.resid = x_out; e.out_f32 = x_out; e.ldo = D;
     e.out_bf16 = cat_out; e.bf16_col0 = cat_col0; e.ld_bf16 = cat_ld;
+    TagScope tag_("fc2");
     gemm_plain(st, EPI_RESID, tb.h, mlp * D, w.fc2_w, mlp * D, T_, D, mlp * D, e);
   }
 }
@@ -275,6 +279,7 @@ void Model::encode_to_latent(const float* x, float* y, const float* mean, const 
     e.add = (const float*)need("g_a.pos_embed", CRA5_DT_F32, (int64_t)T * D);
     e.lda = D;
     e.out_f32 = main_.x; e.ldo = D;
+    TagScope tag_("patch_embed");
     launch_gemm(st, bn, EPI_F32, tmA, tmB, shp, e);
   }
   taps_["tokens"] = TensorRef{main_.x, CRA5_DT_F32, (int64_t)T * D};
@@ -294,6 +299,7 @@ void Model::encode_to_latent(const float* x, float* y, const float* mean, const 
     EpiParams e{};
     e.bias = (const float*)need("quant_conv.bias", CRA5_DT_F32, lat);
     e.out_f32 = y; e.ldo = T;
+    TagScope tag_("quant_conv");
     gemm_plain(st, EPI_T_F32, cat_, 2 * D, (const __nv_bfloat16*)need("quant_conv.weight", CRA5_DT_BF16, (int64_t)lat * 2 * D),
                2 * D, T, lat, 2 * D, e);
   }
@@ -314,6 +320,7 @@ void Model::run_h_a(cudaStream_t st, const float* y) {
     e.add = (const float*)need("h_a.pos_embed", CRA5_DT_F32, (int64_t)Th * Dh);
     e.lda = Dh;
     e.out_f32 = hyper_.x; e.ldo = Dh;
+    TagScope tag_("h_a.patch_embed");
     gemm_plain(st, EPI_F32, ah_, Kc, (const __nv_bfloat16*)need("h_a.patch_embed.proj.weight", CRA5_DT_BF16, (int64_t)Dh * Kc),
                Kc, Th, Dh, Kc, e);
   }
@@ -325,6 +332,7 @@ void Model::run_h_a(cudaStream_t st, const float* y) {
     EpiParams e{};
     e.bias = (const float*)need("h_a.quan_mlp.fc1.bias", CRA5_DT_F32, hidden);
     e.out_bf16 = hyper_.h; e.ldo = hidden;
+    TagScope tag_("h_a.quan_fc1");
     gemm_plain(st, EPI_GELU_BF16, hyper_.a, Dh, (const __nv_bfloat16*)need("h_a.quan_mlp.fc1.weight", CRA5_DT_BF16, (int64_t)hidden * Dh),
                Dh, Th, hidden, Dh, e);
   }
@@ -332,6 +340,7 @@ void Model::run_h_a(cudaStream_t st, const float* y) {
     EpiParams e{};
     e.bias = (const float*)need("h_a.quan_mlp.fc2.bias", CRA5_DT_F32, zc);
     e.out_f32 = z_; e.ldo = Th;
+    TagScope tag_("h_a.quan_fc2");
     gemm_plain(st, EPI_T_F32, hyper_.h, hidden, (const __nv_bfloat16*)need("h_a.quan_mlp.fc2.weight", CRA5_DT_BF16, (int64_t)zc * hidden),
                hidden, Th, zc, hidden, e);
   }
@@ -349,6 +358,7 @@ void Model::run_h_s(cudaStream_t st, const float* z_hat) {
     EpiParams e{};
     e.bias = (const float*)need("h_s.post_quan_mlp.fc1.bias", CRA5_DT_F32, hidden);
     e.out_bf16 = hyper_.h; e.ldo = hidden;
+    TagScope tag_("h_s.post_fc1");
     gemm_plain(st, EPI_GELU_BF16, ztok_, zc, (const __nv_bfloat16*)need("h_s.post_quan_mlp.fc1.weight", CRA5_DT_BF16, (int64_t)hidden * zc),
                zc, Th, hidden, zc, e);
   }
@@ -356,6 +366,7 @@ void Model::run_h_s(cudaStream_t st, const float* z_hat) {
     EpiParams e{};
     e.bias = (const float*)need("h_s.post_quan_mlp.fc2.bias", CRA5_DT_F32, Dh);
     e.out_f32 = hyper_.x; e.ldo = Dh;
+    TagScope tag_("h_s.post_fc2");
     gemm_plain(st, EPI_F32, hyper_.h, hidden, (const __nv_bfloat16*)need("h_s.post_quan_mlp.fc2.weight", CRA5_DT_BF16, (int64_t)Dh * hidden),
                hidden, Th, Dh, hidden, e);
   }
@@ -369,6 +380,7 @@ void Model::run_h_s(cudaStream_t st, const float* z_hat) {
     EpiParams e{};
     e.out_f32 = params_; e.ldo = T;
     e.ps_P1 = c.hyper_patch_h; e.ps_P2 = c.hyper_patch_w; e.ps_C = 2 * lat; e.ps_Wh = Wh;
+    TagScope tag_("h_s.final");
     gemm_plain(st, EPI_PIXSHUF, hyper_.a, Dh, (const __nv_bfloat16*)need("h_s.final.weight", CRA5_DT_BF16, (int64_t)Nf * Dh), Dh, Th,
                Nf, Dh, e);
   }
@@ -452,6 +464,7 @@ void Model::latent_to_reconstruction(const float* y_hat, float* x_hat, cudaStrea
     EpiParams e{};
     e.bias = (const float*)need("post_quant_conv.bias", CRA5_DT_F32, D);
     e.out_f32 = main_.x; e.ldo = D;
+    TagScope tag_("post_quant_conv");
     gemm_plain(st, EPI_F32, ytok_, lat, (const __nv_bfloat16*)need("post_quant_conv.weight", CRA5_DT_BF16, (int64_t)D * lat), lat, T,
                D, lat, e);
   }
@@ -473,6 +486,7 @@ void Model::latent_to_reconstruction(const float* y_hat, float* x_hat, cudaStrea
     e.ct_CS = CS; e.ct_pw = c.patch_w; e.ct_sh = c.stride_h; e.ct_Wp = Wg; e.ct_Himg = c.img_h; e.ct_Wimg = c.img_w;
     if (nA > 0) {
       e.ct_r0 = nB;
+      TagScope tag_("convT_A");
       gemm_plain(st, EPI_CONVT, main_.a, D, (const __nv_bfloat16*)need("g_s.final.A", CRA5_DT_BF16, (int64_t)nA * CS * D), D, T,
                  nA * CS, D, e);
     }
@@ -486,6 +500,7 @@ void Model::latent_to_reconstruction(const float* y_hat, float* x_hat, cudaStrea
       CUtensorMap tmB = make_tmap_bf16_2d(Wb, (uint64_t)K2, (uint64_t)N2, (uint64_t)K2 * 2, GEMM_BK, bn);
       GemmShape shp{};
       shp.M = M2; shp.N = N2; shp.K = K2; shp.a_mode = A_CONCAT; shp.cc_D = D; shp.cc_shift = Wg;
+      TagScope tag_("convT_B");
       launch_gemm(st, bn, EPI_CONVT, tmA, tmB, shp, e);
     }
   } else {
@@ -494,6 +509,7 @@ void Model::latent_to_reconstruction(const float* y_hat, float* x_hat, cudaStrea
     EpiParams e{};
     e.out_f32 = x_hat; e.ldo = (Hg * c.patch_h) * (Wg * c.patch_w);
     e.ps_P1 = c.patch_h; e.ps_P2 = c.patch_w; e.ps_C = c.in_chans; e.ps_Wh = Wg;
+    TagScope tag_("linear_head");
     gemm_plain(st, EPI_PIXSHUF, main_.a, D, (const __nv_bfloat16*)need("g_s.final.weight", CRA5_DT_BF16, (int64_t)Nf * D), D, T, Nf,
                D, e);
   }

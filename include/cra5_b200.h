@@ -157,6 +157,13 @@ CRA5_API int cra5_model_tap(cra5_model* m, const char* name, const void** dev_pt
 
 CRA5_API int cra5_model_tap_read(cra5_model* m, const char* name, void* dst_dev, uint64_t dst_bytes, void* stream);
 
+/* Measurement hooks (bench.py): number of kernels this library has launched on the calling thread; an optional
+ * CUDA-event profiler that brackets every launch on its own stream and reports, per kernel and call site, launches,
+ * summed device milliseconds and algorithmic flops / bytes as a JSON object. */
+CRA5_API int cra5_launch_count(uint64_t* count);
+CRA5_API int cra5_profile_enable(int on);
+CRA5_API int cra5_profile_report(char* buf, uint64_t cap, uint64_t* needed);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Entropy-stage operators on caller-provided device buffers (parity tests drive these directly)
  * ---------------------------------------------------------------------------------------------------------- */
