@@ -317,7 +317,7 @@ def run_b200(args):
                                    f"vaeformer quality={cfg.in_chans} (BASELINE.json configs[2]), one frame per step per GPU",
                        "l2": "inputs larger than L2: two alternating 1.1 GB frames, every kernel's working set is re-streamed",
                        "weights": "random init of the named architecture (seed 1234), CDF tables from update(force=True)",
-                       "bytes_per_frame": nbytes, "coder": "CR5B chunk-parallel rANS, 8 sub-streams per y channel"},
+                       "bytes_per_frame": nbytes, "coder": "CR5B chunk-parallel rANS, 16 sub-streams per y channel, 4 per z channel"},
             "gb_era5_per_s": fps * frame_bytes / 1e9,
             "e2e": e2e, "gpu_launches": int(lc1.value - lc0.value), "clocks": clock_info,
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,

@@ -75,6 +75,16 @@ int cra5_op_attention(const void* Q, const void* K, const void* Vt, void* out, i
   });
 }
 
+int cra5_op_attention_generic(const void* Q, const void* K, const void* Vt, void* out, int ldo, int heads, int head_dim,
+                              int rows_total, int seg_len, void* stream) {
+  return guarded([&] {
+    require_sm100();
+    attention_simt(static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(Q),
+                   static_cast<const __nv_bfloat16*>(K), static_cast<const __nv_bfloat16*>(Vt),
+                   static_cast<__nv_bfloat16*>(out), ldo, heads, head_dim, rows_total, seg_len);
+  });
+}
+
 int cra5_pmf_to_quantized_cdf(const float* pmf, int n, int precision, uint32_t* cdf_out) {
   return guarded([&] {
     CRA5_CHECK(pmf != nullptr && cdf_out != nullptr, ERR_INVALID, "null argument");

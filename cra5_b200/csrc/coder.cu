@@ -20,6 +20,7 @@ RansCoder::RansCoder(size_t max_symbols, int max_channels)
   CRA5_CUDA(cudaMallocHost(&host_meta_, ((size_t)max_streams_ + 4) * 4));
   host_stage_cap_ = payload_cap_ + (size_t)max_streams_ * 4;
   CRA5_CUDA(cudaMallocHost(&host_stage_, host_stage_cap_));
+  CRA5_CUDA(cudaMalloc(&lut_, (size_t)256 * 257 * 2));
 }
 
 RansCoder::~RansCoder() {
@@ -30,6 +31,7 @@ RansCoder::~RansCoder() {
   cudaFree(err_);
   cudaFreeHost(host_meta_);
   cudaFreeHost(host_stage_);
+  cudaFree(lut_);
 }
 
 static void put_u32(uint8_t* p, uint32_t v) { memcpy(p, &v, 4); }
@@ -114,8 +116,21 @@ void RansCoder::decode(cudaStream_t st, const uint8_t* bytes, size_t len, const 
   CRA5_CUDA(cudaMemcpyAsync(lengths_, host_stage_, (size_t)ns * 4, cudaMemcpyHostToDevice, st));
   CRA5_CUDA(cudaMemcpyAsync(payload_, host_stage_ + (size_t)ns * 4, total, cudaMemcpyHostToDevice, st));
   scan_lengths(st, lengths_, (int)ns, offsets_);
-  rans_decode(st, payload_, offsets_, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, n_channels, L,
-              (int)spc, sym_out, mu, median, val_out, err_);
+  // wide tables (GaussianConditional: up to 3133 entries per row) get a coarse inverse table; the per-channel
+  // EntropyBottleneck rows are a few dozen entries and are searched directly
+  const uint16_t* lut = nullptr;
+  int lut_rows = 0;
+  if (idx != nullptr && tab.rows <= 256 && tab.cols > 64) {
+    if (lut_for_ != tab.cdf || lut_rows_ != tab.rows) {
+      build_decode_lut(st, tab.cdf, tab.cols, tab.length, tab.rows, lut_);
+      lut_for_ = tab.cdf;
+      lut_rows_ = tab.rows;
+    }
+    lut = lut_;
+    lut_rows = tab.rows;
+  }
+  rans_decode(st, payload_, offsets_, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, lut, lut_rows,
+              n_channels, L, (int)spc, sym_out, mu, median, val_out, err_);
   CRA5_CUDA(cudaMemcpyAsync(host_meta_, err_, 4, cudaMemcpyDeviceToHost, st));
   CRA5_CUDA(cudaStreamSynchronize(st));
   if (host_meta_[0] != 0) {

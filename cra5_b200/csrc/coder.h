@@ -33,6 +33,7 @@ class RansCoder {
   size_t encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx, const CdfTable& tab, int n_channels, int L,
                 int spc, uint8_t* host_out, size_t host_cap);
   // container in host memory -> symbols and/or dequantised values on the device
+  void invalidate_lut() { lut_for_ = nullptr; lut_rows_ = 0; }
   void decode(cudaStream_t st, const uint8_t* bytes, size_t len, const uint8_t* idx, const CdfTable& tab,
               int n_channels, int L, int32_t* sym_out, const float* mu, const float* median, float* val_out);
 
@@ -45,6 +46,9 @@ class RansCoder {
   int* err_ = nullptr;
   uint32_t* host_meta_ = nullptr;  // pinned: lengths + total + err
   uint8_t* host_stage_ = nullptr;  // pinned upload staging for decode
+  uint16_t* lut_ = nullptr;        // coarse inverse-CDF table of the last GaussianConditional-style table seen
+  const int32_t* lut_for_ = nullptr;
+  int lut_rows_ = 0;
   size_t host_stage_cap_ = 0;
 };
 

@@ -129,6 +129,7 @@ constexpr uint32_t RANS_PRECISION = 16;      // rans_interface.cpp:49
 constexpr uint32_t RANS_BYPASS_BITS = 4;     // rans_interface.cpp:51
 constexpr int32_t RANS_BYPASS_MAX = 15;      // rans_interface.cpp:52
 constexpr uint64_t RANS_L = 1ull << 31;      // rans64.h
+constexpr int RANS_LUT = 257;                // coarse inverse-CDF entries per row (cum >> 8, plus the end sentinel)
 
 struct RansEnc {
   uint64_t x;
@@ -139,11 +140,15 @@ struct RansEnc {
     if (ptr > floor_) { --ptr; *ptr = (uint32_t)x; } else overflow = true;
     x >>= 32;
   }
-  __device__ __forceinline__ void put(uint32_t start, uint32_t freq) {
-    const uint64_t x_max = ((RANS_L >> RANS_PRECISION) << 32) * (uint64_t)freq;
+  // x = C(s, x) = floor(x / freq) * 2^16 + x mod freq + start. The 64-bit quotient is taken from a double-precision
+  // estimate (x < 2^63, quotient < 2^47, so the estimate is within 1 of the truth) and corrected exactly.
+  __device__ __forceinline__ void put(uint32_t start, uint32_t freq, double rcp) {
+    const uint64_t x_max = (uint64_t)freq << (31 - RANS_PRECISION + 32);  // ((L >> 16) << 32) * freq
     if (x >= x_max) emit();
-    const uint64_t q = x / freq;
-    x = (q << RANS_PRECISION) + (x - q * freq) + start;
+    uint64_t q = __double2ull_rz(__ull2double_rn(x) * rcp);
+    int64_t r = (int64_t)(x - q * freq);
+    if (r < 0) { --q; r += freq; } else if (r >= (int64_t)freq) { ++q; r -= freq; }
+    x = (q << RANS_PRECISION) + (uint64_t)r + start;
   }
   __device__ __forceinline__ void put_bits(uint32_t val, uint32_t nbits) {  // rans_interface.cpp:69-87
     const uint64_t x_max = ((RANS_L >> 16) << 32) * (uint64_t)(1u << (16 - nbits));
@@ -152,10 +157,14 @@ struct RansEnc {
   }
 };
 
+constexpr int RANS_BATCH = 8;      // symbols gathered (independent loads) before the serial state updates
+constexpr int RANS_THREADS = 32;   // one warp per CTA: the chains are latency bound, spread them over all SMs
+
 // thread = sub-stream. Symbols are consumed last-to-first (the reference buffers all symbols and encodes the list in
 // reverse, rans_interface.cpp:183-193), words are written backwards into the stream's private scratch window.
-// chan_index < 0: per-symbol indexes from `idx`; otherwise index == channel (EntropyBottleneck).
-__global__ void __launch_bounds__(128)
+// Per batch: phase A gathers (start, freq, 1/freq, raw) for RANS_BATCH symbols with independent loads; phase B runs
+// the serial state recurrence out of registers.
+__global__ void __launch_bounds__(RANS_THREADS)
 rans_encode_kernel(const int32_t* __restrict__ sym, const uint8_t* __restrict__ idx, int index_is_channel,
                    const int32_t* __restrict__ cdf, int cdf_stride, const int32_t* __restrict__ cdf_len,
                    const int32_t* __restrict__ offset, int n_channels, int L, int spc, uint32_t* __restrict__ scratch,
@@ -171,35 +180,58 @@ rans_encode_kernel(const int32_t* __restrict__ sym, const uint8_t* __restrict__ 
   e.floor_ = top - cap_words + 2;  // keep room for the 2-word flush
   e.overflow = false;
   const size_t base = (size_t)c * L + k;
-  for (int i = count - 1; i >= 0; --i) {
-    const size_t pos = base + (size_t)i * spc;
-    const int ci = index_is_channel ? c : (int)idx[pos];
-    const int32_t* row = cdf + (size_t)ci * cdf_stride;
-    const int32_t max_value = cdf_len[ci] - 2;
-    int32_t value = sym[pos] - offset[ci];
-    uint32_t raw = 0;
-    bool bypass = false;
-    if (value < 0) {
-      raw = (uint32_t)(-2 * value - 1);
-      value = max_value;
-      bypass = true;
-    } else if (value >= max_value) {
-      raw = (uint32_t)(2 * (value - max_value));
-      value = max_value;
-      bypass = true;
+  for (int i0 = count; i0 > 0; i0 -= RANS_BATCH) {
+    // phase A: three rounds of independent, branch-free loads (index clamped, results masked in phase B)
+    size_t pos[RANS_BATCH];
+    int32_t sy[RANS_BATCH], ci[RANS_BATCH], off[RANS_BATCH], mxv[RANS_BATCH], val[RANS_BATCH];
+    uint32_t start[RANS_BATCH], freq[RANS_BATCH], raw[RANS_BATCH];
+    double rcp[RANS_BATCH];
+#pragma unroll
+    for (int b = 0; b < RANS_BATCH; ++b) {
+      const int i = max(i0 - 1 - b, 0);
+      pos[b] = base + (size_t)i * spc;
+      sy[b] = sym[pos[b]];
+      ci[b] = index_is_channel ? c : (int)idx[pos[b]];
     }
-    if (bypass) {
-      int32_t nb = 0;
-      while (nb < 8 && (raw >> (nb * RANS_BYPASS_BITS)) != 0) ++nb;
-      for (int32_t j = nb - 1; j >= 0; --j) e.put_bits((raw >> (j * RANS_BYPASS_BITS)) & RANS_BYPASS_MAX, RANS_BYPASS_BITS);
-      // count is sent as [15]*q then (nb - 15q); nb <= 8 for 32-bit raw values so q == 0, kept general
-      const int32_t q = nb / RANS_BYPASS_MAX;
-      e.put_bits((uint32_t)(nb - q * RANS_BYPASS_MAX), RANS_BYPASS_BITS);
-      for (int32_t j = 0; j < q; ++j) e.put_bits(RANS_BYPASS_MAX, RANS_BYPASS_BITS);
+#pragma unroll
+    for (int b = 0; b < RANS_BATCH; ++b) {
+      off[b] = offset[ci[b]];
+      mxv[b] = cdf_len[ci[b]] - 2;
     }
-    const uint32_t start = (uint32_t)row[value];
-    const uint32_t freq = (uint32_t)row[value + 1] - start;
-    e.put(start, freq);
+#pragma unroll
+    for (int b = 0; b < RANS_BATCH; ++b) {
+      const int32_t v = sy[b] - off[b];
+      const bool neg = v < 0, big = v >= mxv[b];
+      raw[b] = neg ? (uint32_t)(-2 * v - 1) : (big ? (uint32_t)(2 * (v - mxv[b])) : 0u);
+      val[b] = (neg || big) ? mxv[b] : v;   // == max_value <=> bypass (value == max_value is the sentinel bin)
+      const int32_t* row = cdf + (size_t)ci[b] * cdf_stride + val[b];
+      start[b] = (uint32_t)row[0];
+      freq[b] = (uint32_t)row[1] - start[b];
+    }
+#pragma unroll
+    for (int b = 0; b < RANS_BATCH; ++b) {
+      // 1/freq to double precision without the slow-path call: float seed + two Newton steps
+      const double f = (double)freq[b];
+      double r = (double)__frcp_rn((float)freq[b]);
+      r = r * __fma_rn(-f, r, 2.0);
+      r = r * __fma_rn(-f, r, 2.0);
+      rcp[b] = r;
+    }
+    // phase B: the serial state recurrence, out of registers
+#pragma unroll
+    for (int b = 0; b < RANS_BATCH; ++b) {
+      if (i0 - 1 - b >= 0) {
+        if (val[b] == mxv[b]) {
+          int32_t nb = 0;
+          while (nb < 8 && (raw[b] >> (nb * RANS_BYPASS_BITS)) != 0) ++nb;
+          for (int32_t j = nb - 1; j >= 0; --j)
+            e.put_bits((raw[b] >> (j * RANS_BYPASS_BITS)) & RANS_BYPASS_MAX, RANS_BYPASS_BITS);
+          // the count is sent as [15]*q then (nb - 15q); nb <= 8 for 32-bit raw values, so q == 0
+          e.put_bits((uint32_t)nb, RANS_BYPASS_BITS);
+        }
+        e.put(start[b], freq[b], rcp[b]);
+      }
+    }
   }
   // flush: stream begins with low32(x), high32(x)
   e.ptr -= 2;
@@ -268,7 +300,7 @@ void rans_encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx, bool i
   if (n_streams == 0) return;
   {
     LaunchScope scope(st, "rans_encode", 0.0, (double)n_channels * L * (index_is_channel ? 4.0 : 5.0));
-    rans_encode_kernel<<<(n_streams + 127) / 128, 128, 0, st>>>(sym, idx, index_is_channel ? 1 : 0, cdf, cdf_stride,
+    rans_encode_kernel<<<(n_streams + RANS_THREADS - 1) / RANS_THREADS, RANS_THREADS, 0, st>>>(sym, idx, index_is_channel ? 1 : 0, cdf, cdf_stride,
                                                                 cdf_len, offset, n_channels, L, spc, scratch,
                                                                 cap_words, lengths, err);
   }
@@ -303,13 +335,52 @@ struct RansDec {
   }
 };
 
+// Coarse inverse-CDF table: lut[row][b] = last v with cdf[row][v] <= 256*b, b = 0..256 (one thread per entry).
+__global__ void build_decode_lut_kernel(const int32_t* __restrict__ cdf, int cdf_stride,
+                                        const int32_t* __restrict__ cdf_len, int rows, uint16_t* __restrict__ lut) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * RANS_LUT) return;
+  const int r = e / RANS_LUT, b = e - r * RANS_LUT;
+  const int32_t* row = cdf + (size_t)r * cdf_stride;
+  const int32_t n_entries = cdf_len[r];
+  const uint32_t target = (uint32_t)b << 8;
+  int lo = 0, hi = n_entries - 1;  // row[0] = 0 <= target; row[n_entries-1] = 65536
+  if (target >= 65536u) {
+    lo = n_entries - 2;
+  } else {
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if ((uint32_t)row[mid] <= target) lo = mid; else hi = mid;
+    }
+  }
+  lut[e] = (uint16_t)lo;
+}
+
+void build_decode_lut(cudaStream_t st, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len, int rows,
+                      uint16_t* lut) {
+  LaunchScope scope(st, "build_decode_lut", 0.0, 0.0);
+  build_decode_lut_kernel<<<(rows * RANS_LUT + 255) / 256, 256, 0, st>>>(cdf, cdf_stride, cdf_len, rows, lut);
+  CRA5_CUDA(cudaGetLastError());
+}
+
 // thread = sub-stream. Writes int32 symbols and/or the dequantised value sym + mean.
-__global__ void __launch_bounds__(128)
+// The reference finds the symbol by a linear scan of the CDF row (rans_interface.cpp:246-250); here the coarse
+// inverse table (staged in shared memory when it fits) narrows the range to a few entries and a short binary search
+// finishes -- same result, ~3 dependent loads instead of up to 3133.
+__global__ void __launch_bounds__(RANS_THREADS)
 rans_decode_kernel(const uint8_t* __restrict__ payload, const uint32_t* __restrict__ offsets,
                    const uint8_t* __restrict__ idx, int index_is_channel, const int32_t* __restrict__ cdf,
                    int cdf_stride, const int32_t* __restrict__ cdf_len, const int32_t* __restrict__ offset,
-                   int n_channels, int L, int spc, int32_t* __restrict__ sym_out, const float* __restrict__ mu,
-                   const float* __restrict__ median, float* __restrict__ val_out, int* __restrict__ err) {
+                   const uint16_t* __restrict__ lut_g, int lut_rows, int n_channels, int L, int spc,
+                   int32_t* __restrict__ sym_out, const float* __restrict__ mu, const float* __restrict__ median,
+                   float* __restrict__ val_out, int* __restrict__ err) {
+  extern __shared__ uint16_t lut_s[];
+  const uint16_t* lut = lut_g;
+  if (lut_g != nullptr && lut_rows > 0) {  // lut_rows > 0: stage the table in shared memory
+    for (int e = threadIdx.x; e < lut_rows * RANS_LUT; e += blockDim.x) lut_s[e] = lut_g[e];
+    __syncthreads();
+    lut = lut_s;
+  }
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_channels * spc) return;
   const int c = s / spc, k = s - c * spc;
@@ -323,57 +394,91 @@ rans_decode_kernel(const uint8_t* __restrict__ payload, const uint32_t* __restri
     d.x = (uint64_t)lo | ((uint64_t)hi << 32);
   }
   const size_t base = (size_t)c * L + k;
-  for (int i = 0; i < count; ++i) {
-    const size_t pos = base + (size_t)i * spc;
-    const int ci = index_is_channel ? c : (int)idx[pos];
-    const int32_t* row = cdf + (size_t)ci * cdf_stride;
-    const int32_t n_entries = cdf_len[ci];
-    const int32_t max_value = n_entries - 2;
-    const uint32_t cum = (uint32_t)(d.x & 0xffffu);
-    // last v in [0, n_entries-1) with row[v] <= cum  (the reference searches linearly, rans_interface.cpp:246-250)
-    int lo = 0, hi = n_entries - 1;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if ((uint32_t)row[mid] <= cum) lo = mid; else hi = mid;
+  for (int i0 = 0; i0 < count; i0 += RANS_BATCH) {
+    int ci[RANS_BATCH];
+    float mean[RANS_BATCH];
+    int32_t outv[RANS_BATCH];
+#pragma unroll
+    for (int b = 0; b < RANS_BATCH; ++b) {  // independent loads first
+      const int i = min(i0 + b, count - 1);
+      const size_t pos = base + (size_t)i * spc;
+      ci[b] = index_is_channel ? c : (int)idx[pos];
+      mean[b] = (val_out == nullptr) ? 0.f : ((mu != nullptr) ? mu[pos] : median[c]);
     }
-    const uint32_t start = (uint32_t)row[lo];
-    const uint32_t freq = (uint32_t)row[lo + 1] - start;
-    d.x = (uint64_t)freq * (d.x >> RANS_PRECISION) + cum - start;
-    if (d.x < RANS_L) d.x = (d.x << 32) | d.next();
-    int32_t value = lo;
-    if (value == max_value) {  // bypass, rans_interface.cpp:256-278
-      int32_t val = (int32_t)d.get_bits(RANS_BYPASS_BITS);
-      int32_t nb = val;
-      while (val == RANS_BYPASS_MAX && !d.underflow) {
-        val = (int32_t)d.get_bits(RANS_BYPASS_BITS);
-        nb += val;
+#pragma unroll
+    for (int b = 0; b < RANS_BATCH; ++b) {
+      outv[b] = 0;
+      if (i0 + b >= count) break;
+      const int32_t* row = cdf + (size_t)ci[b] * cdf_stride;
+      const int32_t n_entries = cdf_len[ci[b]];
+      const int32_t max_value = n_entries - 2;
+      const uint32_t cum = (uint32_t)(d.x & 0xffffu);
+      // last v in [0, n_entries-1) with row[v] <= cum
+      int lo, hi;
+      if (lut != nullptr) {
+        const uint16_t* lr = lut + (size_t)ci[b] * RANS_LUT + (cum >> 8);
+        lo = lr[0];
+        hi = lr[1];
+      } else {
+        lo = 0;
+        hi = n_entries - 2;
       }
-      uint32_t raw = 0;
-      for (int32_t j = 0; j < nb; ++j) {
-        val = (int32_t)d.get_bits(RANS_BYPASS_BITS);
-        if (j < 8) raw |= (uint32_t)val << (j * RANS_BYPASS_BITS);
-        if (d.underflow) break;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((uint32_t)row[mid] <= cum) lo = mid; else hi = mid - 1;
       }
-      value = (int32_t)(raw >> 1);
-      if (raw & 1u) value = -value - 1; else value += max_value;
+      const uint32_t start = (uint32_t)row[lo];
+      const uint32_t freq = (uint32_t)row[lo + 1] - start;
+      d.x = (uint64_t)freq * (d.x >> RANS_PRECISION) + cum - start;
+      if (d.x < RANS_L) d.x = (d.x << 32) | d.next();
+      int32_t value = lo;
+      if (value == max_value) {  // bypass, rans_interface.cpp:256-278
+        int32_t val = (int32_t)d.get_bits(RANS_BYPASS_BITS);
+        int32_t nb = val;
+        while (val == RANS_BYPASS_MAX && !d.underflow) {
+          val = (int32_t)d.get_bits(RANS_BYPASS_BITS);
+          nb += val;
+        }
+        uint32_t raw = 0;
+        for (int32_t j = 0; j < nb; ++j) {
+          val = (int32_t)d.get_bits(RANS_BYPASS_BITS);
+          if (j < 8) raw |= (uint32_t)val << (j * RANS_BYPASS_BITS);
+          if (d.underflow) break;
+        }
+        value = (int32_t)(raw >> 1);
+        if (raw & 1u) value = -value - 1; else value += max_value;
+      }
+      outv[b] = value + offset[ci[b]];
     }
-    const int32_t out = value + offset[ci];
-    if (sym_out != nullptr) sym_out[pos] = out;
-    if (val_out != nullptr) val_out[pos] = __fadd_rn((float)out, (mu != nullptr) ? mu[pos] : median[c]);
+#pragma unroll
+    for (int b = 0; b < RANS_BATCH; ++b) {
+      const int i = i0 + b;
+      if (i < count) {
+        const size_t pos = base + (size_t)i * spc;
+        if (sym_out != nullptr) sym_out[pos] = outv[b];
+        if (val_out != nullptr) val_out[pos] = __fadd_rn((float)outv[b], mean[b]);
+      }
+    }
   }
   if (d.underflow) atomicExch(err, 2);
 }
 
 void rans_decode(cudaStream_t st, const uint8_t* payload, const uint32_t* offsets, const uint8_t* idx,
                  bool index_is_channel, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len,
-                 const int32_t* offset, int n_channels, int L, int spc, int32_t* sym_out, const float* mu,
-                 const float* median, float* val_out, int* err) {
+                 const int32_t* offset, const uint16_t* lut, int lut_rows, int n_channels, int L, int spc,
+                 int32_t* sym_out, const float* mu, const float* median, float* val_out, int* err) {
   const int n_streams = n_channels * spc;
   if (n_streams == 0) return;
+  size_t smem = 0;
+  int stage_rows = 0;
+  if (lut != nullptr && (size_t)lut_rows * RANS_LUT * 2 <= 48 * 1024) {
+    stage_rows = lut_rows;
+    smem = (size_t)lut_rows * RANS_LUT * 2;
+  }
   LaunchScope scope(st, "rans_decode", 0.0, (double)n_channels * L * (index_is_channel ? 4.0 : 9.0));
-  rans_decode_kernel<<<(n_streams + 127) / 128, 128, 0, st>>>(payload, offsets, idx, index_is_channel ? 1 : 0, cdf,
-                                                              cdf_stride, cdf_len, offset, n_channels, L, spc, sym_out,
-                                                              mu, median, val_out, err);
+  rans_decode_kernel<<<(n_streams + RANS_THREADS - 1) / RANS_THREADS, RANS_THREADS, smem, st>>>(
+      payload, offsets, idx, index_is_channel ? 1 : 0, cdf, cdf_stride, cdf_len, offset, lut, stage_rows, n_channels, L,
+      spc, sym_out, mu, median, val_out, err);
   CRA5_CUDA(cudaGetLastError());
 }
 

@@ -55,8 +55,8 @@ Model::Model(const cra5_config& c) : cfg_(c) {
   CRA5_CHECK(box_rows != 0, ERR_INVALID, "unsupported geometry: patches per row must be a multiple of 8");
   nB = c.patch_h - c.stride_h;
   nA = c.stride_h - nB;
-  spc_y_ = c.streams_per_channel_y > 0 ? c.streams_per_channel_y : 8;
-  spc_z_ = c.streams_per_channel_z > 0 ? c.streams_per_channel_z : 1;
+  spc_y_ = c.streams_per_channel_y > 0 ? c.streams_per_channel_y : 16;
+  spc_z_ = c.streams_per_channel_z > 0 ? c.streams_per_channel_z : 4;
   CRA5_CHECK(spc_y_ <= CR5B_MAX_SPC && spc_z_ <= CR5B_MAX_SPC, ERR_INVALID, "streams per channel must be <= 64");
 
   // ---------------- workspace
@@ -142,6 +142,7 @@ void Model::set_cdf(int which, const int32_t* cdf, const int32_t* len, const int
   if (which == 0) CRA5_CHECK(rows == cfg_.z_chans, ERR_INVALID, "set_cdf: EntropyBottleneck needs one row per z channel");
   if (which == 1) CRA5_CHECK(rows <= 256, ERR_INVALID, "set_cdf: at most 256 scale levels");
   t.cdf = cdf; t.length = len; t.offset = off; t.rows = rows; t.cols = cols;
+  if (coder_ != nullptr) coder_->invalidate_lut();
 }
 
 void Model::set_coder(int spc_y, int spc_z) {

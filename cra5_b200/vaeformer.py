@@ -109,7 +109,7 @@ class VAEformer:
     """
 
     def __init__(self, model_version: int = 268, cfg: Optional[C.VaeformerConfig] = None, device="cuda",
-                 streams_per_channel=(8, 1), init_seed: Optional[int] = 0, **kwargs):
+                 streams_per_channel=(16, 4), init_seed: Optional[int] = 0, **kwargs):
         if cfg is None:
             if model_version != 268:
                 # the reference dies on `Encoder(**None)` here (vaeformer.py:150); say why instead
@@ -285,7 +285,7 @@ class VAEformer:
                 updated = True
         return updated
 
-    def set_coder(self, streams_per_channel_y: int = 8, streams_per_channel_z: int = 1):
+    def set_coder(self, streams_per_channel_y: int = 16, streams_per_channel_z: int = 4):
         _lib.check(_lib.lib.cra5_model_set_coder(self._handle, streams_per_channel_y, streams_per_channel_z))
         self._spc = (streams_per_channel_y, streams_per_channel_z)
 

@@ -61,6 +61,11 @@ CRA5_API int cra5_op_gemm_check(const void* A_dev, int lda, const void* B_dev, i
 CRA5_API int cra5_op_attention(const void* Q_dev, const void* K_dev, const void* Vt_dev, void* out_dev, int ldo, int heads,
                       int rows_total, int seg_len, void* stream);
 
+/* Same contract for any even head_dim (fp32 SIMT kernel; the hyperprior transformer's 5 heads x 72, vit_nlc.py:94-112
+ * through HyperpriorEncoder/Decoder). Q,K: [heads][rows][head_dim], Vt: [heads][head_dim][rows]. */
+CRA5_API int cra5_op_attention_generic(const void* Q_dev, const void* K_dev, const void* Vt_dev, void* out_dev, int ldo,
+                                       int heads, int head_dim, int rows_total, int seg_len, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Host utilities (run once per model, like the reference's C++ helpers)
  * ---------------------------------------------------------------------------------------------------------- */

@@ -121,3 +121,27 @@ def test_attention_matches_fp32_reference(heads, nseg, seg_len):
     # P and the output are rounded to bf16 (2^-8 relative); values are O(1)
     assert err <= 2.5e-2, err
     assert (out.float() - ref).abs().mean().item() <= 2e-3
+
+
+@pytest.mark.parametrize("heads,hd,nseg,seg_len", [(5, 72, 1, 648), (2, 24, 1, 648), (2, 24, 1, 32), (3, 72, 2, 100),
+                                                   (2, 80, 1, 4000)])
+def test_generic_attention_matches_fp32_reference(heads, hd, nseg, seg_len):
+    """hyperprior attention (h_a / h_s: 648 tokens, 5 heads x 72) -- fp32 SIMT kernels, bf16 operands"""
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(heads * 100 + seg_len + hd)
+    rows = nseg * seg_len
+    q = (torch.randn(heads, rows, hd, device="cuda", generator=g) * hd ** -0.5 * 2.0).to(torch.bfloat16)
+    k = (torch.randn(heads, rows, hd, device="cuda", generator=g) * 2.0).to(torch.bfloat16)
+    v = torch.randn(heads, rows, hd, device="cuda", generator=g).to(torch.bfloat16)
+    vt = v.transpose(1, 2).contiguous()
+    out = torch.full((rows, heads * hd), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.check(L.lib.cra5_op_attention_generic(L.ptr(q), L.ptr(k), L.ptr(vt), L.ptr(out), heads * hd, heads, hd, rows,
+                                            seg_len, L.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = torch.empty(rows, heads * hd, device="cuda")
+    for s in range(nseg):
+        sl = slice(s * seg_len, (s + 1) * seg_len)
+        r = _attention_ref(q[:, sl].float(), k[:, sl].float(), v[:, sl].float())
+        ref[sl] = r.permute(1, 0, 2).reshape(seg_len, heads * hd)
+    # fp32 math throughout, only the bf16 rounding of the output remains: 2^-8 relative
+    assert (out.float() - ref).abs().max().item() <= 2 ** -7 * max(1.0, ref.abs().max().item())

@@ -160,7 +160,7 @@ def test_per_variable_rmse_within_tolerance_of_reference(ctx):
     # rate within 1 % + container overhead of the reference's single-stream coder
     ref_bytes = len(ctx.gold["y_string"]) + len(ctx.gold["z_string"])
     new_bytes = len(out["strings"][0][0]) + len(out["strings"][1][0])
-    n_streams = ctx.cfg.latent_chans * 8 + ctx.cfg.z_chans
+    n_streams = ctx.cfg.latent_chans * 16 + ctx.cfg.z_chans * 4
     assert new_bytes <= 1.01 * ref_bytes + 12 * n_streams + 64
 
 
@@ -190,7 +190,7 @@ def test_coder_stream_count_knob(ctx):
         y_hat = net.decompress(out["strings"], out["z_shape"], return_format="latent")
         assert torch.equal(net.tap("y_symbols").cpu(), ctx.ysym_g)
         sizes[spc] = len(out["strings"][0][0])
-    net.set_coder(8, 1)
+    net.set_coder(16, 4)
     assert sizes[1] < sizes[4] < sizes[32]
     with pytest.raises(ValueError):
         net.set_coder(0, 1)
