@@ -1,0 +1,152 @@
+"""CPU tests of the host-side logic: geometry/config, state-dict schema, .bin container, CDF-table construction through
+the C ABI, ABI symbol export, error behaviour without a GPU, and the N>1 sharding/timing plumbing on gloo."""
+import ctypes
+import io
+import os
+import re
+import struct
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from cra5_b200 import config as C
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shipped_geometry_matches_survey():
+    cfg = C.cra5_268()
+    assert cfg.grid == (72, 144) and cfg.tokens == 10368 and cfg.hyper_grid == (18, 36) and cfg.hyper_tokens == 648
+    assert cfg.enc_blocks == 13 and cfg.dec_blocks == 12 and cfg.conv_head
+    W = [(24, 24), (12, 48), (48, 12), None]
+    assert cfg.enc_block_windows() == W * 3 + [None]          # W,W,W,G x3 + extra global
+    assert cfg.dec_block_windows() == W * 3
+    shapes = C.param_shapes(cfg)
+    assert shapes["g_a.patch_embed.proj.weight"] == (1024, 268, 11, 10)
+    assert shapes["g_s.final.weight"] == (1024, 268, 11, 10)
+    assert shapes["quant_conv.weight"] == (512, 2048, 1, 1) and shapes["post_quant_conv.weight"] == (1024, 256, 1, 1)
+    assert shapes["h_s.final.weight"] == (8192, 360) and shapes["h_a.quan_mlp.fc1.weight"] == (256, 360)
+    n_params = sum(int(np.prod(s)) for s in shapes.values())
+    assert abs(n_params / 1e6 - 404.68) < 0.05                  # SURVEY section 3.1 [probed]
+    assert C.variant(159).in_chans == 159 and C.tiny_fullres().conv_head and not C.small_lowres().conv_head
+
+
+def test_unsupported_geometry_is_rejected():
+    with pytest.raises(ValueError):
+        C.VaeformerConfig(patch_size=(11, 12), patch_stride=(10, 10)).validate()
+    with pytest.raises(ValueError):
+        C.VaeformerConfig(patch_size=(25, 10), patch_stride=(10, 10)).validate()
+    with pytest.raises(ValueError):
+        C.VaeformerConfig(num_heads=7).validate()
+
+
+def test_bin_container_wire_format(tmp_path):
+    from cra5_b200.api.utils import read_bin, write_bin
+    strings = [[b"yyyy-stream"], [b"zz"]]
+    p = tmp_path / "2024" / "frame.bin"
+    n = write_bin(p, strings, (18, 36))
+    raw = p.read_bytes()
+    assert n == len(raw)
+    # >I z_h, >I z_w, >I n_strings, then [>I len, bytes] per string (cra5_api.py:108-116)
+    assert raw[:12] == struct.pack(">3I", 18, 36, 2)
+    assert raw[12:16] == struct.pack(">I", 11) and raw[16:27] == b"yyyy-stream"
+    assert raw[27:31] == struct.pack(">I", 2) and raw[31:] == b"zz"
+    got, shape = read_bin(p)
+    assert got == strings and tuple(shape) == (18, 36)
+    with pytest.raises(ValueError):
+        (tmp_path / "t.bin").write_bytes(raw[:20])
+        read_bin(tmp_path / "t.bin")
+
+
+def test_library_exports_every_declared_symbol():
+    from cra5_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "cra5_b200.h")).read()
+    names = re.findall(r"CRA5_API\s+[\w\s\*]+?\b(cra5_\w+)\s*\(", header)
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(_lib.lib, n), f"{n} declared in include/cra5_b200.h but not exported"
+    assert _lib.lib.cra5_abi_version() >= 1
+
+
+def test_cdf_tables_through_c_abi_match_oracle():
+    """update()'s integer tables (product path: torch pmf + cra5_pmf_to_quantized_cdf) == oracle == reference fixture"""
+    from cra5_b200 import entropy_tables as ET
+    from oracle import entropy_oracle as EO, weights
+    assert ET.pmf_to_quantized_cdf(torch.tensor([0.1, 0.2, 0.7])).tolist() == [0, 6554, 19661, 65536]
+    with pytest.raises(ValueError):
+        ET.pmf_to_quantized_cdf(torch.tensor([0.5, float("nan")]))
+    with pytest.raises(ValueError):
+        ET.pmf_to_quantized_cdf(torch.tensor([0.0, 0.0]))
+    g = ET.gaussian_conditional_tables(ET.get_scale_table())
+    o = EO.gaussian_conditional_tables()
+    assert torch.equal(g.quantized_cdf, o.cdf) and torch.equal(g.cdf_length, o.cdf_length) and torch.equal(g.offset, o.offset)
+    cfg = C.tiny_fullres(69)
+    sd = weights.seeded_state_dict(C.param_shapes(cfg), 7)
+    e, eo = ET.entropy_bottleneck_tables(sd), EO.entropy_bottleneck_tables(sd)
+    assert torch.equal(e.quantized_cdf, eo.cdf) and torch.equal(e.cdf_length, eo.cdf_length) and torch.equal(e.offset, eo.offset)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "tiny69.npz"))
+    assert np.array_equal(e.quantized_cdf.numpy(), gold["eb_cdf"])
+    # zero-probability bins get a count stolen from the narrowest donor
+    cdf = ET.pmf_to_quantized_cdf(torch.tensor([0.5, 0.0, 0.5 - 1e-7, 1e-7])).tolist()
+    assert all(b > a for a, b in zip(cdf, cdf[1:])) and cdf[-1] == 65536
+
+
+def test_no_cpu_fallback_and_reference_errors():
+    from cra5_b200 import zoo
+    with pytest.raises(ValueError, match="Invalid metric"):      # zoo/image.py:316
+        zoo.vaeformer_pretrained(268, metric="psnr")
+    with pytest.raises(ValueError, match="Invalid quality"):     # zoo/image.py:319
+        zoo.vaeformer_pretrained(0)
+    with pytest.raises(ValueError, match="Invalid quality"):     # zoo/image.py:281-282
+        zoo.vaeformer_pretrained(5)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU execution path"):
+            zoo.vaeformer_pretrained(268)
+
+
+def test_channel_table_and_api_bookkeeping():
+    import json
+    from cra5_b200.api import era5_268v as V
+    names = V.channel_names()
+    assert len(names) == 268 and names[0] == "z_1000" and names[37] == "q_1000" and names[74] == "u_1000" and names[-1] == "msl"
+    stats = json.load(open(os.path.join(ROOT, "cra5_b200", "api", "era5_268v_stats.json")))["channels"]
+    assert [r["name"] for r in stats] == names and all(r["std"] > 0 for r in stats)
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from cra5_b200 import stream
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = stream.shard_frames(11, rank, world)
+    slowest = stream.max_over_ranks(1.0 + rank)
+    counts = stream.gather_counts([100 + i for i in mine])
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, mine, slowest, counts))
+
+
+def test_frame_sharding_world_size_2_gloo():
+    """N > 1 path: rank-strided frames, no data-path collective, max-over-ranks timing"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, f0, s0, c0), (r1, f1, s1, c1) = res
+    assert f0 == [0, 2, 4, 6, 8, 10] and f1 == [1, 3, 5, 7, 9]
+    assert sorted(f0 + f1) == list(range(11))
+    assert s0 == s1 == 2.0
+    assert c0 == c1 == [[100 + i for i in f0], [100 + i for i in f1]]
+    from cra5_b200 import stream
+    assert stream.shard_frames(5, 0, 1) == [0, 1, 2, 3, 4] and stream.max_over_ranks(3.5) == 3.5
+    with pytest.raises(ValueError):
+        stream.shard_frames(5, 2, 2)
