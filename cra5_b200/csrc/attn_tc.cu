@@ -16,10 +16,16 @@
 
 namespace cra5 {
 
+__device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2, no range fix-up: inputs are <= 0 (or -inf)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int AT_BM = 128;
 constexpr int AT_BN = 128;
 constexpr int AT_HD = 64;
-constexpr int AT_STAGES = 3;
+constexpr int AT_STAGES = 2;   // two CTAs share an SM: 2 x (16 KB Q + 2 x 32 KB KV + 32 KB P) = 224 KB
 constexpr int AT_THREADS = 256;
 
 struct AttnSmem {
@@ -31,8 +37,8 @@ struct AttnSmem {
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_KV = OFF_Q + Q_BYTES;
   static constexpr int OFF_P = OFF_KV + AT_STAGES * KV_BYTES;
-  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
-  static constexpr int TOTAL = OFF_BAR + 256 + 1024;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 128;  // no alignment slack: the dynamic window starts 1024-aligned (checked)
 };
 
 struct AttnParams {
@@ -42,18 +48,19 @@ struct AttnParams {
   int ldo;
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmVt, const AttnParams p) {
   using L = AttnSmem;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
   uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* kv_full = q_full + 1;
   uint64_t* kv_empty = kv_full + AT_STAGES;
   uint64_t* s_full = kv_empty + AT_STAGES;
-  uint64_t* p_full = s_full + 2;
-  uint64_t* pv_full = p_full + 2;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* pv_full = p_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -75,20 +82,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 128);
-      mbar_init(&pv_full[s], 1);
-    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    for (int s = 0; s < 2; ++s) mbar_init(&pv_full[s], 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 2) tmem_alloc<256>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t TM_S = 0;     // 2 x 128 columns
-  constexpr uint32_t TM_PV = 256;  // 2 x 64 columns
+  constexpr uint32_t TM_S = 0;     // 128 columns (single buffer: the second CTA on the SM fills the bubbles)
+  constexpr uint32_t TM_PV = 128;  // 2 x 64 columns
 
   if (warp == 0) {
     if (lane == 0) {
@@ -121,19 +126,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(smem + L::OFF_KV + s * L::KV_BYTES));
 #pragma unroll
         for (int k = 0; k < AT_HD / 16; ++k)
-          umma_bf16(tmem_base + TM_S + (j & 1) * AT_BN, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[j & 1]);
+          umma_bf16(tmem_base + TM_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        umma_commit(s_full);
       };
       mbar_wait(q_full, 0);
       tc_fence_after();
       issue_s(0);
       for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) issue_s(j + 1);
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        mbar_wait(p_full, j & 1);   // softmax has consumed S_j and published P_j
         tc_fence_after();
         const int s = j % AT_STAGES;
         const uint32_t sv = smem_u32(smem + L::OFF_KV + s * L::KV_BYTES + L::K_BYTES);
-        const uint32_t sp = smem_u32(smem + L::OFF_P + (j & 1) * L::P_BYTES);
+        const uint32_t sp = smem_u32(smem + L::OFF_P);
 #pragma unroll
         for (int kk = 0; kk < AT_BN / 16; ++kk) {
           const int half = kk >> 2, k = kk & 3;
@@ -143,6 +147,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         umma_commit(&pv_full[j & 1]);
         umma_commit(&kv_empty[s]);
+        if (j + 1 < n_kv) issue_s(j + 1);  // S is single-buffered: next scores only after P_j was read out of S
       }
     }
   } else if (warp >= 4) {
@@ -158,9 +163,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
     for (int j = 0; j < n_kv; ++j) {
       const int valid = min(AT_BN, p.seg_len - j * AT_BN);
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      const bool full_tile = (valid == AT_BN);   // warp-uniform: only a segment's last tile can be partial
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const uint32_t s_addr = tmem_base + lane_addr + TM_S + (j & 1) * AT_BN;
+      const uint32_t s_addr = tmem_base + lane_addr + TM_S;
       // pass 1: row maximum
       float mx = m;
 #pragma unroll 1
@@ -168,17 +174,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         uint32_t sv[32];
         tmem_ld_32x32(s_addr + c, sv);
         tmem_ld_wait();
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(sv[i]);
-          if (c + i < valid) mx = fmaxf(mx, x);
+          for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < valid) mx = fmaxf(mx, __uint_as_float(sv[i]));
         }
       }
-      const float alpha = exp2f((m - mx) * LOG2E);  // 0 on the first tile (m = -inf)
+      const float alpha = ex2_approx((m - mx) * LOG2E);  // 0 on the first tile (m = -inf)
       const float mxl = mx * LOG2E;
       // pass 2: probabilities -> bf16 P tile in smem (K-major, SWIZZLE_128B)
       float rowsum = 0.f;
-      uint8_t* pbase = smem + L::OFF_P + (j & 1) * L::P_BYTES;
+      uint8_t* pbase = smem + L::OFF_P;
 #pragma unroll 1
       for (int c = 0; c < AT_BN; c += 32) {
         uint32_t sv[32];
@@ -186,12 +195,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tmem_ld_wait();
         float pr[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(sv[i]);
-          float e = exp2f(fmaf(x, LOG2E, -mxl));
-          pr[i] = (c + i < valid) ? e : 0.f;
-          rowsum += pr[i];
+        for (int i = 0; i < 32; ++i) pr[i] = ex2_approx(fmaf(__uint_as_float(sv[i]), LOG2E, -mxl));
+        if (!full_tile) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) pr[i] = (c + i < valid) ? pr[i] : 0.f;
         }
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) { s0 += pr[i]; s1 += pr[i + 1]; s2 += pr[i + 2]; s3 += pr[i + 3]; }
+        rowsum += (s0 + s1) + (s2 + s3);
         uint8_t* region = pbase + (c >> 6) * (L::P_BYTES / 2);
         const int chunk0 = (c & 63) >> 3;  // 0 or 4
 #pragma unroll
@@ -208,7 +220,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       m = mx;
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&p_full[j & 1]);
+      mbar_arrive(p_full);
       // fold the previous tile's P V product, then rescale everything to the new maximum
       if (j > 0) {
         mbar_wait(&pv_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
@@ -256,7 +268,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<256>(tmem_base);
   }
 }
 
