@@ -48,3 +48,80 @@ def stream_frames(codec, frames: Iterable, rank: int, world: int, n_frames: int)
         out = codec.compress(x.unsqueeze(0) if x.dim() == 3 else x)
         rec = codec.decompress(out["strings"], out["z_shape"])
         yield i, out["strings"], rec["x_hat"]
+
+
+class FramePipeline:
+    """Host-to-host streaming of frames through one GPU with the PCIe copies hidden behind compute.
+
+    Three CUDA streams: H2D of frame i+1 and D2H of reconstruction i-1 run while frame i is being compressed /
+    decompressed (PCIe is full duplex; a 268x721x1440 frame is 1.1 GB each way, ~21 ms at 53 GB/s, about the same as
+    the GPU time of the codec itself). The reference loops synchronously over timestamps (test.py:13): read, `.to(device)`,
+    compress, decompress, `.cpu()`.
+
+        pipe = FramePipeline(api)                      # api: cra5_b200.api.cra5_api
+        for idx, strings, x_hat_host in pipe.run(host_frames, out_buffers): ...
+
+    `host_frames`: indexable of pinned (C, H, W) fp32 host tensors in physical units; `out_buffers`: >= 2 pinned host
+    tensors that receive the (normalised) reconstructions round-robin -- an entry is valid until it is reused.
+    """
+
+    def __init__(self, api, roundtrip: bool = True):
+        import torch
+        self.api = api
+        self.roundtrip = roundtrip
+        self.dev = torch.device(api.device)
+        self.copy_in = torch.cuda.Stream(self.dev)
+        self.copy_out = torch.cuda.Stream(self.dev)
+
+    def run(self, host_frames, out_buffers, n_frames=None):
+        import torch
+        api, dev = self.api, self.dev
+        n = len(host_frames) if n_frames is None else n_frames
+        if n == 0:
+            return
+        main = torch.cuda.current_stream(dev)
+        shape = tuple(host_frames[0].shape)
+        dev_in = [torch.empty(shape, device=dev, dtype=torch.float32) for _ in range(2)]
+        in_ready = [torch.cuda.Event() for _ in range(2)]
+        in_free = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(i):
+            b = i % 2
+            with torch.cuda.stream(self.copy_in):
+                self.copy_in.wait_event(in_free[b])          # the compute that last read this buffer has finished
+                dev_in[b].copy_(host_frames[i % len(host_frames)], non_blocking=True)
+                in_ready[b].record(self.copy_in)
+
+        for b in range(2):
+            in_free[b].record(main)
+        prefetch(0)
+        pending = None  # (index, strings, host buffer, event): reconstruction still in flight to the host
+        for i in range(n):
+            b = i % 2
+            if i + 1 < n:
+                prefetch(i + 1)
+            main.wait_event(in_ready[b])
+            y = api.encode_to_latent(data=dev_in[b])          # fused normalise + g_a + quant_conv
+            in_free[b].record(main)
+            out = api.latent_to_bin(y)                        # h_a, h_s, quantise, rANS -> host bytes
+            if not self.roundtrip:
+                yield i, out["strings"], None
+                continue
+            y_hat = api.net.decompress(out["strings"], out["z_shape"], return_format="latent")
+            x_hat = api.latent_to_reconstruction(y_hat)       # post_quant_conv + g_s
+            done = torch.cuda.Event()
+            done.record(main)
+            ob = out_buffers[i % len(out_buffers)]
+            with torch.cuda.stream(self.copy_out):
+                self.copy_out.wait_event(done)
+                ob.copy_(x_hat[0], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_out)
+            x_hat.record_stream(self.copy_out)
+            if pending is not None:
+                pending[3].synchronize()                      # reconstruction i-1 has landed in host memory
+                yield pending[0], pending[1], pending[2]
+            pending = (i, out["strings"], ob, ev)
+        if pending is not None:
+            pending[3].synchronize()
+            yield pending[0], pending[1], pending[2]
