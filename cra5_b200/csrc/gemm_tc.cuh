@@ -241,13 +241,135 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Row-wise epilogue: a warp's 32x32 accumulator chunk has been staged in shared memory (stg[r * 33 + c]); lanes now
+// run along the COLUMNS of one output row at a time, so every global access of the warp is one contiguous
+// 128-byte (fp32) / 64-byte (bf16) segment instead of 32 scattered ones.
+constexpr int STG_LD = 33;  // padded row stride (words): conflict-free both for the row writes and the column reads
+
+template <int KIND>
+__device__ __forceinline__ void epilogue_rows(const EpiParams& p, const float* stg, int row_base, int col0, int lane,
+                                              int M, int N) {
+  const int rows_valid = min(32, M - row_base);
+  if (rows_valid <= 0) return;
+  if constexpr (KIND == EPI_F32) {
+    const int col = col0 + lane;
+    const bool ok = col < N;
+    const float b = (p.bias != nullptr && ok) ? __ldg(p.bias + col) : 0.f;
+    const int colc = ok ? col : 0;
+    if (p.add != nullptr) {  // all loads first, from always-valid (clamped) addresses so nothing waits on a select
+      float av[32];
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr)
+        av[rr] = __ldg(p.add + (size_t)(row_base + min(rr, rows_valid - 1)) * p.lda + colc);
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr)
+        if (ok && rr < rows_valid) p.out_f32[(size_t)(row_base + rr) * p.ldo + col] = stg[rr * STG_LD + lane] + b + av[rr];
+    } else {
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr)
+        if (ok && rr < rows_valid) p.out_f32[(size_t)(row_base + rr) * p.ldo + col] = stg[rr * STG_LD + lane] + b;
+    }
+  } else if constexpr (KIND == EPI_BF16 || KIND == EPI_GELU_BF16) {
+    // two rows per step: lanes 0-15 take row rr, lanes 16-31 row rr+1, two adjacent columns each (4-byte stores)
+    const int half = lane >> 4, l2 = (lane & 15) * 2;
+    const int col = col0 + l2;
+    const float b0 = (p.bias != nullptr && col < N) ? __ldg(p.bias + col) : 0.f;
+    const float b1 = (p.bias != nullptr && col + 1 < N) ? __ldg(p.bias + col + 1) : 0.f;
+    const bool pair_ok = (col + 1 < N) && ((p.ldo & 1) == 0);
+    for (int rr = half; rr < rows_valid; rr += 2) {
+      float v0 = stg[rr * STG_LD + l2] + b0, v1 = stg[rr * STG_LD + l2 + 1] + b1;
+      if constexpr (KIND == EPI_GELU_BF16) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); }
+      __nv_bfloat16* o = p.out_bf16 + (size_t)(row_base + rr) * p.ldo + col;
+      if (pair_ok) {
+        *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(v0, v1);
+      } else {
+        if (col < N) o[0] = __float2bfloat16(v0);
+        if (col + 1 < N) o[1] = __float2bfloat16(v1);
+      }
+    }
+  } else if constexpr (KIND == EPI_QKV) {
+    // columns ordered [q|k|v][head][dim] (vit_nlc.py:99,242); each lane owns one column for all rows of the chunk
+    const int col = col0 + lane;
+    if (col >= N) return;
+    const float b = (p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
+    const int which = col / p.D;
+    const int within = col - which * p.D;
+    const int head = within / p.hd, d = within - head * p.hd;
+    if (which == 2) {  // (only reached when a chunk straddles the k|v boundary; whole-V chunks take the direct path)
+      __nv_bfloat16* dst = p.vt + ((size_t)head * p.hd + d) * p.rows_total + row_base;
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr)
+        if (rr < rows_valid) dst[rr] = __float2bfloat16(stg[rr * STG_LD + lane] + b);
+    } else {
+      const float sc = (which == 0) ? p.qscale : 1.0f;
+      __nv_bfloat16* dst = (which == 0 ? p.q : p.k) + ((size_t)head * p.rows_total + row_base) * p.hd + d;
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr)
+        if (rr < rows_valid) dst[(size_t)rr * p.hd] = __float2bfloat16((stg[rr * STG_LD + lane] + b) * sc);
+    }
+  } else if constexpr (KIND == EPI_RESID) {
+    // handled by epilogue_resid_load / epilogue_resid_finish (the residual loads are issued before the TMEM read)
+  } else if constexpr (KIND == EPI_CONVT) {
+    // row = (i, j) patch position; col = (r - r0, c, s); out[c][sh*i + r][pw*j + s]: a lane's column fixes (r, c, s)
+    const int col = col0 + lane;
+    if (col >= N) return;
+    const int rk = col / p.ct_CS, cs = col - rk * p.ct_CS;
+    const int c = cs / p.ct_pw, s_ = cs - c * p.ct_pw;
+    float* plane = p.out_f32 + (size_t)c * p.ct_Himg * p.ct_Wimg + s_;
+#pragma unroll 8
+    for (int rr = 0; rr < rows_valid; ++rr) {
+      const int row = row_base + rr;
+      const int i_ = row / p.ct_Wp, j_ = row - i_ * p.ct_Wp;
+      const int h = p.ct_sh * i_ + p.ct_r0 + rk;
+      if (h < p.ct_Himg) plane[(size_t)h * p.ct_Wimg + p.ct_pw * j_] = stg[rr * STG_LD + lane];
+    }
+  }
+}
+
+// EPI_RESID, phase 1: issue the 32 residual loads of this chunk (clamped, unconditional addresses) -- called BEFORE the
+// accumulator is read out of TMEM and staged, so the DRAM/L2 latency overlaps that work. resid may alias out.
+__device__ __forceinline__ void epilogue_resid_load(const EpiParams& p, int row_base, int col0, int lane, int M, int N,
+                                                    float (&rv)[32], int& my_t) {
+  const int rows_valid = min(32, M - row_base);
+  const int col = col0 + lane;
+  const int colc = (col < N) ? col : 0;
+  my_t = (lane < rows_valid) ? p.wm.to_token(row_base + lane) : -1;
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) {
+    const int t = __shfl_sync(0xffffffffu, my_t, rr);
+    rv[rr] = p.resid[(size_t)max(t, 0) * p.ldo + colc];
+  }
+}
+__device__ __forceinline__ void epilogue_resid_finish(const EpiParams& p, const float* stg, int col0, int lane, int N,
+                                                      const float (&rv)[32], int my_t) {
+  const int col = col0 + lane;
+  const bool ok = col < N;
+  const float b = (p.bias != nullptr && ok) ? __ldg(p.bias + col) : 0.f;
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) {
+    const int t = __shfl_sync(0xffffffffu, my_t, rr);
+    if (t >= 0 && ok) {
+      const float v = stg[rr * STG_LD + lane] + b + rv[rr];
+      p.out_f32[(size_t)t * p.ldo + col] = v;
+      if (p.out_bf16 != nullptr) p.out_bf16[(size_t)t * p.ld_bf16 + p.bf16_col0 + col] = __float2bfloat16(v);
+    }
+  }
+}
+
+// kinds whose natural store direction is along the ROWS (thread = row): written straight from registers
+template <int KIND>
+__device__ __forceinline__ constexpr bool epi_is_direct() { return KIND == EPI_T_F32 || KIND == EPI_PIXSHUF; }
+
 template <int BN>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = GEMM_STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+  static constexpr int STG_OFFSET = GEMM_STAGES * STAGE_BYTES;          // 8 epilogue warps x [32][33] fp32 staging
+  static constexpr int STG_BYTES = 8 * 32 * STG_LD * 4;
+  static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256;  // no alignment slack: the dynamic window starts 1024-aligned (checked)
 };
 
 template <int BN, int KIND>
@@ -257,7 +379,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using L = GemmSmem<BN>;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // 256 or 512: power of two >= 32
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B operand tiles need 1024-byte alignment
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + GEMM_STAGES;
   uint64_t* tfull_bar = empty_bar + GEMM_STAGES;
@@ -370,16 +493,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t aph = (tl >> 1) & 1;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
+      const int row_base = m0 + quarter * 32;
+      const int row = row_base + lane;
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN + half * (BN / 2);
+      float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET) + ew * (32 * STG_LD);
 #pragma unroll 1
       for (int c = 0; c < BN / 2; c += 32) {
         const int col0 = n0 + half * (BN / 2) + c;
         if (col0 >= shp.N) break;  // warp-uniform
+        float rv[32];
+        int my_t = -1;
+        if constexpr (KIND == EPI_RESID) epilogue_resid_load(epi, row_base, col0, lane, shp.M, shp.N, rv, my_t);
         uint32_t acc[32];
         tmem_ld_32x32(taddr + c, acc);
         tmem_ld_wait();
-        epilogue_store<KIND>(epi, row, col0, acc, shp.M, shp.N);
+        bool direct = epi_is_direct<KIND>();
+        if constexpr (KIND == EPI_QKV)  // a chunk that lies wholly inside V is written transposed, thread = row
+          direct = (col0 >= 2 * epi.D) && (col0 + 32 <= shp.N);
+        if (direct) {
+          epilogue_store<KIND>(epi, row, col0, acc, shp.M, shp.N);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = __uint_as_float(acc[i]);
+          __syncwarp();
+          if constexpr (KIND == EPI_RESID)
+            epilogue_resid_finish(epi, stg, col0, lane, shp.N, rv, my_t);
+          else
+            epilogue_rows<KIND>(epi, stg, row_base, col0, lane, shp.M, shp.N);
+          __syncwarp();
+        }
       }
       tc_fence_before();
       __syncwarp();
