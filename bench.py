@@ -253,7 +253,7 @@ def run_b200(args):
                        "latent_to_reconstruction -> D2H -> pinned host; copies on side streams overlap compute"}
 
     # ---- per-kernel profile (CUDA events on the launch stream, separate pass so the events do not perturb `value`)
-    roofline, kernels = None, None
+    roofline, kernels, sites = None, None, None
     if not args.no_kernel_profile and rank == 0:
         peaks = measured_peaks()
         _lib.check(_lib.lib.cra5_profile_enable(1))
@@ -285,6 +285,9 @@ def run_b200(args):
             roofline = {"kernel": tname, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
                         "share_of_step": tk["ms"] / tot}
+        sites = {n: {"ms_per_step": round(k["ms"] / 2, 4), "launches_per_step": k["launches"] / 2,
+                     "tflops": round(k["flops"] / (k["ms"] / 1e3) / 1e12, 1) if k["flops"] and k["ms"] else None}
+                 for n, k in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"]) if ":" in n}
         kernels = {n: {"ms_per_step": k["ms"] / 2, "launches_per_step": k["launches"] / 2,
                        "tflops": (k["flops"] / (k["ms"] / 1e3) / 1e12) if k["flops"] and k["ms"] else None,
                        "gbs": (k["bytes"] / (k["ms"] / 1e3) / 1e9) if k["bytes"] and k["ms"] else None}
@@ -321,7 +324,7 @@ def run_b200(args):
                        "bytes_per_frame": nbytes, "coder": "CR5B chunk-parallel rANS, 16 sub-streams per y channel, 4 per z channel"},
             "gb_era5_per_s": fps * frame_bytes / 1e9,
             "e2e": e2e, "gpu_launches": int(lc1.value - lc0.value), "clocks": clock_info,
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+            "roofline": roofline, "kernels": kernels, "kernel_sites": sites if kernels else None, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
