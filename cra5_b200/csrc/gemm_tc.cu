@@ -3,6 +3,7 @@
 #include "gemm_tc.cuh"
 #include "host_util.h"
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace cra5 {
 
@@ -43,7 +44,11 @@ static void launch_kind(cudaStream_t st, int kind, const CUtensorMap& tmA, const
   }
 }
 
-int gemm_pick_bn(int N) { return N > 128 ? 256 : 128; }
+int gemm_pick_bn(int N) {
+  static const char* env = getenv("CRA5_GEMM_BN");  // diagnostics only
+  if (env != nullptr && N > 128) return atoi(env) == 128 ? 128 : 256;
+  return N > 128 ? 256 : 128;
+}
 
 void launch_gemm(cudaStream_t st, int bn, int kind, const CUtensorMap& tmA, const CUtensorMap& tmB,
                  const GemmShape& shp, const EpiParams& epi) {

@@ -102,7 +102,23 @@ struct EpiParams {
   int ct_Himg, ct_Wimg;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// exact (erf) GELU, nn.GELU default (vit_nlc.py:53). erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32
+// round-off level, branch-free, 2 MUFU + ~12 FMA-pipe instructions; the libm erff costs about twice that and made the
+// fc1 epilogue longer than its K=1024 main loop).
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float erf_abs = fmaf(-p, e, 1.0f);            // erf(|x|/sqrt2)
+  return 0.5f * x + 0.5f * fabsf(x) * erf_abs;          // 0.5 x (1 + sign(x) erf(|x|/sqrt2))
+}
 
 template <int KIND>
 __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int col0, const uint32_t (&acc)[32],
@@ -162,13 +178,29 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
       const int d = within - head * p.hd;
       const bool vec = ((p.hd | p.D) & 7) == 0 && (col + 8 <= N);  // 8 columns stay inside one head
       if (which == 2) {
+        if (vec && (p.rows_total & 1) == 0 && (M & 1) == 0) {
+          // V^T[d][row]: neighbouring lanes hold neighbouring rows; even lanes write rows (row, row+1) of column i, odd
+          // lanes rows (row-1, row) of column i+1 -> one 4-byte store per lane covers two rows
+          const bool odd = threadIdx.x & 1;
+          const unsigned am = __activemask();  // rows >= M have returned; M is even, so lane pairs stay together
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (col + i < N) {
-            int c2 = col + i - 2 * p.D;
-            int h2 = c2 / p.hd, d2 = c2 - h2 * p.hd;
-            p.vt[((size_t)h2 * p.hd + d2) * p.rows_total + row] = __float2bfloat16(v[i0 + i]);
+          for (int i = 0; i < 8; i += 2) {
+            const float mine0 = v[i0 + i], mine1 = v[i0 + i + 1];
+            const float other0 = __shfl_xor_sync(am, mine0, 1), other1 = __shfl_xor_sync(am, mine1, 1);
+            const int dcol = d + i + (odd ? 1 : 0);
+            const float lo = odd ? other1 : mine0, hi = odd ? mine1 : other0;
+            const int r0_ = odd ? row - 1 : row;
+            *reinterpret_cast<uint32_t*>(p.vt + ((size_t)head * p.hd + dcol) * p.rows_total + r0_) = pack_bf16x2(lo, hi);
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (col + i < N) {
+              int c2 = col + i - 2 * p.D;
+              int h2 = c2 / p.hd, d2 = c2 - h2 * p.hd;
+              p.vt[((size_t)h2 * p.hd + d2) * p.rows_total + row] = __float2bfloat16(v[i0 + i]);
+            }
+        }
       } else {
         __nv_bfloat16* dst = (which == 0 ? p.q : p.k) + ((size_t)head * p.rows_total + row) * p.hd + d;
         const float s = (which == 0) ? p.qscale : 1.0f;
@@ -247,6 +279,16 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
 // 128-byte (fp32) / 64-byte (bf16) segment instead of 32 scattered ones.
 constexpr int STG_LD = 33;  // padded row stride (words): conflict-free both for the row writes and the column reads
 
+// bf16 row stores, two rows per step: lanes 0-15 take row rr, lanes 16-31 row rr+1, two adjacent columns each
+__device__ __forceinline__ void store_rows_bf16x2(const float* stg, __nv_bfloat16* base, size_t ld, int rows_valid,
+                                                  int lane, float b0, float b1, float scale) {
+  const int half = lane >> 4, l2 = (lane & 15) * 2;
+  for (int rr = half; rr < rows_valid; rr += 2) {
+    const float v0 = (stg[rr * STG_LD + l2] + b0) * scale, v1 = (stg[rr * STG_LD + l2 + 1] + b1) * scale;
+    *reinterpret_cast<uint32_t*>(base + (size_t)rr * ld + l2) = pack_bf16x2(v0, v1);
+  }
+}
+
 template <int KIND>
 __device__ __forceinline__ void epilogue_rows(const EpiParams& p, const float* stg, int row_base, int col0, int lane,
                                               int M, int N) {
@@ -289,7 +331,20 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& p, const float* s
       }
     }
   } else if constexpr (KIND == EPI_QKV) {
-    // columns ordered [q|k|v][head][dim] (vit_nlc.py:99,242); each lane owns one column for all rows of the chunk
+    // columns ordered [q|k|v][head][dim] (vit_nlc.py:99,242)
+    if (((p.D | p.hd) & 31) == 0 && col0 + 32 <= N) {
+      // the whole 32-column chunk lies inside one head of Q or K (V chunks take the direct path): 4-byte stores
+      const int which = col0 / p.D;
+      const int within = col0 - which * p.D;
+      const int head = within / p.hd, d0 = within - head * p.hd;
+      const int l2 = (lane & 15) * 2;
+      const float b0 = (p.bias != nullptr) ? __ldg(p.bias + col0 + l2) : 0.f;
+      const float b1 = (p.bias != nullptr) ? __ldg(p.bias + col0 + l2 + 1) : 0.f;
+      __nv_bfloat16* base = (which == 0 ? p.q : p.k) + ((size_t)head * p.rows_total + row_base) * p.hd + d0;
+      store_rows_bf16x2(stg, base, (size_t)p.hd, rows_valid, lane, b0, b1, which == 0 ? p.qscale : 1.0f);
+      return;
+    }
+    // generic: each lane owns one column for all rows of the chunk
     const int col = col0 + lane;
     if (col >= N) return;
     const float b = (p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
@@ -491,6 +546,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = (tile / m_tiles) * BN;
       const uint32_t as = tl & 1;
       const uint32_t aph = (tl >> 1) & 1;
+      if constexpr (KIND == EPI_RESID) {
+        // pull this warp's share of the residual tile (32 rows x BN/2 fp32) towards L2 while the main loop of the tile
+        // is still running: the epilogue is otherwise bound by four serial DRAM round trips per tile
+        const int prow = m0 + quarter * 32 + lane;
+        const int pt = (prow < shp.M) ? epi.wm.to_token(prow) : -1;
+        if (pt >= 0) {
+          const float* pr = epi.resid + (size_t)pt * epi.ldo + n0 + half * (BN / 2);
+#pragma unroll
+          for (int q = 0; q < BN / 2; q += 32)
+            if (n0 + half * (BN / 2) + q < shp.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + q));
+        }
+      }
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const int row_base = m0 + quarter * 32;

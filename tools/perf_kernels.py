@@ -46,7 +46,7 @@ def attn(heads, nseg, seg):
     fl = 4.0 * heads * nseg * seg * seg * 64
     print(f"attn heads={heads} nseg={nseg} seg={seg}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s")
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     gemm(10368, 3072, 1024, 1)
     gemm(10368, 4096, 1024, 2)
     gemm(10368, 1024, 4096, 4)
@@ -56,3 +56,8 @@ if __name__ == "__main__":
     attn(16, 1, 10368)
     attn(16, 18, 576)
     attn(16, 24, 576)
+
+if len(sys.argv) > 1 and sys.argv[1] == "epi":
+    for epi in (0, 1, 4):
+        gemm(10368, 1024, 1024, epi)
+        gemm(10368, 1024, 4096, epi)
