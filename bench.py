@@ -97,6 +97,11 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def workload(cfg):
+    return (f"full encode->rANS bin->decode round trip, {cfg.in_chans}x721x1440 frame, vaeformer quality={cfg.in_chans} "
+            f"(BASELINE.json configs[2]), one frame per step per GPU")
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -131,8 +136,8 @@ def run_reference(args):
         "impl": "reference", "metric": "ERA5 frames/s (268x721x1440) encode+decode", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": frame_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"full encode->rANS bin->decode round trip, {cfg.in_chans}x721x1440 frame, quality={cfg.in_chans}",
-                   "l2": "inputs larger than L2 (n/a on CPU)"},
+        "config": {"workload": workload(cfg), "l2": "n/a (CPU arm)",
+                   "weights": "random init of the named architecture", "coder": "reference single-stream rANS"},
         "gb_era5_per_s": fps * cfg.in_chans * 721 * 1440 * 4 / 1e9,
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": s.describe()},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -317,8 +322,7 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 tensor-core operands, fp32 accumulate/residual/softmax; int32/u8 entropy stage",
             "data": "synthetic",
-            "config": {"workload": f"full encode->rANS bin->decode round trip, {cfg.in_chans}x721x1440 frame, "
-                                   f"vaeformer quality={cfg.in_chans} (BASELINE.json configs[2]), one frame per step per GPU",
+            "config": {"workload": workload(cfg),
                        "l2": "inputs larger than L2: two alternating 1.1 GB frames, every kernel's working set is re-streamed",
                        "weights": "random init of the named architecture (seed 1234), CDF tables from update(force=True)",
                        "bytes_per_frame": nbytes, "coder": "CR5B chunk-parallel rANS, 16 sub-streams per y channel, 4 per z channel"},

@@ -28,6 +28,49 @@ static void launch_one(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMa
   CRA5_CUDA(cudaGetLastError());
 }
 
+template <int KIND>
+static void launch_pair(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp,
+                        const EpiParams& epi) {
+  static bool configured = false;
+  auto kern = gemm_tc2_kernel<KIND>;
+  if (!configured) {
+    CRA5_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem2::TOTAL));
+    configured = true;
+  }
+  const int m_tiles = (shp.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int n_tiles = (shp.N + GemmSmem2::BN - 1) / GemmSmem2::BN;
+  int clusters = m_tiles * n_tiles;
+  const int max_clusters = device_sm_count() / 2;
+  if (clusters > max_clusters) clusters = max_clusters;
+  LaunchScope scope(st, "gemm_tc2", 2.0 * shp.M * shp.N * shp.K,
+                    2.0 * ((double)shp.M * shp.K + (double)shp.N * shp.K) +
+                        (double)shp.M * shp.N * ((KIND == EPI_BF16 || KIND == EPI_GELU_BF16 || KIND == EPI_QKV) ? 2.0 : 4.0));
+  kern<<<2 * clusters, GEMM_THREADS, GemmSmem2::TOTAL, st>>>(tmA, tmB, shp, epi);  // cluster dims are compiled in
+  CRA5_CUDA(cudaGetLastError());
+}
+
+void launch_gemm_pair(cudaStream_t st, int kind, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp,
+                      const EpiParams& epi) {
+  switch (kind) {
+    case EPI_F32: launch_pair<EPI_F32>(st, tmA, tmB, shp, epi); break;
+    case EPI_BF16: launch_pair<EPI_BF16>(st, tmA, tmB, shp, epi); break;
+    case EPI_GELU_BF16: launch_pair<EPI_GELU_BF16>(st, tmA, tmB, shp, epi); break;
+    case EPI_QKV: launch_pair<EPI_QKV>(st, tmA, tmB, shp, epi); break;
+    case EPI_RESID: launch_pair<EPI_RESID>(st, tmA, tmB, shp, epi); break;
+    case EPI_T_F32: launch_pair<EPI_T_F32>(st, tmA, tmB, shp, epi); break;
+    case EPI_PIXSHUF: launch_pair<EPI_PIXSHUF>(st, tmA, tmB, shp, epi); break;
+    case EPI_CONVT: launch_pair<EPI_CONVT>(st, tmA, tmB, shp, epi); break;
+    default: throw Error(ERR_INTERNAL, "unknown epilogue kind");
+  }
+}
+
+// CTA-pair tiles pay off for large problems (>= one 256 x 256 tile per SM pair); small / skinny ones keep the 1-CTA kernel
+bool gemm_use_pair(int M, int N) {
+  static const char* env = getenv("CRA5_GEMM_PAIR");  // diagnostics: 0 = never, 1 = whenever legal
+  if (env != nullptr) return atoi(env) != 0 && N >= 256;
+  return false;
+}
+
 template <int BN>
 static void launch_kind(cudaStream_t st, int kind, const CUtensorMap& tmA, const CUtensorMap& tmB,
                         const GemmShape& shp, const EpiParams& epi) {
@@ -64,6 +107,14 @@ void launch_gemm(cudaStream_t st, int bn, int kind, const CUtensorMap& tmA, cons
 // Plain row-major GEMM convenience: A [M,K] (row stride lda elements), B [N,K] (row stride ldb), both bf16.
 void gemm_plain(cudaStream_t st, int kind, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M,
                 int N, int K, const EpiParams& epi) {
+  if (gemm_use_pair(M, N)) {
+    CUtensorMap tmA = make_tmap_bf16_2d(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, GEMM_BK, GEMM_BM);
+    CUtensorMap tmB = make_tmap_bf16_2d(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, GEMM_BK, GemmSmem2::BN / 2);
+    GemmShape shp{};
+    shp.M = M; shp.N = N; shp.K = K; shp.a_mode = A_PLAIN;
+    launch_gemm_pair(st, kind, tmA, tmB, shp, epi);
+    return;
+  }
   const int bn = gemm_pick_bn(N);
   CUtensorMap tmA = make_tmap_bf16_2d(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, GEMM_BK, GEMM_BM);
   CUtensorMap tmB = make_tmap_bf16_2d(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, GEMM_BK, bn);

@@ -603,4 +603,202 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+
+// =================================================================================================================
+// CTA-pair variant: a cluster of two CTAs (two SMs of one TPC) computes one 256 x 256 output tile with
+// tcgen05.mma.cta_group::2. Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 N rows), so
+// the L2 -> SM traffic per output element drops by a third against the single-CTA 128 x 256 tile -- and the
+// single-CTA kernel is L2-bandwidth bound (48 KB per 512 MMA cycles per SM, chip-wide above the LTS throughput cap).
+// The leader CTA (cluster rank 0) issues the MMAs; both CTAs run a TMA producer and eight epilogue warps over their own
+// half of the accumulator (TMEM lanes = their 128 rows).
+struct GemmSmem2 {
+  static constexpr int BN = 256;
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;        // 16 KB: this CTA's 128 rows
+  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;       // 16 KB: this CTA's half of the N rows
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STG_BYTES = 8 * 32 * STG_LD * 4;
+  static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256;
+};
+
+template <int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape shp,
+                const EpiParams epi) {
+  using L = GemmSmem2;
+  constexpr int BN = L::BN;
+  constexpr int ST = L::STAGES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + ST;
+  uint64_t* tfull_bar = empty_bar + ST;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+  const int m_tiles = (shp.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int n_tiles = (shp.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (shp.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(&full_bar[s], 1);    // leader's producer arrives (with the byte count of BOTH CTAs)
+      mbar_init(&empty_bar[s], 1);   // multicast MMA commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);   // multicast MMA commit
+      mbar_init(&tempty_bar[s], 16); // 8 epilogue warps of each CTA arrive on the LEADER's barrier
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        const int m0 = (tile % m_tiles) * (2 * GEMM_BM) + (int)rank * GEMM_BM;
+        const int n0 = (tile / m_tiles) * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % ST;
+          const uint32_t ph = (it / ST) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          const uint32_t fb = map_to_cta(smem_u32(&full_bar[s]), 0);  // the leader's barrier
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES);
+          if (shp.a_mode == A_PLAIN) {
+            tma_load_2d_pair(sa, &tmA, fb, kb * GEMM_BK, m0);
+          } else if (shp.a_mode == A_PATCH) {
+            const int r = kb / shp.pe_kpr;
+            const int cs0 = (kb - r * shp.pe_kpr) * GEMM_BK;
+            const int nbox = GEMM_BM / shp.pe_box_rows;
+            for (int g = 0; g < nbox; ++g) {
+              const int t = m0 + g * shp.pe_box_rows;
+              const int i = t / shp.pe_Wp, j0 = t - i * shp.pe_Wp;
+              tma_load_3d_pair(sa + g * shp.pe_box_rows * 128, &tmA, fb, cs0, j0, shp.pe_sh * i + r);
+            }
+          } else {  // A_CONCAT
+            const int k0 = kb * GEMM_BK;
+            if (k0 < shp.cc_D)
+              tma_load_2d_pair(sa, &tmA, fb, k0, m0);
+            else
+              tma_load_2d_pair(sa, &tmA, fb, k0 - shp.cc_D, m0 - shp.cc_shift);
+          }
+          tma_load_2d_pair(sb, &tmB, fb, kb * GEMM_BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN);
+      uint32_t it = 0, tl = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++tl) {
+        const uint32_t as = tl & 1;
+        const uint32_t aph = (tl >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % ST;
+          const uint32_t ph = (it / ST) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint64_t adesc = umma_smem_desc_sw128(sa);
+          const uint64_t bdesc = umma_smem_desc_sw128(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_pair(&empty_bar[s]);   // frees this stage in BOTH CTAs
+        }
+        umma_commit_pair(&tfull_bar[as]);    // accumulator complete, both CTAs
+      }
+    }
+  } else if (warp >= GEMM_EPI_WARP0) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int ew = warp - GEMM_EPI_WARP0;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    uint32_t tl = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++tl) {
+      const int m0 = (tile % m_tiles) * (2 * GEMM_BM) + (int)rank * GEMM_BM;
+      const int n0 = (tile / m_tiles) * BN;
+      const uint32_t as = tl & 1;
+      const uint32_t aph = (tl >> 1) & 1;
+      if constexpr (KIND == EPI_RESID) {
+        const int prow = m0 + quarter * 32 + lane;
+        const int pt = (prow < shp.M) ? epi.wm.to_token(prow) : -1;
+        if (pt >= 0) {
+          const float* pr = epi.resid + (size_t)pt * epi.ldo + n0 + half * (BN / 2);
+#pragma unroll
+          for (int q = 0; q < BN / 2; q += 32)
+            if (n0 + half * (BN / 2) + q < shp.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + q));
+        }
+      }
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const int row_base = m0 + quarter * 32;
+      const int row = row_base + lane;
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN + half * (BN / 2);
+      float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET) + ew * (32 * STG_LD);
+#pragma unroll 1
+      for (int c = 0; c < BN / 2; c += 32) {
+        const int col0 = n0 + half * (BN / 2) + c;
+        if (col0 >= shp.N) break;  // warp-uniform
+        float rv[32];
+        int my_t = -1;
+        if constexpr (KIND == EPI_RESID) epilogue_resid_load(epi, row_base, col0, lane, shp.M, shp.N, rv, my_t);
+        uint32_t acc[32];
+        tmem_ld_32x32(taddr + c, acc);
+        tmem_ld_wait();
+        bool direct = epi_is_direct<KIND>();
+        if constexpr (KIND == EPI_QKV) direct = (col0 >= 2 * epi.D) && (col0 + 32 <= shp.N);
+        if (direct) {
+          epilogue_store<KIND>(epi, row, col0, acc, shp.M, shp.N);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) stg[lane * STG_LD + i] = __uint_as_float(acc[i]);
+          __syncwarp();
+          if constexpr (KIND == EPI_RESID)
+            epilogue_resid_finish(epi, stg, col0, lane, shp.N, rv, my_t);
+          else
+            epilogue_rows<KIND>(epi, stg, row_base, col0, lane, shp.M, shp.N);
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tempty_bar[as]), 0));
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();   // nobody leaves (or frees TMEM) while the peer may still touch this CTA's smem / barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+  }
+}
+
 }  // namespace cra5
