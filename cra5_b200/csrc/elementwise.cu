@@ -43,12 +43,68 @@ __global__ void __launch_bounds__(256) frame_to_patches_kernel(const float* __re
   }
 }
 
+// specialised for a compile-time patch width (PW = 10 for ERA5): 128-bit loads of the NCHW rows, 128-bit stores of the
+// patch-major rows, constant-divisor index arithmetic.
+template <int TOK, int CH, int PW>
+__global__ void __launch_bounds__(256) frame_to_patches_vec_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                                   const float* __restrict__ mean,
+                                                                   const float* __restrict__ std_, int C, int H, int W,
+                                                                   int Wp, int cs_pad) {
+  constexpr int RUN = TOK * PW;       // floats per channel row segment (80)
+  constexpr int RUN4 = RUN / 4;
+  constexpr int LD = RUN + 1;         // padded smem row
+  __shared__ float tile[CH * LD];
+  const int j0 = blockIdx.x * TOK;
+  const int h = blockIdx.y;
+  const int c0 = blockIdx.z * CH;
+  const int nch = min(CH, C - c0);
+  for (int e = threadIdx.x; e < nch * RUN4; e += blockDim.x) {
+    const int cl = e / RUN4, w4 = e - cl * RUN4;
+    const int c = c0 + cl;
+    float4 v = *reinterpret_cast<const float4*>(x + ((size_t)c * H + h) * W + (size_t)j0 * PW + 4 * w4);
+    if (mean != nullptr) {
+      const float m = mean[c], sd = std_[c];
+      v.x = (v.x - m) / sd; v.y = (v.y - m) / sd; v.z = (v.z - m) / sd; v.w = (v.w - m) / sd;
+    }
+    float* t = tile + cl * LD + 4 * w4;
+    t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+  }
+  __syncthreads();
+  const int seg = nch * PW;           // contiguous output run per token (bf16), multiple of 2
+  const int seg8 = seg / 8;
+  for (int e = threadIdx.x; e < TOK * seg8; e += blockDim.x) {
+    const int jl = e / seg8, q0 = (e - jl * seg8) * 8;
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int qa = q0 + 2 * k, qb = qa + 1;
+      const int ca = qa / PW, sa = qa - ca * PW, cb = qb / PW, sb = qb - cb * PW;
+      w[k] = pack_bf16x2(tile[ca * LD + jl * PW + sa], tile[cb * LD + jl * PW + sb]);
+    }
+    *reinterpret_cast<uint4*>(out + ((size_t)h * Wp + j0 + jl) * cs_pad + (size_t)c0 * PW + q0) =
+        make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  // tail of the run when nch * PW is not a multiple of 8 (last channel block of e.g. 69 channels)
+  for (int e = threadIdx.x + seg8 * 8; e < seg; e += blockDim.x) {
+    const int ca = e / PW, sa = e - ca * PW;
+#pragma unroll
+    for (int jl = 0; jl < TOK; ++jl)
+      out[((size_t)h * Wp + j0 + jl) * cs_pad + (size_t)c0 * PW + e] = __float2bfloat16(tile[ca * LD + jl * PW + sa]);
+  }
+}
+
 void frame_to_patches(cudaStream_t st, const float* x, __nv_bfloat16* out, const float* mean, const float* std_,
                       int C, int H, int W, int Wp, int pw, int cs_pad) {
   constexpr int TOK = 8, CH = 64;
   CRA5_CHECK(Wp % TOK == 0, ERR_INVALID, "unsupported geometry: patches per row must be a multiple of 8");
   CRA5_CHECK(Wp * pw <= W, ERR_INVALID, "frame_to_patches: geometry");
   dim3 grid(Wp / TOK, H, (C + CH - 1) / CH);
+  if (pw == 10 && (W & 3) == 0 && (cs_pad & 7) == 0) {
+    LaunchScope scope(st, "frame_to_patches", 0.0, 4.0 * C * H * (double)W + 2.0 * H * (double)Wp * C * pw);
+    frame_to_patches_vec_kernel<TOK, CH, 10><<<grid, 256, 0, st>>>(x, out, mean, std_, C, H, W, Wp, cs_pad);
+    CRA5_CUDA(cudaGetLastError());
+    return;
+  }
   const size_t smem = (size_t)CH * TOK * pw * sizeof(float);
   CRA5_CHECK(smem <= 48 * 1024, ERR_INVALID, "unsupported geometry: patch width too large");
   LaunchScope scope(st, "frame_to_patches", 0.0, 4.0 * C * H * (double)W + 2.0 * H * (double)Wp * C * pw);
@@ -101,10 +157,69 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __rest
   }
 }
 
+// vectorised variant for D % 128 == 0 (the 1024-wide trunk): each lane owns float4 groups at columns 4*lane + 128*i, so
+// every load is a 512-byte warp transaction and every store 256 bytes.
+template <int NV>  // NV = D / 128 float4 groups per lane
+__global__ void __launch_bounds__(256) layernorm_bf16_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float eps,
+                                                                 __nv_bfloat16* __restrict__ out, int rows_out, WinMap wm) {
+  constexpr int D = NV * 128;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows_out) return;
+  uint2* o = reinterpret_cast<uint2*>(out + (size_t)warp * D);
+  const int t = wm.to_token(warp);
+  if (t < 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) o[lane + 32 * i] = make_uint2(0u, 0u);
+    return;
+  }
+  const float4* r = reinterpret_cast<const float4*>(x + (size_t)t * D);
+  float4 v[NV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = r[lane + 32 * i];
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o_ = 16; o_ > 0; o_ >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o_);
+  const float mean = sum * (1.0f / D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    sq += (a * a + b * b) + (c * c + d * d);
+  }
+#pragma unroll
+  for (int o_ = 16; o_ > 0; o_ >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o_);
+  const float rstd = rsqrtf(sq * (1.0f / D) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(g4 + lane + 32 * i), b = __ldg(b4 + lane + 32 * i);
+    uint2 u;
+    u.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+    u.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+    o[lane + 32 * i] = u;
+  }
+}
+
 void layernorm_bf16(cudaStream_t st, const float* x, const float* gamma, const float* beta, float eps,
                     __nv_bfloat16* out, int rows_out, int D, const WinMap& wm) {
   const int blocks = (rows_out + 7) / 8;
   LaunchScope scope(st, "layernorm_bf16", 0.0, 6.0 * rows_out * (double)D);
+  if (D == 1024) {
+    layernorm_bf16_vec_kernel<8><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, rows_out, wm);
+    CRA5_CUDA(cudaGetLastError());
+    return;
+  }
+  if (D == 128) {
+    layernorm_bf16_vec_kernel<1><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, rows_out, wm);
+    CRA5_CUDA(cudaGetLastError());
+    return;
+  }
   if (D <= 128)
     layernorm_bf16_kernel<4><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, rows_out, D, wm);
   else if (D <= 512)

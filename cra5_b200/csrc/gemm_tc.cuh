@@ -475,8 +475,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ===================== TMA producer =====================
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % m_tiles) * GEMM_BM;
-        const int n0 = (tile / m_tiles) * BN;
+        const int m0 = (tile / n_tiles) * GEMM_BM;   // n fastest: CTAs running together share the A tile
+        const int n0 = (tile % n_tiles) * BN;
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const int s = it % GEMM_STAGES;
           const uint32_t ph = (it / GEMM_STAGES) & 1;
@@ -542,8 +542,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = ew >> 2;                  // which half of the columns
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
-      const int m0 = (tile % m_tiles) * GEMM_BM;
-      const int n0 = (tile / m_tiles) * BN;
+      const int m0 = (tile / n_tiles) * GEMM_BM;
+      const int n0 = (tile % n_tiles) * BN;
       const uint32_t as = tl & 1;
       const uint32_t aph = (tl >> 1) & 1;
       if constexpr (KIND == EPI_RESID) {
@@ -677,8 +677,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // ===================== TMA producer (both CTAs) =====================
       uint32_t it = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
-        const int m0 = (tile % m_tiles) * (2 * GEMM_BM) + (int)rank * GEMM_BM;
-        const int n0 = (tile / m_tiles) * BN + (int)rank * (BN / 2);
+        const int m0 = (tile / n_tiles) * (2 * GEMM_BM) + (int)rank * GEMM_BM;
+        const int n0 = (tile % n_tiles) * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const int s = it % ST;
           const uint32_t ph = (it / ST) & 1;
@@ -743,8 +743,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int half = ew >> 2;
     uint32_t tl = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++tl) {
-      const int m0 = (tile % m_tiles) * (2 * GEMM_BM) + (int)rank * GEMM_BM;
-      const int n0 = (tile / m_tiles) * BN;
+      const int m0 = (tile / n_tiles) * (2 * GEMM_BM) + (int)rank * GEMM_BM;
+      const int n0 = (tile % n_tiles) * BN;
       const uint32_t as = tl & 1;
       const uint32_t aph = (tl >> 1) & 1;
       if constexpr (KIND == EPI_RESID) {
