@@ -283,9 +283,17 @@ constexpr int STG_LD = 33;  // padded row stride (words): conflict-free both for
 __device__ __forceinline__ void store_rows_bf16x2(const float* stg, __nv_bfloat16* base, size_t ld, int rows_valid,
                                                   int lane, float b0, float b1, float scale) {
   const int half = lane >> 4, l2 = (lane & 15) * 2;
-  for (int rr = half; rr < rows_valid; rr += 2) {
-    const float v0 = (stg[rr * STG_LD + l2] + b0) * scale, v1 = (stg[rr * STG_LD + l2 + 1] + b1) * scale;
-    *reinterpret_cast<uint32_t*>(base + (size_t)rr * ld + l2) = pack_bf16x2(v0, v1);
+  float a0[16], a1[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {  // all shared-memory reads first: independent, so their latencies overlap
+    a0[k] = stg[(2 * k + half) * STG_LD + l2];
+    a1[k] = stg[(2 * k + half) * STG_LD + l2 + 1];
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int rr = 2 * k + half;
+    if (rr < rows_valid)
+      *reinterpret_cast<uint32_t*>(base + (size_t)rr * ld + l2) = pack_bf16x2((a0[k] + b0) * scale, (a1[k] + b1) * scale);
   }
 }
 
@@ -319,15 +327,25 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& p, const float* s
     const float b0 = (p.bias != nullptr && col < N) ? __ldg(p.bias + col) : 0.f;
     const float b1 = (p.bias != nullptr && col + 1 < N) ? __ldg(p.bias + col + 1) : 0.f;
     const bool pair_ok = (col + 1 < N) && ((p.ldo & 1) == 0);
-    for (int rr = half; rr < rows_valid; rr += 2) {
-      float v0 = stg[rr * STG_LD + l2] + b0, v1 = stg[rr * STG_LD + l2 + 1] + b1;
+    float a0[16], a1[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {  // all shared-memory reads first: independent, so their latencies overlap
+      a0[k] = stg[(2 * k + half) * STG_LD + l2];
+      a1[k] = stg[(2 * k + half) * STG_LD + l2 + 1];
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int rr = 2 * k + half;
+      float v0 = a0[k] + b0, v1 = a1[k] + b1;
       if constexpr (KIND == EPI_GELU_BF16) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); }
-      __nv_bfloat16* o = p.out_bf16 + (size_t)(row_base + rr) * p.ldo + col;
-      if (pair_ok) {
-        *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(v0, v1);
-      } else {
-        if (col < N) o[0] = __float2bfloat16(v0);
-        if (col + 1 < N) o[1] = __float2bfloat16(v1);
+      if (rr < rows_valid) {
+        __nv_bfloat16* o = p.out_bf16 + (size_t)(row_base + rr) * p.ldo + col;
+        if (pair_ok) {
+          *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(v0, v1);
+        } else {
+          if (col < N) o[0] = __float2bfloat16(v0);
+          if (col + 1 < N) o[1] = __float2bfloat16(v1);
+        }
       }
     }
   } else if constexpr (KIND == EPI_QKV) {
@@ -477,6 +495,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / n_tiles) * GEMM_BM;   // n fastest: CTAs running together share the A tile
         const int n0 = (tile % n_tiles) * BN;
+        int pe_j0[8], pe_h0[8], pe_nbox = 0, pe_r = 0, pe_kc = 0, pe_cs0 = 0;
+        if (shp.a_mode == A_PATCH) {
+          pe_nbox = GEMM_BM / shp.pe_box_rows;  // <= 8 (box rows >= 16 for the supported geometries, checked on the host)
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int t = m0 + g * shp.pe_box_rows;
+            const int i = t / shp.pe_Wp;
+            pe_j0[g] = t - i * shp.pe_Wp;
+            pe_h0[g] = shp.pe_sh * i;
+          }
+        }
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const int s = it % GEMM_STAGES;
           const uint32_t ph = (it / GEMM_STAGES) & 1;
@@ -487,14 +516,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (shp.a_mode == A_PLAIN) {
             tma_load_2d(sa, &tmA, &full_bar[s], kb * GEMM_BK, m0);
           } else if (shp.a_mode == A_PATCH) {
-            const int r = kb / shp.pe_kpr;
-            const int cs0 = (kb - r * shp.pe_kpr) * GEMM_BK;
-            const int nbox = GEMM_BM / shp.pe_box_rows;
-            for (int g = 0; g < nbox; ++g) {
-              const int t = m0 + g * shp.pe_box_rows;
-              const int i = t / shp.pe_Wp, j0 = t - i * shp.pe_Wp;
-              tma_load_3d(sa + g * shp.pe_box_rows * 128, &tmA, &full_bar[s], cs0, j0, shp.pe_sh * i + r);
-            }
+            // (the kernel row r and column block advance incrementally; box coordinates were hoisted per tile)
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              if (g < pe_nbox)
+                tma_load_3d(sa + g * shp.pe_box_rows * 128, &tmA, &full_bar[s], pe_cs0, pe_j0[g], pe_h0[g] + pe_r);
+            if (++pe_kc == shp.pe_kpr) { pe_kc = 0; pe_cs0 = 0; ++pe_r; } else { pe_cs0 += GEMM_BK; }
           } else {  // A_CONCAT
             const int k0 = kb * GEMM_BK;
             if (k0 < shp.cc_D)
@@ -679,6 +706,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
         const int m0 = (tile / n_tiles) * (2 * GEMM_BM) + (int)rank * GEMM_BM;
         const int n0 = (tile % n_tiles) * BN + (int)rank * (BN / 2);
+        int pe_j0[8], pe_h0[8], pe_nbox = 0, pe_r = 0, pe_kc = 0, pe_cs0 = 0;
+        if (shp.a_mode == A_PATCH) {
+          pe_nbox = GEMM_BM / shp.pe_box_rows;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int t = m0 + g * shp.pe_box_rows;
+            const int i = t / shp.pe_Wp;
+            pe_j0[g] = t - i * shp.pe_Wp;
+            pe_h0[g] = shp.pe_sh * i;
+          }
+        }
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const int s = it % ST;
           const uint32_t ph = (it / ST) & 1;
@@ -690,14 +728,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (shp.a_mode == A_PLAIN) {
             tma_load_2d_pair(sa, &tmA, fb, kb * GEMM_BK, m0);
           } else if (shp.a_mode == A_PATCH) {
-            const int r = kb / shp.pe_kpr;
-            const int cs0 = (kb - r * shp.pe_kpr) * GEMM_BK;
-            const int nbox = GEMM_BM / shp.pe_box_rows;
-            for (int g = 0; g < nbox; ++g) {
-              const int t = m0 + g * shp.pe_box_rows;
-              const int i = t / shp.pe_Wp, j0 = t - i * shp.pe_Wp;
-              tma_load_3d_pair(sa + g * shp.pe_box_rows * 128, &tmA, fb, cs0, j0, shp.pe_sh * i + r);
-            }
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              if (g < pe_nbox)
+                tma_load_3d_pair(sa + g * shp.pe_box_rows * 128, &tmA, fb, pe_cs0, pe_j0[g], pe_h0[g] + pe_r);
+            if (++pe_kc == shp.pe_kpr) { pe_kc = 0; pe_cs0 = 0; ++pe_r; } else { pe_cs0 += GEMM_BK; }
           } else {  // A_CONCAT
             const int k0 = kb * GEMM_BK;
             if (k0 < shp.cc_D)

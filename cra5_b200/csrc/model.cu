@@ -50,9 +50,9 @@ Model::Model(const cra5_config& c) : cfg_(c) {
   kpr = ceil_div(CS, GEMM_BK);
   cs_pad = (int)align_up((size_t)CS, 8);
   box_rows = 0;
-  for (int b = 128; b >= 8; b >>= 1)
+  for (int b = 128; b >= 16; b >>= 1)   // >= 16 rows per TMA box keeps a 128-row tile within 8 boxes
     if (Wg % b == 0) { box_rows = b; break; }
-  CRA5_CHECK(box_rows != 0, ERR_INVALID, "unsupported geometry: patches per row must be a multiple of 8");
+  CRA5_CHECK(box_rows != 0, ERR_INVALID, "unsupported geometry: patches per row must be a multiple of 16");
   nB = c.patch_h - c.stride_h;
   nA = c.stride_h - nB;
   spc_y_ = c.streams_per_channel_y > 0 ? c.streams_per_channel_y : 16;
