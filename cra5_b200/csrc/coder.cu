@@ -18,7 +18,7 @@ RansCoder::RansCoder(size_t max_symbols, int max_channels)
   CRA5_CUDA(cudaMalloc(&err_, sizeof(int)));
   CRA5_CUDA(cudaMemset(err_, 0, sizeof(int)));
   CRA5_CUDA(cudaMallocHost(&host_meta_, ((size_t)max_streams_ + 4) * 4));
-  host_stage_cap_ = payload_cap_ + (size_t)max_streams_ * 4;
+  host_stage_cap_ = payload_cap_ + (size_t)max_streams_ * 4 + 64;
   CRA5_CUDA(cudaMallocHost(&host_stage_, host_stage_cap_));
   CRA5_CUDA(cudaMalloc(&lut_, (size_t)256 * 257 * 2));
 }
@@ -44,8 +44,30 @@ static uint32_t get_u32(const uint8_t* p) {
 size_t RansCoder::encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx, const CdfTable& tab, int n_channels,
                          int L, int spc, uint8_t* host_out, size_t host_cap) {
   CRA5_CHECK(tab.ready(), ERR_STATE, "Uninitialized CDFs. Run update() first");
-  CRA5_CHECK(spc >= 1 && spc <= CR5B_MAX_SPC, ERR_INVALID, "streams per channel must be in [1, 64]");
+  CRA5_CHECK(spc >= 0 && spc <= CR5B_MAX_SPC, ERR_INVALID, "streams per channel must be in [0, 64]");
   CRA5_CHECK(n_channels >= 0 && L >= 0, ERR_INVALID, "rans_encode: negative size");
+  if (spc == 0) {
+    // reference format: the whole tensor as ONE sequential stream, no container -- byte-identical to what
+    // RansEncoder.encode_with_indexes returns (rans_interface.cpp:202-213). One GPU thread; interop, not throughput.
+    const size_t n = (size_t)n_channels * L;
+    CRA5_CHECK(n <= max_symbols_ && n < (size_t)1 << 30, ERR_INVALID, "rans_encode: tensor larger than the coder was sized for");
+    const int cap_words = (int)(2 * n + 6);
+    CRA5_CHECK((size_t)cap_words <= scratch_words_, ERR_INTERNAL, "rans_encode: scratch sizing");
+    rans_encode(st, sym, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, 1, (int)n, 1, L > 0 ? L : 1,
+                scratch_, cap_words, lengths_, offsets_, payload_, err_);
+    CRA5_CUDA(cudaMemcpyAsync(host_meta_, lengths_, 4, cudaMemcpyDeviceToHost, st));
+    CRA5_CUDA(cudaMemcpyAsync(host_meta_ + 1, err_, 4, cudaMemcpyDeviceToHost, st));
+    CRA5_CUDA(cudaStreamSynchronize(st));
+    if (host_meta_[1] != 0) {
+      CRA5_CUDA(cudaMemsetAsync(err_, 0, sizeof(int), st));
+      throw Error(ERR_INTERNAL, "rans_encode: scratch overflow");
+    }
+    const uint32_t total = host_meta_[0];
+    CRA5_CHECK(host_cap >= total, ERR_INVALID, "rans_encode: output buffer too small");
+    CRA5_CUDA(cudaMemcpyAsync(host_out, payload_, total, cudaMemcpyDeviceToHost, st));
+    CRA5_CUDA(cudaStreamSynchronize(st));
+    return total;
+  }
   const int n_streams = n_channels * spc;
   CRA5_CHECK((size_t)n_channels * L <= max_symbols_ && n_streams <= max_streams_, ERR_INVALID,
              "rans_encode: tensor larger than the coder was sized for");
@@ -56,8 +78,8 @@ size_t RansCoder::encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx
   CRA5_CHECK((size_t)n_streams * cap_words <= scratch_words_, ERR_INTERNAL, "rans_encode: scratch sizing");
   uint32_t total = 0;
   if (n_streams > 0 && L > 0) {
-    rans_encode(st, sym, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, n_channels, L, spc, scratch_,
-                cap_words, lengths_, offsets_, payload_, err_);
+    rans_encode(st, sym, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, n_channels, L, spc, L > 0 ? L : 1,
+                scratch_, cap_words, lengths_, offsets_, payload_, err_);
     CRA5_CUDA(cudaMemcpyAsync(host_meta_, lengths_, (size_t)n_streams * 4, cudaMemcpyDeviceToHost, st));
     CRA5_CUDA(cudaMemcpyAsync(host_meta_ + n_streams, offsets_ + n_streams, 4, cudaMemcpyDeviceToHost, st));
     CRA5_CUDA(cudaMemcpyAsync(host_meta_ + n_streams + 1, err_, 4, cudaMemcpyDeviceToHost, st));
@@ -90,9 +112,32 @@ size_t RansCoder::encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx
 void RansCoder::decode(cudaStream_t st, const uint8_t* bytes, size_t len, const uint8_t* idx, const CdfTable& tab,
                        int n_channels, int L, int32_t* sym_out, const float* mu, const float* median, float* val_out) {
   CRA5_CHECK(tab.ready(), ERR_STATE, "Uninitialized CDFs. Run update() first");
-  CRA5_CHECK(bytes != nullptr && len >= CR5B_HEADER, ERR_BITSTREAM, "bitstream: truncated header");
-  CRA5_CHECK(memcmp(bytes, "CR5B", 4) == 0, ERR_BITSTREAM,
-             "bitstream: not a CR5B chunk-parallel stream (reference single-stream format is not accepted here)");
+  CRA5_CHECK(bytes != nullptr && len >= 8, ERR_BITSTREAM, "bitstream: truncated");
+  if (memcmp(bytes, "CR5B", 4) != 0) {
+    // no container magic: a reference-format stream (one sequential rANS stream per tensor, as CRA5 .bin archives
+    // written by the PyTorch reference hold) -- decoded by a single thread
+    const size_t n = (size_t)n_channels * L;
+    CRA5_CHECK((len & 3) == 0, ERR_BITSTREAM, "bitstream: reference stream length must be a multiple of 4");
+    CRA5_CHECK(n <= max_symbols_ && len <= payload_cap_ && len <= host_stage_cap_, ERR_BITSTREAM, "bitstream: too large");
+    if (n == 0) return;
+    CRA5_CUDA(cudaStreamSynchronize(st));
+    memcpy(host_stage_, bytes, len);
+    uint32_t* offs = reinterpret_cast<uint32_t*>(host_stage_ + ((len + 15) & ~size_t(15)));
+    offs[0] = 0;
+    offs[1] = (uint32_t)len;
+    CRA5_CUDA(cudaMemcpyAsync(payload_, host_stage_, len, cudaMemcpyHostToDevice, st));
+    CRA5_CUDA(cudaMemcpyAsync(offsets_, offs, 8, cudaMemcpyHostToDevice, st));
+    rans_decode(st, payload_, offsets_, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, nullptr, 0, 1,
+                (int)n, 1, L > 0 ? L : 1, sym_out, mu, median, val_out, err_);
+    CRA5_CUDA(cudaMemcpyAsync(host_meta_, err_, 4, cudaMemcpyDeviceToHost, st));
+    CRA5_CUDA(cudaStreamSynchronize(st));
+    if (host_meta_[0] != 0) {
+      CRA5_CUDA(cudaMemsetAsync(err_, 0, sizeof(int), st));
+      throw Error(ERR_BITSTREAM, "bitstream: stream exhausted while decoding (corrupt data or wrong tensor shape)");
+    }
+    return;
+  }
+  CRA5_CHECK(len >= CR5B_HEADER, ERR_BITSTREAM, "bitstream: truncated header");
   CRA5_CHECK(bytes[4] == 1, ERR_BITSTREAM, "bitstream: unsupported version");
   const uint32_t nc = get_u32(bytes + 8), l = get_u32(bytes + 12), spc = get_u32(bytes + 16),
                  ns = get_u32(bytes + 20);
@@ -130,7 +175,7 @@ void RansCoder::decode(cudaStream_t st, const uint8_t* bytes, size_t len, const 
     lut_rows = tab.rows;
   }
   rans_decode(st, payload_, offsets_, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, lut, lut_rows,
-              n_channels, L, (int)spc, sym_out, mu, median, val_out, err_);
+              n_channels, L, (int)spc, L > 0 ? L : 1, sym_out, mu, median, val_out, err_);
   CRA5_CUDA(cudaMemcpyAsync(host_meta_, err_, 4, cudaMemcpyDeviceToHost, st));
   CRA5_CUDA(cudaStreamSynchronize(st));
   if (host_meta_[0] != 0) {

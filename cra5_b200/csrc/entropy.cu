@@ -167,8 +167,9 @@ constexpr int RANS_THREADS = 32;   // one warp per CTA: the chains are latency b
 __global__ void __launch_bounds__(RANS_THREADS)
 rans_encode_kernel(const int32_t* __restrict__ sym, const uint8_t* __restrict__ idx, int index_is_channel,
                    const int32_t* __restrict__ cdf, int cdf_stride, const int32_t* __restrict__ cdf_len,
-                   const int32_t* __restrict__ offset, int n_channels, int L, int spc, uint32_t* __restrict__ scratch,
-                   int cap_words, uint32_t* __restrict__ lengths, int* __restrict__ err) {
+                   const int32_t* __restrict__ offset, int n_channels, int L, int spc, int chan_len,
+                   uint32_t* __restrict__ scratch, int cap_words, uint32_t* __restrict__ lengths,
+                   int* __restrict__ err) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_channels * spc) return;
   const int c = s / spc, k = s - c * spc;
@@ -191,7 +192,7 @@ rans_encode_kernel(const int32_t* __restrict__ sym, const uint8_t* __restrict__ 
       const int i = max(i0 - 1 - b, 0);
       pos[b] = base + (size_t)i * spc;
       sy[b] = sym[pos[b]];
-      ci[b] = index_is_channel ? c : (int)idx[pos[b]];
+      ci[b] = index_is_channel ? (int)(pos[b] / (size_t)chan_len) : (int)idx[pos[b]];
     }
 #pragma unroll
     for (int b = 0; b < RANS_BATCH; ++b) {
@@ -294,15 +295,15 @@ __global__ void __launch_bounds__(256) compact_streams_kernel(const uint32_t* __
 }
 
 void rans_encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx, bool index_is_channel, const int32_t* cdf,
-                 int cdf_stride, const int32_t* cdf_len, const int32_t* offset, int n_channels, int L, int spc,
+                 int cdf_stride, const int32_t* cdf_len, const int32_t* offset, int n_channels, int L, int spc, int chan_len,
                  uint32_t* scratch, int cap_words, uint32_t* lengths, uint32_t* offsets, uint8_t* payload, int* err) {
   const int n_streams = n_channels * spc;
   if (n_streams == 0) return;
   {
     LaunchScope scope(st, "rans_encode", 0.0, (double)n_channels * L * (index_is_channel ? 4.0 : 5.0));
     rans_encode_kernel<<<(n_streams + RANS_THREADS - 1) / RANS_THREADS, RANS_THREADS, 0, st>>>(sym, idx, index_is_channel ? 1 : 0, cdf, cdf_stride,
-                                                                cdf_len, offset, n_channels, L, spc, scratch,
-                                                                cap_words, lengths, err);
+                                                                cdf_len, offset, n_channels, L, spc, chan_len,
+                                                                scratch, cap_words, lengths, err);
   }
   CRA5_CUDA(cudaGetLastError());
   {
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(RANS_THREADS)
 rans_decode_kernel(const uint8_t* __restrict__ payload, const uint32_t* __restrict__ offsets,
                    const uint8_t* __restrict__ idx, int index_is_channel, const int32_t* __restrict__ cdf,
                    int cdf_stride, const int32_t* __restrict__ cdf_len, const int32_t* __restrict__ offset,
-                   const uint16_t* __restrict__ lut_g, int lut_rows, int n_channels, int L, int spc,
+                   const uint16_t* __restrict__ lut_g, int lut_rows, int n_channels, int L, int spc, int chan_len,
                    int32_t* __restrict__ sym_out, const float* __restrict__ mu, const float* __restrict__ median,
                    float* __restrict__ val_out, int* __restrict__ err) {
   extern __shared__ uint16_t lut_s[];
@@ -402,8 +403,8 @@ rans_decode_kernel(const uint8_t* __restrict__ payload, const uint32_t* __restri
     for (int b = 0; b < RANS_BATCH; ++b) {  // independent loads first
       const int i = min(i0 + b, count - 1);
       const size_t pos = base + (size_t)i * spc;
-      ci[b] = index_is_channel ? c : (int)idx[pos];
-      mean[b] = (val_out == nullptr) ? 0.f : ((mu != nullptr) ? mu[pos] : median[c]);
+      ci[b] = index_is_channel ? (int)(pos / (size_t)chan_len) : (int)idx[pos];
+      mean[b] = (val_out == nullptr) ? 0.f : ((mu != nullptr) ? mu[pos] : median[ci[b]]);
     }
 #pragma unroll
     for (int b = 0; b < RANS_BATCH; ++b) {
@@ -466,7 +467,7 @@ rans_decode_kernel(const uint8_t* __restrict__ payload, const uint32_t* __restri
 void rans_decode(cudaStream_t st, const uint8_t* payload, const uint32_t* offsets, const uint8_t* idx,
                  bool index_is_channel, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len,
                  const int32_t* offset, const uint16_t* lut, int lut_rows, int n_channels, int L, int spc,
-                 int32_t* sym_out, const float* mu, const float* median, float* val_out, int* err) {
+                 int chan_len, int32_t* sym_out, const float* mu, const float* median, float* val_out, int* err) {
   const int n_streams = n_channels * spc;
   if (n_streams == 0) return;
   size_t smem = 0;
@@ -478,7 +479,7 @@ void rans_decode(cudaStream_t st, const uint8_t* payload, const uint32_t* offset
   LaunchScope scope(st, "rans_decode", 0.0, (double)n_channels * L * (index_is_channel ? 4.0 : 9.0));
   rans_decode_kernel<<<(n_streams + RANS_THREADS - 1) / RANS_THREADS, RANS_THREADS, smem, st>>>(
       payload, offsets, idx, index_is_channel ? 1 : 0, cdf, cdf_stride, cdf_len, offset, lut, stage_rows, n_channels, L,
-      spc, sym_out, mu, median, val_out, err);
+      spc, chan_len, sym_out, mu, median, val_out, err);
   CRA5_CUDA(cudaGetLastError());
 }
 

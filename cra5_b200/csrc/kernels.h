@@ -45,11 +45,11 @@ void dequantize(cudaStream_t st, const int32_t* sym, const float* mu, const floa
                 size_t n);
 void rans_encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx, bool index_is_channel, const int32_t* cdf,
                  int cdf_stride, const int32_t* cdf_len, const int32_t* offset, int n_channels, int L, int spc,
-                 uint32_t* scratch, int cap_words, uint32_t* lengths, uint32_t* offsets, uint8_t* payload, int* err);
+                 int chan_len, uint32_t* scratch, int cap_words, uint32_t* lengths, uint32_t* offsets, uint8_t* payload, int* err);
 void rans_decode(cudaStream_t st, const uint8_t* payload, const uint32_t* offsets, const uint8_t* idx,
                  bool index_is_channel, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len,
                  const int32_t* offset, const uint16_t* lut, int lut_rows, int n_channels, int L, int spc,
-                 int32_t* sym_out, const float* mu, const float* median, float* val_out, int* err);
+                 int chan_len, int32_t* sym_out, const float* mu, const float* median, float* val_out, int* err);
 void build_decode_lut(cudaStream_t st, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len, int rows,
                       uint16_t* lut);
 void scan_lengths(cudaStream_t st, const uint32_t* lengths, int n, uint32_t* offsets);

@@ -146,8 +146,9 @@ void Model::set_cdf(int which, const int32_t* cdf, const int32_t* len, const int
 }
 
 void Model::set_coder(int spc_y, int spc_z) {
-  CRA5_CHECK(spc_y >= 1 && spc_y <= CR5B_MAX_SPC && spc_z >= 1 && spc_z <= CR5B_MAX_SPC, ERR_INVALID,
-             "streams per channel must be in [1, 64]");
+  // 0 selects the reference's single sequential stream (interop with archives / the PyTorch reference)
+  CRA5_CHECK(spc_y >= 0 && spc_y <= CR5B_MAX_SPC && spc_z >= 0 && spc_z <= CR5B_MAX_SPC, ERR_INVALID,
+             "streams per channel must be in [0, 64]");
   spc_y_ = spc_y;
   spc_z_ = spc_z;
 }

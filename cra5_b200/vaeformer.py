@@ -285,7 +285,16 @@ class VAEformer:
                 updated = True
         return updated
 
-    def set_coder(self, streams_per_channel_y: int = 16, streams_per_channel_z: int = 4):
+    def set_coder(self, streams_per_channel_y: int = 16, streams_per_channel_z: int = 4, format: str = None):
+        """entropy-coder layout. Default: CR5B chunk-parallel container (16 / 4 interleaved rANS sub-streams per y / z
+        channel). `format="ref"` (or 0 streams) selects the reference's single sequential stream per tensor: strings are
+        then byte-identical to what compressai.ans would write for the same symbols, and reference-written strings can be
+        decoded (one GPU thread per tensor: interoperability, not throughput). Decoding auto-detects the format."""
+        if format is not None:
+            if format not in ("ref", "cr5b"):
+                raise ValueError(f'Invalid coder format "{format}" (choose "cr5b" or "ref")')
+            if format == "ref":
+                streams_per_channel_y = streams_per_channel_z = 0
         _lib.check(_lib.lib.cra5_model_set_coder(self._handle, streams_per_channel_y, streams_per_channel_z))
         self._spc = (streams_per_channel_y, streams_per_channel_z)
 

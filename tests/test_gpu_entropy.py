@@ -154,12 +154,33 @@ def test_entropy_bottleneck_mode_index_is_channel():
 
 def test_corrupt_streams_are_rejected(tabs):
     t, dev = tabs
-    sym = torch.zeros(64, dtype=torch.int32, device="cuda")
-    idx = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    g = torch.Generator().manual_seed(9)
+    idx = torch.randint(20, 50, (64,), generator=g).to(torch.uint8).cuda()
+    sym = torch.round(torch.randn(64, generator=g) * 20).int().cuda()
     b = gpu_encode(sym, idx, dev, 2, 32, 2)
-    for bad in (b[:10], b"XXXX" + b[4:], b[:-4], b + b"\0\0\0\0"):
+    for bad in (b[:10], b[:-4], b + b"\0\0\0\0", b"CR5B" + b"\x09" + b[5:]):
         with pytest.raises(ValueError):
             gpu_decode(bad, idx, dev, 2, 32)
+    # without the magic the bytes are taken for a reference-format stream: garbage in, garbage (or an error) out
+    try:
+        assert not torch.equal(gpu_decode(b"XXXX" + b[4:], idx, dev, 2, 32), sym)
+    except ValueError:
+        pass
     with pytest.raises(ValueError):
         gpu_decode(b, idx, dev, 2, 33)  # shape mismatch
     assert torch.equal(gpu_decode(b, idx, dev, 2, 32), sym)
+
+
+def test_reference_format_streams_interoperate(tabs):
+    """spc == 0: one sequential stream per tensor, byte-identical to the reference coder (oracle pinned to it), and
+    reference-written streams decode on the GPU"""
+    t, dev = tabs
+    g = torch.Generator().manual_seed(77)
+    n_ch, Lc = 7, 501
+    idx = torch.randint(0, 64, (n_ch * Lc,), generator=g, dtype=torch.int32)
+    sym = torch.round(torch.randn(n_ch * Lc, generator=g) * t.scale_table[idx.long()] * 1.2).int()
+    sym[::29] = (torch.randn(sym[::29].shape, generator=g) * 20000).int()
+    ref_stream = EO.rans_encode(sym, idx, *t.coder_args())             # == compressai.ans output (test_oracle_pins)
+    b = gpu_encode(sym.cuda(), idx.to(torch.uint8).cuda(), dev, n_ch, Lc, 0)
+    assert b == ref_stream
+    assert torch.equal(gpu_decode(ref_stream, idx.to(torch.uint8).cuda(), dev, n_ch, Lc).cpu(), sym)

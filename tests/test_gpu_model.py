@@ -193,4 +193,29 @@ def test_coder_stream_count_knob(ctx):
     net.set_coder(16, 4)
     assert sizes[1] < sizes[4] < sizes[32]
     with pytest.raises(ValueError):
-        net.set_coder(0, 1)
+        net.set_coder(65, 1)
+    with pytest.raises(ValueError):
+        net.set_coder(4, -1)
+    with pytest.raises(ValueError):
+        net.set_coder(format="zip")
+
+
+def test_reference_coder_format_end_to_end(ctx):
+    """format="ref": strings are the reference's own single-stream format -- byte-identical to the reference coder fed
+    the GPU's symbols -- and a stream written by the reference coder decodes to the same latent"""
+    net, cfg = ctx.net, ctx.cfg
+    net.set_coder(format="ref")
+    try:
+        out = net.compress_from_latent(ctx.y_g)
+        ysym, yidx, zsym = net.tap("y_symbols").cpu(), net.tap("y_indexes").cpu().int(), net.tap("z_symbols").cpu()
+        assert torch.equal(ysym, ctx.ysym_g) and torch.equal(zsym, ctx.zsym_g)
+        zidx = EO.eb_indexes((1, cfg.z_chans, *cfg.hyper_grid)).reshape(-1)
+        assert out["strings"][0][0] == EO.rans_encode(ysym, yidx, *ctx.codec.gc.coder_args())
+        assert out["strings"][1][0] == EO.rans_encode(zsym, zidx, *ctx.codec.eb.coder_args())
+        y_hat = net.decompress(out["strings"], out["z_shape"], return_format="latent")
+        assert torch.equal(y_hat.cpu(), ysym.reshape(ctx.mu_g.shape).float() + ctx.mu_g)
+    finally:
+        net.set_coder(16, 4)
+    # auto-detection: the chunked container still decodes after the switch back
+    y_hat2 = net.decompress(ctx.out["strings"], ctx.out["z_shape"], return_format="latent")
+    assert torch.equal(y_hat2.cpu(), y_hat.cpu())
