@@ -153,6 +153,14 @@ int cra5_latent_quantized(cra5_model* m, const float* y, float* y_hat, void* str
   });
 }
 
+int cra5_latent_likelihoods(cra5_model* m, const float* y, float* y_hat, float* y_lik, float* z_lik, void* stream) {
+  return guarded([&] {
+    MODEL_GUARD(m);
+    CRA5_CHECK(y != nullptr, ERR_INVALID, "null tensor");
+    m->impl->latent_likelihoods(y, y_hat, y_lik, z_lik, static_cast<cudaStream_t>(stream));
+  });
+}
+
 int cra5_latent_to_bin(cra5_model* m, const float* y, const uint8_t** y_bytes, uint64_t* y_len, const uint8_t** z_bytes,
                        uint64_t* z_len, void* stream) {
   return guarded([&] {

@@ -124,6 +124,82 @@ void dequantize(cudaStream_t st, const int32_t* sym, const float* mu, const floa
   CRA5_CUDA(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------------ likelihoods
+// Rate-estimation outputs of VAEformer.forward / encode_latent('quantized') (vaeformer.py:284-290, 314-319):
+//   GaussianConditional: y_hat = round(y - mu) + mu; p = Phi((.5 - |y_hat - mu|)/s) - Phi((-.5 - |y_hat - mu|)/s),
+//                        s = max(sigma, 0.11), Phi(x) = erfc(-x/sqrt 2)/2, floored at 1e-9   (entropy_models.py:645-677)
+__global__ void __launch_bounds__(256)
+gc_likelihood_kernel(const float* __restrict__ y, const float* __restrict__ sigma, const float* __restrict__ mu,
+                     float scale_bound, float lik_bound, float* __restrict__ y_hat, float* __restrict__ lik, size_t n) {
+  const float c = -0.70710678118654752440f;  // float(-(2 ** -0.5)), entropy_models.py:600
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const float m = mu[e];
+    const float yh = __fadd_rn(rintf(__fsub_rn(y[e], m)), m);
+    const float v = fabsf(__fsub_rn(yh, m));
+    const float sc = fmaxf(sigma[e], scale_bound);
+    const float upper = 0.5f * erfcf(c * __fdiv_rn(__fsub_rn(0.5f, v), sc));
+    const float lower = 0.5f * erfcf(c * __fdiv_rn(__fsub_rn(-0.5f, v), sc));
+    if (y_hat != nullptr) y_hat[e] = yh;
+    lik[e] = fmaxf(__fsub_rn(upper, lower), lik_bound);
+  }
+}
+
+void gc_likelihood(cudaStream_t st, const float* y, const float* sigma, const float* mu, float scale_bound,
+                   float lik_bound, float* y_hat, float* lik, size_t n) {
+  if (n == 0) return;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+  LaunchScope scope(st, "gc_likelihood", 0.0, (double)n * 20.0);
+  gc_likelihood_kernel<<<blocks, 256, 0, st>>>(y, sigma, mu, scale_bound, lik_bound, y_hat, lik, n);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+//   EntropyBottleneck: per-channel factorised density, p = sigmoid(F(z+.5)) - sigmoid(F(z-.5)) with the 1-3-3-3-3-1
+//   softplus/tanh cumulative F (entropy_models.py:434-463). `packed` holds, per channel, softplus(matrix_k), bias_k and
+//   tanh(factor_k) of the five layers: m0[3] b0[3] f0[3] | (m[9] b[3] f[3]) x3 | m4[3] b4[1]  = 58 floats.
+constexpr int EB_PACK = 58;
+__device__ __forceinline__ float eb_logits(const float* __restrict__ p, float v) {
+  float a[3], b[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float l = fmaf(p[i], v, p[3 + i]);
+    a[i] = fmaf(p[6 + i], tanhf(l), l);
+  }
+  p += 9;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float l = fmaf(p[3 * i + 2], a[2], fmaf(p[3 * i + 1], a[1], p[3 * i] * a[0])) + p[9 + i];
+      b[i] = fmaf(p[12 + i], tanhf(l), l);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) a[i] = b[i];
+    p += 15;
+  }
+  return fmaf(p[2], a[2], fmaf(p[1], a[1], p[0] * a[0])) + p[3];
+}
+
+__global__ void __launch_bounds__(256)
+eb_likelihood_kernel(const float* __restrict__ z_hat, const float* __restrict__ packed, int L, float lik_bound,
+                     float* __restrict__ lik, size_t n) {
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const float* p = packed + (e / L) * EB_PACK;
+    const float v = z_hat[e];
+    const float lo = eb_logits(p, v - 0.5f), up = eb_logits(p, v + 0.5f);
+    const float s_up = 1.0f / (1.0f + expf(-up)), s_lo = 1.0f / (1.0f + expf(-lo));
+    lik[e] = fmaxf(s_up - s_lo, lik_bound);
+  }
+}
+
+void eb_likelihood(cudaStream_t st, const float* z_hat, const float* packed, int L, float lik_bound, float* lik,
+                   size_t n) {
+  if (n == 0) return;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+  LaunchScope scope(st, "eb_likelihood", 0.0, (double)n * 8.0);
+  eb_likelihood_kernel<<<blocks, 256, 0, st>>>(z_hat, packed, L, lik_bound, lik, n);
+  CRA5_CUDA(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------------------------------------ rANS primitives
 constexpr uint32_t RANS_PRECISION = 16;      // rans_interface.cpp:49
 constexpr uint32_t RANS_BYPASS_BITS = 4;     // rans_interface.cpp:51

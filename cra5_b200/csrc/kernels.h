@@ -43,6 +43,10 @@ void gc_quantize_index(cudaStream_t st, const float* y, const float* sigma, cons
 void eb_quantize(cudaStream_t st, const float* z, const float* median, int L, int32_t* sym, float* z_hat, size_t n);
 void dequantize(cudaStream_t st, const int32_t* sym, const float* mu, const float* median, int L, float* out,
                 size_t n);
+void gc_likelihood(cudaStream_t st, const float* y, const float* sigma, const float* mu, float scale_bound,
+                   float lik_bound, float* y_hat, float* lik, size_t n);
+void eb_likelihood(cudaStream_t st, const float* z_hat, const float* packed, int L, float lik_bound, float* lik,
+                   size_t n);
 void rans_encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx, bool index_is_channel, const int32_t* cdf,
                  int cdf_stride, const int32_t* cdf_len, const int32_t* offset, int n_channels, int L, int spc,
                  int chan_len, uint32_t* scratch, int cap_words, uint32_t* lengths, uint32_t* offsets, uint8_t* payload, int* err);

@@ -413,6 +413,26 @@ void Model::latent_quantized(const float* y, float* y_hat, cudaStream_t st) {
                     gc_.rows, SCALE_BOUND, nullptr, nullptr, y_hat, (size_t)c.latent_chans * T);
 }
 
+// eval-mode forward up to the latent (vaeformer.py:314-319): z_hat / z likelihoods from the EntropyBottleneck, then
+// y_hat / y likelihoods from the GaussianConditional fed by h_s(z_hat)
+void Model::latent_likelihoods(const float* y, float* y_hat, float* y_lik, float* z_lik, cudaStream_t st) {
+  const cra5_config& c = cfg_;
+  constexpr float LIK_BOUND = 1e-9f;  // entropy_models.py:111
+  const float* med = (const float*)need("entropy_bottleneck.medians", CRA5_DT_F32, c.z_chans);
+  run_h_a(st, y);
+  eb_quantize(st, z_, med, Th, nullptr, zhat_, (size_t)c.z_chans * Th);
+  if (z_lik != nullptr)
+    eb_likelihood(st, zhat_, (const float*)need("entropy_bottleneck.packed", CRA5_DT_F32, (int64_t)c.z_chans * 58), Th,
+                  LIK_BOUND, z_lik, (size_t)c.z_chans * Th);
+  run_h_s(st, zhat_);
+  const size_t n = (size_t)c.latent_chans * T;
+  if (y_lik != nullptr)
+    gc_likelihood(st, y, params_, params_ + n, SCALE_BOUND, LIK_BOUND, y_hat, y_lik, n);
+  else if (y_hat != nullptr)
+    gc_quantize_index(st, y, nullptr, params_ + n, nullptr, 1, SCALE_BOUND, nullptr, nullptr, y_hat, n);
+  taps_["z_hat"] = TensorRef{zhat_, CRA5_DT_F32, (int64_t)c.z_chans * Th};
+}
+
 // VAEformer.compress_from_latent (vaeformer.py:334-348)
 void Model::latent_to_bin(const float* y, const uint8_t** y_bytes, size_t* y_len, const uint8_t** z_bytes,
                           size_t* z_len, cudaStream_t st) {

@@ -59,6 +59,8 @@ class Model {
   void encode_to_latent(const float* x, float* y, const float* mean, const float* std_, cudaStream_t st);
   void latent_to_reconstruction(const float* y_hat, float* x_hat, cudaStream_t st);
   void latent_quantized(const float* y, float* y_hat, cudaStream_t st);  // encode_latent(type='quantized') tail
+  // same, plus the likelihood tensors of the eval-mode forward (rate estimation); any output may be null
+  void latent_likelihoods(const float* y, float* y_hat, float* y_lik, float* z_lik, cudaStream_t st);
   // entropy stage; returns pinned host buffers owned by the model, valid until the next call
   void latent_to_bin(const float* y, const uint8_t** y_bytes, size_t* y_len, const uint8_t** z_bytes, size_t* z_len,
                      cudaStream_t st);

@@ -247,6 +247,18 @@ class VAEformer:
         self._set("post_quant_conv.weight", bf(sd["post_quant_conv.weight"].reshape(D, lat)))
         self._set("h_a.patch_embed.proj.weight", bf(sd["h_a.patch_embed.proj.weight"].reshape(cfg.hyper_dim, -1)))
         self._set("entropy_bottleneck.medians", sd["entropy_bottleneck.quantiles"][:, 0, 1].float())
+        # factorised-density parameters for the likelihood kernel: softplus(matrix), bias, tanh(factor) per layer, packed
+        # per channel as m0[3] b0[3] f0[3] | (m[9] b[3] f[3]) x3 | m4[3] b4[1]  (entropy_models.py:434-453)
+        zc = cfg.z_chans
+        parts = []
+        for i in range(5):
+            parts.append(torch.nn.functional.softplus(sd[f"entropy_bottleneck._matrix{i}"].float()).reshape(zc, -1))
+            parts.append(sd[f"entropy_bottleneck._bias{i}"].float().reshape(zc, -1))
+            if i < 4:
+                parts.append(torch.tanh(sd[f"entropy_bottleneck._factor{i}"].float()).reshape(zc, -1))
+        packed = torch.cat(parts, dim=1).contiguous()
+        assert packed.shape == (zc, 58)
+        self._set("entropy_bottleneck.packed", packed)
 
     def state_dict(self):
         out = OrderedDict(self._sd)
@@ -331,11 +343,13 @@ class VAEformer:
                                                           _lib.ptr(std), s))
             if type != "quantized":
                 return y, None, None
-            self._require_cdfs()
             y_hat = torch.empty_like(y)
+            y_lik = torch.empty_like(y)
+            self._z_likelihoods = torch.empty((x.shape[0], self.cfg.z_chans, *self.cfg.hyper_grid), device=self.device)
             for b in range(x.shape[0]):
-                _lib.check(_lib.lib.cra5_latent_quantized(self._handle, _lib.ptr(y[b]), _lib.ptr(y_hat[b]), s))
-        return y, y_hat, None
+                _lib.check(_lib.lib.cra5_latent_likelihoods(self._handle, _lib.ptr(y[b]), _lib.ptr(y_hat[b]),
+                                                            _lib.ptr(y_lik[b]), _lib.ptr(self._z_likelihoods[b]), s))
+        return y, y_hat, y_lik
 
     def decode_latent(self, y, type="quantized"):
         y = self._check_y(y)
@@ -387,9 +401,11 @@ class VAEformer:
         return {"x_hat": self.decode_latent(y_hat)}
 
     def forward(self, x):
-        """eval-mode forward (vaeformer.py:302-333) without the likelihood tensors (rate estimation: SURVEY 8f-3)."""
-        y, y_hat, _ = self.encode_latent(x, type="quantized")
-        return {"x_hat": self.decode_latent(y_hat), "likelihoods": {"y": None, "z": None}, "posterior": None}
+        """eval-mode forward (vaeformer.py:302-333): reconstruction through the dequantise path plus the likelihood
+        tensors used for bit-rate estimation (bpp = sum(-log2 p) / values)."""
+        y, y_hat, y_lik = self.encode_latent(x, type="quantized")
+        return {"x_hat": self.decode_latent(y_hat), "likelihoods": {"y": y_lik, "z": self._z_likelihoods},
+                "posterior": None}
 
     __call__ = forward
 

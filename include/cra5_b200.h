@@ -133,6 +133,12 @@ CRA5_API int cra5_encode_to_latent(cra5_model* m, const float* x_dev, float* y_d
  * tail of VAEformer.encode_latent (vaeformer.py:284-290). */
 CRA5_API int cra5_latent_quantized(cra5_model* m, const float* y_dev, float* y_hat_dev, void* stream);
 
+/* Eval-mode forward up to the latent with the rate-estimation outputs: y_hat as above, y_lik (latent, Hg, Wg) =
+ * GaussianConditional likelihoods and z_lik (z_chans, Hh, Wh) = EntropyBottleneck likelihoods, both floored at 1e-9
+ * (vaeformer.py:314-319; entropy_models.py:465-510, 645-677). Any output may be NULL. */
+CRA5_API int cra5_latent_likelihoods(cra5_model* m, const float* y_dev, float* y_hat_dev, float* y_lik_dev,
+                                     float* z_lik_dev, void* stream);
+
 /* y -> {y string, z string}. The returned pointers are pinned host buffers owned by the handle, valid until the next
  * call on it. Replaces VAEformer.compress_from_latent (vaeformer.py:334-348) = cra5_api.latent_to_bin (:73-79), i.e.
  * h_a, EntropyBottleneck.compress, h_s, build_indexes, GaussianConditional.compress and the C++ coder behind them

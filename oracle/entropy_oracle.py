@@ -201,3 +201,27 @@ def entropy_bottleneck_tables(sd) -> Tables:
     tail_mass = torch.sigmoid(lower[:, 0, :1]) + torch.sigmoid(-upper[:, 0, -1:])
     cdf = _pmf_to_cdf(pmf, tail_mass, pmf_length, max_length)
     return Tables(cdf, (pmf_length + 2).int(), offset.int())
+
+
+# ---------------------------------------------------------------------------------------------- likelihoods (forward)
+LIKELIHOOD_BOUND = 1e-9  # entropy_models.py:111
+
+
+def gc_likelihood(y_hat: torch.Tensor, scales: torch.Tensor, means: torch.Tensor) -> torch.Tensor:
+    """GaussianConditional._likelihood + lower bound, entropy_models.py:645-677 (eval mode: inputs already dequantised)"""
+    values = torch.abs(y_hat - means)
+    s = torch.max(scales, torch.tensor(SCALE_BOUND, dtype=scales.dtype))
+    upper = _std_cumulative((0.5 - values) / s)
+    lower = _std_cumulative((-0.5 - values) / s)
+    return torch.max(upper - lower, torch.tensor(LIKELIHOOD_BOUND))
+
+
+def eb_likelihood(sd, z_hat: torch.Tensor) -> torch.Tensor:
+    """EntropyBottleneck.forward likelihood path, entropy_models.py:456-510: per-channel factorised density"""
+    B, C = z_hat.shape[:2]
+    v = z_hat.permute(1, 0, 2, 3).reshape(C, 1, -1)
+    lower = _logits_cumulative(sd, v - 0.5)
+    upper = _logits_cumulative(sd, v + 0.5)
+    lik = torch.sigmoid(upper) - torch.sigmoid(lower)
+    lik = torch.max(lik, torch.tensor(LIKELIHOOD_BOUND))
+    return lik.reshape(C, B, *z_hat.shape[2:]).permute(1, 0, 2, 3).contiguous()

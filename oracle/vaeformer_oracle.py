@@ -233,4 +233,5 @@ class OracleCodec:
         scales, means = h_s(sd, cfg, z_hat)
         y_hat = torch.round(y - means) + means
         return {"x_hat": decode_y(sd, cfg, y_hat), "y": y, "y_hat": y_hat, "z": z, "z_hat": z_hat,
-                "scales": scales, "means": means}
+                "scales": scales, "means": means,
+                "likelihoods": {"y": EO.gc_likelihood(y_hat, scales, means), "z": EO.eb_likelihood(sd, z_hat)}}

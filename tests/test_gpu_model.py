@@ -219,3 +219,28 @@ def test_reference_coder_format_end_to_end(ctx):
     # auto-detection: the chunked container still decodes after the switch back
     y_hat2 = net.decompress(ctx.out["strings"], ctx.out["z_shape"], return_format="latent")
     assert torch.equal(y_hat2.cpu(), y_hat.cpu())
+
+
+def test_forward_likelihoods_match_reference_arithmetic(ctx):
+    """rate-estimation path (VAEformer.forward, vaeformer.py:302-333): likelihood tensors against the oracle's fp32
+    erfc / logistic arithmetic on the GPU's own (y, sigma, mu, z_hat); total bits against the reference's own forward()"""
+    net, cfg = ctx.net, ctx.cfg
+    with torch.no_grad():
+        out = net.forward(ctx.x.cuda())
+    lik_y, lik_z = out["likelihoods"]["y"].cpu(), out["likelihoods"]["z"].cpu()
+    assert tuple(lik_y.shape) == (1, cfg.latent_chans, *cfg.grid) and tuple(lik_z.shape) == (1, cfg.z_chans, *cfg.hyper_grid)
+    y_hat = ctx.ysym_g.reshape(ctx.mu_g.shape).float() + ctx.mu_g
+    ref_y = EO.gc_likelihood(y_hat, ctx.sc_g, ctx.mu_g)
+    ref_z = EO.eb_likelihood(ctx.codec.sd, ctx.zhat_g)
+    # fp32 erfc / tanh / exp of two libraries: elementwise within 1e-6 absolute + 2e-4 relative
+    assert ((lik_y - ref_y).abs() <= 1e-6 + 2e-4 * ref_y).all()
+    assert ((lik_z - ref_z).abs() <= 1e-6 + 2e-4 * ref_z).all()
+    bits_y = float(-torch.log2(lik_y.double()).sum())
+    bits_z = float(-torch.log2(lik_z.double()).sum())
+    assert abs(bits_y - float(-torch.log2(ref_y.double()).sum())) <= 1e-4 * bits_y
+    assert abs(bits_z - float(-torch.log2(ref_z.double()).sum())) <= 1e-4 * bits_z
+    # against the reference's own forward() on the same frame: bf16 transforms move individual symbols, the estimated
+    # rate stays within 1 %
+    assert abs(bits_y - float(ctx.gold["bits_y"])) <= 1e-2 * float(ctx.gold["bits_y"])
+    assert abs(bits_z - float(ctx.gold["bits_z"])) <= 2e-2 * float(ctx.gold["bits_z"])
+    assert torch.isfinite(out["x_hat"]).all() and out["posterior"] is None

@@ -142,6 +142,10 @@ def test_oracle_codec_matches_reference_fixture(name):
         # dequantize path == coded path (reference invariant)
         f = codec.forward(x)
         assert (f["x_hat"] - x_hat).abs().max().item() <= 1e-4
+        # rate-estimation outputs pinned to the reference's forward()
+        _check_sample(g, "lik_y", f["likelihoods"]["y"], 1e-6)
+        _check_sample(g, "lik_z", f["likelihoods"]["z"], 1e-6)
+        assert abs(float(-torch.log2(f["likelihoods"]["y"]).double().sum()) - float(g["bits_y"])) <= 1e-6 * float(g["bits_y"])
 
 
 @pytest.mark.skipif(not ref_import.available(), reason="reference mount not present (GPU box)")

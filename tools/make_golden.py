@@ -148,6 +148,17 @@ def run(name, cfg, wseed, fseed):
     assert o_c["strings"][0][0] == ref_c["strings"][0][0], "y stream differs from the reference coder"
     assert o_c["strings"][1][0] == ref_c["strings"][1][0], "z stream differs from the reference coder"
     close(o_d["x_hat"], ref_d["x_hat"], "x_hat")
+    # rate estimation path (forward() likelihoods, vaeformer.py:302-333): oracle == reference
+    o_f = codec.forward(x)
+    close(o_f["likelihoods"]["y"], ref_fwd["likelihoods"]["y"], "y likelihood", 1e-6)
+    close(o_f["likelihoods"]["z"], ref_fwd["likelihoods"]["z"], "z likelihood", 1e-6)
+    out["bits_y"] = np.array(float(-torch.log2(ref_fwd["likelihoods"]["y"]).double().sum()))
+    out["bits_z"] = np.array(float(-torch.log2(ref_fwd["likelihoods"]["z"]).double().sum()))
+    for tag, tt in (("lik_y", ref_fwd["likelihoods"]["y"]), ("lik_z", ref_fwd["likelihoods"]["z"])):
+        sm = sample(tt)
+        out[f"s_{tag}_values"] = sm["values"]
+        out[f"s_{tag}_info"] = np.array([sm["step"], sm["sum"], sm["abssum"]], dtype=np.float64)
+        out[f"s_{tag}_shape"] = np.array(sm["shape"])
     # the reference's own self-consistency invariants
     close(ref_fwd["x_hat"], ref_d["x_hat"], "fwd vs coded", 1e-4)
     close(ref_rec, ref_d["x_hat"], "decode_latent")
