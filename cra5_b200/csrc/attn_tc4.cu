@@ -1,0 +1,496 @@
+// attn_tc4.cu -- persistent, ping-pong fused softmax(Q K^T) V on tcgen05 tensor cores for head_dim 64.
+//
+// Same contract as attn_tc.cu (reference: WindowAttention.forward vit_nlc.py:219-258 incl. the un-masked zero-pad
+// tokens, and Attention.forward vit_nlc.py:94-112; token list in "attention order", a segment = seg_len contiguous
+// rows, Q pre-multiplied by head_dim^-0.5), restructured around what bounds head_dim 64 on Blackwell: the softmax, not
+// the MMAs (512 tensor cycles per 128x128 tile against 16 384 exponentials on 16 MUFU lanes per SM and clock).
+//
+//   * one CTA per SM, persistent over work items; an item = TWO 128-row query tiles (A, B) of one (segment, head) that
+//     share every K/V tile streamed through a 4-stage TMA ring; the next item's Q and K/V are prefetched while the
+//     current one drains, TMEM is allocated once;
+//   * warp 0 TMA producer, warps 1 / 3 MMA issuers of tile A / B, warp 2 TMEM allocator, warps 4-7 softmax of tile A,
+//     warps 8-11 softmax of tile B (thread = query row, all 128 scores of the row in registers; setmaxnreg moves registers from warps
+//     0-3 to the softmax warps);
+//   * S = Q K^T lands in TMEM (one buffer per tile; it is free again as soon as the row is in registers, so S of step
+//     j+1 is computed during the softmax of step j); P goes back to TMEM as bf16 and feeds the PV product straight
+//     from TMEM (tcgen05.mma with the A operand in tensor memory) -- no shared-memory round trip, no proxy fence;
+//   * O accumulates in TMEM over the whole KV loop. The running maximum is only moved when a row's tile maximum
+//     exceeds it by more than 2^8 (in the exp2 domain); then, and only then, O and the row sum are rescaled -- the
+//     result is exact because numerator and denominator always share the same reference;
+//   * exponentials: packed fp32x2 arithmetic (fma.rn.f32x2 / add.f32x2) for the scale-subtract and the row sums; a
+//     fixed fraction of the column pairs evaluates 2^x with a Cody-Waite split + cubic on the FMA pipe instead of
+//     MUFU.EX2, which balances the two pipes.
+#include "ptx.cuh"
+#include "host_util.h"
+#include "kernels.h"
+#include <cstdlib>
+
+namespace cra5 {
+
+namespace {
+
+constexpr int A4_BM = 128;          // rows per query tile
+constexpr int A4_BN = 128;          // keys per KV tile
+constexpr int A4_HD = 64;
+constexpr int A4_STAGES = 4;
+constexpr int A4_THREADS = 384;
+
+struct A4Smem {
+  static constexpr int Q_TILE = A4_BM * A4_HD * 2;         // 16 KB
+  static constexpr int Q_BUF = 2 * Q_TILE;                 // tiles A and B
+  static constexpr int K_BYTES = A4_BN * A4_HD * 2;        // 16 KB
+  static constexpr int V_BYTES = A4_HD * A4_BN * 2;        // 16 KB (two 64-key halves, each [64 dims][64 keys])
+  static constexpr int KV_BYTES = K_BYTES + V_BYTES;
+  static constexpr int OFF_Q = 0;                          // two Q buffers (items alternate)
+  static constexpr int OFF_KV = OFF_Q + 2 * Q_BUF;
+  static constexpr int OFF_BAR = OFF_KV + A4_STAGES * KV_BYTES;
+  static constexpr int TOTAL = OFF_BAR + 256;
+};
+
+// TMEM columns (512 allocated)
+constexpr uint32_t TM_S = 0;      // S_A at 0, S_B at 128 (fp32, 128 columns each)
+constexpr uint32_t TM_P = 256;    // P_A at 256, P_B at 320 (bf16 pairs, 64 columns each)
+constexpr uint32_t TM_O = 384;    // O_A at 384, O_B at 448 (fp32, 64 columns each)
+
+struct A4Params {
+  int seg_len;        // tokens per segment
+  int rows_total;     // rows of Q/K per head (= row stride of Vt)
+  int n_seg;
+  int heads;
+  int n_qp;           // query-tile pairs per segment
+  int q_part_from;    // segments >= this index only need their first q_part_rows query rows (padded windows)
+  int q_part_rows;
+  __nv_bfloat16* out; // [rows_total, ldo]
+  int ldo;
+};
+
+__device__ __forceinline__ float ex2_mufu(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// 2^x for a pair, x <= ~8, on the FMA/ALU pipes: n = round(x), f = x - n in [-0.5, 0.5], cubic minimax for 2^f
+// (relative error ~1e-4, an order of magnitude below the bf16 rounding of P), exponent added as an integer.
+__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& r0, float& r1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x0 = fmaxf(x0, -125.0f);
+  x1 = fmaxf(x1, -125.0f);
+  const uint64_t xc = pack2(x0, x1);
+  const uint64_t magic = pack2(12582912.0f, 12582912.0f);      // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const uint64_t nmagic = pack2(-12582912.0f, -12582912.0f);
+  const uint64_t t = add2(xc, magic);
+  const uint64_t n = add2(t, nmagic);
+  const uint64_t f = fma2(n, pack2(-1.0f, -1.0f), xc);
+  uint64_t p = fma2(pack2(0.0555041f, 0.0555041f), f, pack2(0.2402265f, 0.2402265f));
+  p = fma2(p, f, pack2(0.6931472f, 0.6931472f));
+  p = fma2(p, f, pack2(1.0f, 1.0f));
+  float p0, p1, t0, t1;
+  unpack2(p, p0, p1);
+  unpack2(t, t0, t1);
+  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+// D[tmem] (+)= A[tmem] * B[smem desc]: A is a 128-lane x K bf16 operand in tensor memory (two K elements per column)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+struct Item {
+  int head, seg, q0;
+  bool act_a, act_b;
+};
+__device__ __forceinline__ Item decode_item(const A4Params& p, int item) {
+  Item it;
+  const int qp = item % p.n_qp;
+  const int rest = item / p.n_qp;
+  it.seg = rest % p.n_seg;
+  it.head = rest / p.n_seg;
+  it.q0 = qp * (2 * A4_BM);
+  const int need = (it.seg >= p.q_part_from) ? p.q_part_rows : p.seg_len;  // query rows whose output is consumed
+  it.act_a = it.q0 < need;
+  it.act_b = it.q0 + A4_BM < need;
+  return it;
+}
+
+// POLY: of every 8 column pairs, this many take the polynomial exp2
+template <int POLY>
+__global__ void __launch_bounds__(A4_THREADS, 1)
+attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmVt, const A4Params p) {
+  using L = A4Smem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);   // [2]
+  uint64_t* q_empty = q_full + 2;                                       // [2]
+  uint64_t* kv_full = q_empty + 2;                                      // [STAGES]
+  uint64_t* kv_empty = kv_full + A4_STAGES;                             // [STAGES]
+  uint64_t* s_full = kv_empty + A4_STAGES;                              // [2] per query tile
+  uint64_t* s_empty = s_full + 2;
+  uint64_t* p_full = s_empty + 2;
+  uint64_t* pv_done = p_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_items = p.heads * p.n_seg * p.n_qp;
+  const int n_kv = (p.seg_len + A4_BN - 1) / A4_BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmVt);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 2);       // one arrival per query tile's MMA thread
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 128);
+      mbar_init(&p_full[s], 128);
+      mbar_init(&pv_done[s], 1);
+    }
+    for (int s = 0; s < A4_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 2);      // one arrival per query tile's MMA thread
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    reg_dec<64>();    // the pool setmaxnreg draws from is what the launch allocated: 384 x 168 >= 128 x 64 + 256 x 216
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer =====================
+      uint32_t it_q = 0, it_kv = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item it = decode_item(p, item);
+        if (!it.act_a) continue;
+        const int seg_row0 = it.seg * p.seg_len;
+        const int qb = it_q & 1;
+        mbar_wait(&q_empty[qb], ((it_q >> 1) & 1) ^ 1);
+        uint8_t* sq = smem + L::OFF_Q + qb * L::Q_BUF;
+        mbar_expect_tx(&q_full[qb], it.act_b ? L::Q_BUF : L::Q_TILE);
+        tma_load_2d(sq, &tmQ, &q_full[qb], 0, it.head * p.rows_total + seg_row0 + it.q0);
+        if (it.act_b) tma_load_2d(sq + L::Q_TILE, &tmQ, &q_full[qb], 0, it.head * p.rows_total + seg_row0 + it.q0 + A4_BM);
+        ++it_q;
+        for (int j = 0; j < n_kv; ++j, ++it_kv) {
+          const int s = it_kv % A4_STAGES;
+          mbar_wait(&kv_empty[s], ((it_kv / A4_STAGES) & 1) ^ 1);
+          uint8_t* sk = smem + L::OFF_KV + s * L::KV_BYTES;
+          uint8_t* sv = sk + L::K_BYTES;
+          const int kv0 = seg_row0 + j * A4_BN;
+          mbar_expect_tx(&kv_full[s], L::KV_BYTES);
+          tma_load_2d(sk, &tmK, &kv_full[s], 0, it.head * p.rows_total + kv0);
+          tma_load_2d(sv, &tmVt, &kv_full[s], kv0, it.head * A4_HD);
+          tma_load_2d(sv + L::V_BYTES / 2, &tmVt, &kv_full[s], kv0 + 64, it.head * A4_HD);
+        }
+      }
+    } else if ((warp == 1 || warp == 3) && lane == 0) {
+      // ===================== MMA issuers: warp 1 drives query tile A, warp 3 tile B =====================
+      // (two independent in-order instruction streams: neither tile's PV product ever queues behind a wait that
+      // belongs to the other tile)
+      const int x = warp >> 1;
+      constexpr uint32_t idesc_s = umma_idesc_bf16(A4_BM, A4_BN);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(A4_BM, A4_HD);
+      const uint64_t q_desc0 = umma_smem_desc_sw128(smem_u32(smem + L::OFF_Q));
+      const uint64_t kv_desc0 = umma_smem_desc_sw128(smem_u32(smem + L::OFF_KV));
+      const uint32_t d_s = tmem_base + TM_S + x * A4_BN;
+      const uint32_t d_o = tmem_base + TM_O + x * A4_HD;
+      const uint32_t a_p = tmem_base + TM_P + x * 64;   // 8 columns (16 keys) per MMA
+      uint32_t it_q = 0, it_kv = 0;
+      uint32_t cnt_s = 0, cnt_p = 0;   // S / PV products issued for this tile (phases of s_full,s_empty / p_full,pv_done)
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const Item it = decode_item(p, item);
+        if (!it.act_a) continue;
+        const int qb = it_q & 1;
+        const uint32_t q_phase = (it_q >> 1) & 1;
+        const uint32_t kv_first = it_kv;
+        it_kv += n_kv;
+        ++it_q;
+        if (x == 1 && !it.act_b) continue;
+        const int n_arrive = (x == 0 && !it.act_b) ? 2 : 1;   // tile A also signs for an absent tile B
+        mbar_wait(&q_full[qb], q_phase);
+        tc_fence_after();
+        const uint64_t qdesc = q_desc0 + (uint64_t)((qb * L::Q_BUF + x * L::Q_TILE) >> 4);
+        for (int j = 0; j <= n_kv; ++j) {
+          if (j < n_kv) {
+            const int s = (kv_first + j) % A4_STAGES;
+            mbar_wait(&kv_full[s], ((kv_first + j) / A4_STAGES) & 1);
+            mbar_wait(&s_empty[x], (cnt_s & 1) ^ 1);   // the softmax warps hold the previous S of this tile in registers
+            tc_fence_after();
+            const uint64_t kdesc = kv_desc0 + (uint64_t)((s * L::KV_BYTES) >> 4);
+            umma_bf16(d_s, qdesc + 0, kdesc + 0, idesc_s, 0);
+            umma_bf16(d_s, qdesc + 2, kdesc + 2, idesc_s, 1);
+            umma_bf16(d_s, qdesc + 4, kdesc + 4, idesc_s, 1);
+            umma_bf16(d_s, qdesc + 6, kdesc + 6, idesc_s, 1);
+            umma_commit(&s_full[x]);
+            ++cnt_s;
+            if (j == n_kv - 1)                         // Q buffer reusable once the last S products retire
+              for (int a = 0; a < n_arrive; ++a) umma_commit(&q_empty[qb]);
+          }
+          if (j > 0) {
+            const int s = (kv_first + j - 1) % A4_STAGES;
+            const uint64_t vdesc = kv_desc0 + (uint64_t)((s * L::KV_BYTES + L::K_BYTES) >> 4);
+            constexpr uint64_t VH = (L::V_BYTES / 2) >> 4;    // second 64-key half
+            mbar_wait(&p_full[x], cnt_p & 1);
+            tc_fence_after();
+            const uint32_t acc = (j - 1) > 0;
+            umma_bf16_ts(d_o, a_p + 0, vdesc + 0, idesc_pv, acc);
+            umma_bf16_ts(d_o, a_p + 8, vdesc + 2, idesc_pv, 1);
+            umma_bf16_ts(d_o, a_p + 16, vdesc + 4, idesc_pv, 1);
+            umma_bf16_ts(d_o, a_p + 24, vdesc + 6, idesc_pv, 1);
+            umma_bf16_ts(d_o, a_p + 32, vdesc + VH + 0, idesc_pv, 1);
+            umma_bf16_ts(d_o, a_p + 40, vdesc + VH + 2, idesc_pv, 1);
+            umma_bf16_ts(d_o, a_p + 48, vdesc + VH + 4, idesc_pv, 1);
+            umma_bf16_ts(d_o, a_p + 56, vdesc + VH + 6, idesc_pv, 1);
+            umma_commit(&pv_done[x]);
+            ++cnt_p;
+            for (int a = 0; a < n_arrive; ++a) umma_commit(&kv_empty[s]);
+          }
+        }
+      }
+    }
+  } else {
+    reg_inc<216>();
+    // ===================== softmax: thread = query row, all 128 scores of the row in registers =====================
+    constexpr int NC = A4_BN;                   // score columns per thread
+    constexpr int ND = A4_HD;                   // output dims per thread
+    const int sw = warp - 4;
+    const int x = sw >> 2;                      // query tile: 0 = A, 1 = B
+    const int quarter = warp & 3;               // TMEM lane quarter
+    const int r = quarter * 32 + lane;          // row inside the tile == TMEM lane
+    const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_addr + TM_S + x * A4_BN;
+    const uint32_t t_p = tmem_base + lane_addr + TM_P + x * 64;
+    const uint32_t t_o = tmem_base + lane_addr + TM_O + x * A4_HD;
+    constexpr float LOG2E = 1.4426950408889634f;
+    constexpr float RESCALE_TH = 8.0f / LOG2E;  // move the reference maximum only for growth beyond 2^8
+    const uint64_t l2e2 = pack2(LOG2E, LOG2E);
+    uint32_t cnt = 0;                           // steps processed by this tile (phases of all four barriers)
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const Item it = decode_item(p, item);
+      if (!(x == 0 ? it.act_a : it.act_b)) continue;
+      float m_ref = -INFINITY, l = 0.f;
+      for (int j = 0; j < n_kv; ++j, ++cnt) {
+        const int valid = p.seg_len - j * A4_BN;   // >= 128 for all but a segment's last tile
+        mbar_wait(&s_full[x], cnt & 1);
+        tc_fence_after();
+        uint32_t s[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c += 32) tmem_ld_32x32(t_s + c, *reinterpret_cast<uint32_t(*)[32]>(&s[c]));
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&s_empty[x]);                  // S of the next step may overwrite the buffer now
+        if (valid < NC) {                          // warp-uniform: keys beyond the segment do not exist
+#pragma unroll
+          for (int i = 0; i < NC; ++i)
+            if (i >= valid) s[i] = 0xff800000u;    // -inf
+        }
+        float mt0 = -INFINITY, mt1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < NC; i += 4) {
+          mt0 = fmaxf(mt0, fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
+          mt1 = fmaxf(mt1, fmaxf(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])));
+        }
+        const float mt = fmaxf(mt0, mt1);
+        if (j == 0) {
+          m_ref = mt;
+        } else if (__any_sync(0xffffffffu, mt > m_ref + RESCALE_TH)) {
+          // rare: move the reference maximum and rescale O / l. Every earlier PV product of this tile must have retired.
+          mbar_wait(&pv_done[x], (cnt - 1) & 1);
+          tc_fence_after();
+          const float m_new = fmaxf(m_ref, mt);
+          const float alpha = ex2_mufu((m_ref - m_new) * LOG2E);
+          l *= alpha;
+          m_ref = m_new;
+          const uint64_t a2 = pack2(alpha, alpha);
+#pragma unroll
+          for (int h = 0; h < ND; h += 32) {
+            uint32_t o[32];
+            tmem_ld_32x32(t_o + h, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const uint64_t v = mul2(pack2(__uint_as_float(o[i]), __uint_as_float(o[i + 1])), a2);
+              float v0, v1;
+              unpack2(v, v0, v1);
+              o[i] = __float_as_uint(v0);
+              o[i + 1] = __float_as_uint(v1);
+            }
+            tmem_st_32x32(t_o + h, o);
+          }
+          tmem_st_wait();
+        }
+        const float nm = -m_ref * LOG2E;
+        const uint64_t nm2 = pack2(nm, nm);
+        uint64_t sum_a = pack2(0.f, 0.f), sum_b = pack2(0.f, 0.f);
+        uint32_t pk[NC / 2];                      // P as packed bf16 pairs
+#pragma unroll
+        for (int q = 0; q < NC / 2; ++q) {
+          const int i = 2 * q;
+          const uint64_t xs = fma2(pack2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), l2e2, nm2);
+          float e0, e1;
+          if ((q & 7) < POLY) {
+            ex2_poly2(xs, e0, e1);
+          } else {
+            float x0, x1;
+            unpack2(xs, x0, x1);
+            e0 = ex2_mufu(x0);
+            e1 = ex2_mufu(x1);
+          }
+          if (q & 1) sum_b = add2(sum_b, pack2(e0, e1)); else sum_a = add2(sum_a, pack2(e0, e1));
+          pk[q] = pack_bf16x2(e0, e1);
+        }
+        {
+          float a0, a1, b0, b1;
+          unpack2(sum_a, a0, a1);
+          unpack2(sum_b, b0, b1);
+          l += (a0 + a1) + (b0 + b1);
+        }
+        // the previous PV product of this tile reads P: it must have retired before P is overwritten (it was issued a
+        // whole softmax step ago, so this wait does not stall in steady state)
+        if (j > 0) {
+          mbar_wait(&pv_done[x], (cnt - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int c = 0; c < NC / 2; c += 32) tmem_st_32x32(t_p + c, *reinterpret_cast<uint32_t(*)[32]>(&pk[c]));
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[x]);
+      }
+      // ---- item epilogue: O / l -> bf16 -> global
+      mbar_wait(&pv_done[x], (cnt - 1) & 1);
+      tc_fence_after();
+      const float inv = 1.0f / l;
+      const int qrow = it.q0 + x * A4_BM + r;     // row inside the segment
+      const bool store = qrow < p.seg_len;
+      __nv_bfloat16* dst = p.out + (size_t)(it.seg * p.seg_len + qrow) * p.ldo + it.head * A4_HD;
+#pragma unroll
+      for (int h = 0; h < ND; h += 32) {
+        uint32_t o[32];
+        tmem_ld_32x32(t_o + h, o);
+        tmem_ld_wait();
+        if (store) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + h + i) = u;
+          }
+        }
+      }
+      tc_fence_before();   // the O reads are ordered before this thread's next p_full arrive, which gates the next PV
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace
+
+// Q, K: [heads][rows_total][64] bf16; Vt: [heads][64][rows_total] bf16; out: [rows_total][ldo] bf16.
+// Segments with index >= q_part_from only need their first q_part_rows query rows (the rest are window-pad rows whose
+// output the caller drops); pass q_part_from >= n_seg for "all rows".
+void attention_tc(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* Vt,
+                  __nv_bfloat16* out, int ldo, int heads, int rows_total, int seg_len, int q_part_from,
+                  int q_part_rows) {
+  static const char* env = getenv("CRA5_ATTN");  // diagnostics: 3 = previous kernel
+  if (env != nullptr && atoi(env) == 3) {
+    attention_tc3(st, Q, K, Vt, out, ldo, heads, rows_total, seg_len);
+    return;
+  }
+  CRA5_CHECK(seg_len > 0 && rows_total % seg_len == 0, ERR_INVALID, "attention: rows must be whole segments");
+  CRA5_CHECK((rows_total & 7) == 0, ERR_INVALID, "attention: rows_total must be a multiple of 8 (TMA stride)");
+  static const int poly = [] { const char* e = getenv("CRA5_ATTN_POLY"); return e ? atoi(e) : 3; }();
+  auto kern = poly == 0 ? attn_tc4_kernel<0> : poly == 2 ? attn_tc4_kernel<2> : poly == 4 ? attn_tc4_kernel<4> : attn_tc4_kernel<3>;
+  static bool configured = false;
+  if (!configured) {
+    CRA5_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A4Smem::TOTAL));
+    configured = true;
+  }
+  CUtensorMap tmQ = make_tmap_bf16_2d(Q, A4_HD, (uint64_t)heads * rows_total, A4_HD * 2, A4_HD, A4_BM);
+  CUtensorMap tmK = make_tmap_bf16_2d(K, A4_HD, (uint64_t)heads * rows_total, A4_HD * 2, A4_HD, A4_BN);
+  CUtensorMap tmVt = make_tmap_bf16_2d(Vt, (uint64_t)rows_total, (uint64_t)heads * A4_HD, (uint64_t)rows_total * 2,
+                                       64, A4_HD);
+  A4Params p;
+  p.seg_len = seg_len;
+  p.rows_total = rows_total;
+  p.n_seg = rows_total / seg_len;
+  p.heads = heads;
+  p.n_qp = (seg_len + 2 * A4_BM - 1) / (2 * A4_BM);
+  p.q_part_from = (q_part_rows > 0 && q_part_rows < seg_len) ? q_part_from : p.n_seg;
+  p.q_part_rows = q_part_rows;
+  p.out = out;
+  p.ldo = ldo;
+  const int n_items = heads * p.n_seg * p.n_qp;
+  const int grid = n_items < device_sm_count() ? n_items : device_sm_count();
+  LaunchScope scope(st, "attn_tc", 4.0 * heads * (double)rows_total * seg_len * A4_HD,
+                    4.0 * 2.0 * heads * (double)rows_total * A4_HD);
+  kern<<<grid, A4_THREADS, A4Smem::TOTAL, st>>>(tmQ, tmK, tmVt, p);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+}  // namespace cra5

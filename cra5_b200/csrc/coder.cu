@@ -7,6 +7,47 @@
 
 namespace cra5 {
 
+// ---------------------------------------------------------------------------------------------------------------
+// Small transfers between the device and MAPPED pinned host memory are done by the SMs (zero-copy loads / stores over
+// PCIe), not by cudaMemcpyAsync: a copy-engine transfer queues FIFO behind whatever that engine is already moving, and
+// in a streaming pipeline that is the 1.1 GB frame of the next / previous time step (20 ms) -- the 2-5 MB bitstream
+// would wait for it and serialise encode, decode and both frame copies.
+namespace {
+constexpr int XFER_BLOCKS = 64, XFER_THREADS = 256;
+
+// lengths[n_streams], total, err -> meta_host; payload[0, total) -> payload_host   (total = offsets[n_streams])
+__global__ void container_to_host_kernel(const uint32_t* __restrict__ lengths, const uint32_t* __restrict__ offsets,
+                                         const int* __restrict__ err, int n_streams,
+                                         const uint32_t* __restrict__ payload, uint32_t* meta_host,
+                                         uint32_t* payload_host) {
+  const uint32_t total = offsets[n_streams];
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+  for (int i = gt; i < n_streams; i += gs) meta_host[i] = lengths[i];
+  if (gt == 0) {
+    meta_host[n_streams] = total;
+    meta_host[n_streams + 1] = (uint32_t)*err;
+  }
+  if (payload_host != nullptr)
+    for (uint32_t i = gt; i < total / 4; i += gs) payload_host[i] = payload[i];
+}
+// stage_host = [lengths: ns words][payload: words] -> lengths, payload on the device
+__global__ void container_from_host_kernel(const uint32_t* stage_host, int ns, uint32_t n_words, uint32_t* lengths,
+                                           uint32_t* payload) {
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
+  for (uint32_t i = gt; i < n_words; i += gs) {
+    const uint32_t v = stage_host[i];
+    if (i < (uint32_t)ns) lengths[i] = v; else payload[i - ns] = v;
+  }
+}
+__global__ void word_to_host_kernel(const int* src, uint32_t* dst_host) { *dst_host = (uint32_t)*src; }
+
+void* device_alias(void* host_mapped) {
+  void* d = nullptr;
+  CRA5_CUDA(cudaHostGetDevicePointer(&d, host_mapped, 0));
+  return d;
+}
+}  // namespace
+
 RansCoder::RansCoder(size_t max_symbols, int max_channels)
     : max_symbols_(max_symbols), max_streams_(max_channels * CR5B_MAX_SPC) {
   scratch_words_ = 2 * max_symbols + 8 * (size_t)max_streams_;
@@ -17,9 +58,12 @@ RansCoder::RansCoder(size_t max_symbols, int max_channels)
   CRA5_CUDA(cudaMalloc(&payload_, payload_cap_));
   CRA5_CUDA(cudaMalloc(&err_, sizeof(int)));
   CRA5_CUDA(cudaMemset(err_, 0, sizeof(int)));
-  CRA5_CUDA(cudaMallocHost(&host_meta_, ((size_t)max_streams_ + 4) * 4));
+  meta_slot_words_ = (size_t)max_streams_ + 4;
+  CRA5_CUDA(cudaHostAlloc(&host_meta_, 2 * meta_slot_words_ * 4, cudaHostAllocMapped));
   host_stage_cap_ = payload_cap_ + (size_t)max_streams_ * 4 + 64;
-  CRA5_CUDA(cudaMallocHost(&host_stage_, host_stage_cap_));
+  CRA5_CUDA(cudaHostAlloc(&host_stage_, host_stage_cap_, cudaHostAllocMapped));
+  host_meta_dev_ = static_cast<uint32_t*>(device_alias(host_meta_));
+  host_stage_dev_ = static_cast<uint8_t*>(device_alias(host_stage_));
   CRA5_CUDA(cudaMalloc(&lut_, (size_t)256 * 257 * 2));
 }
 
@@ -68,44 +112,70 @@ size_t RansCoder::encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx
     CRA5_CUDA(cudaStreamSynchronize(st));
     return total;
   }
+  // chunked container through caller memory that the device may not be able to reach: stage, then memcpy
+  const int n_streams = n_channels * spc;
+  const size_t head = CR5B_HEADER + 4 * (size_t)n_streams;
+  CRA5_CHECK(host_cap >= head, ERR_INVALID, "rans_encode: output buffer too small");
+  encode_begin(st, 0, sym, idx, tab, n_channels, L, spc, host_stage_, host_stage_cap_);
+  CRA5_CUDA(cudaStreamSynchronize(st));
+  const size_t total = encode_end(st, 0, n_channels, L, spc, host_stage_, host_stage_cap_);
+  CRA5_CHECK(host_cap >= total, ERR_INVALID, "rans_encode: output buffer too small");
+  memcpy(host_out, host_stage_, total);
+  return total;
+}
+
+// Enqueue the encode of one tensor; its container lands in `host_mapped` (pinned + mapped, at least
+// max_container_bytes() large) once the stream has been synchronised and encode_end() has written the header.
+void RansCoder::encode_begin(cudaStream_t st, int slot, const int32_t* sym, const uint8_t* idx, const CdfTable& tab,
+                             int n_channels, int L, int spc, uint8_t* host_mapped, size_t host_cap) {
+  CRA5_CHECK(tab.ready(), ERR_STATE, "Uninitialized CDFs. Run update() first");
+  CRA5_CHECK(spc >= 1 && spc <= CR5B_MAX_SPC, ERR_INVALID, "streams per channel must be in [1, 64]");
+  CRA5_CHECK(n_channels >= 0 && L >= 0 && (slot == 0 || slot == 1), ERR_INVALID, "rans_encode: bad argument");
   const int n_streams = n_channels * spc;
   CRA5_CHECK((size_t)n_channels * L <= max_symbols_ && n_streams <= max_streams_, ERR_INVALID,
              "rans_encode: tensor larger than the coder was sized for");
+  CRA5_CHECK(host_cap >= max_container_bytes((size_t)n_channels * L, n_streams), ERR_INVALID,
+             "rans_encode: output buffer too small");
   const size_t head = CR5B_HEADER + 4 * (size_t)n_streams;
-  CRA5_CHECK(host_cap >= head, ERR_INVALID, "rans_encode: output buffer too small");
   const int count_max = (L + spc - 1) / spc;
   const int cap_words = 2 * count_max + 6;
   CRA5_CHECK((size_t)n_streams * cap_words <= scratch_words_, ERR_INTERNAL, "rans_encode: scratch sizing");
+  if (n_streams == 0 || L == 0) return;
+  rans_encode(st, sym, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, n_channels, L, spc, L > 0 ? L : 1,
+              scratch_, cap_words, lengths_, offsets_, payload_, err_);
+  uint8_t* out_dev = static_cast<uint8_t*>(device_alias(host_mapped)) + head;   // 4-byte aligned: head is
+  count_launch();
+  container_to_host_kernel<<<XFER_BLOCKS, XFER_THREADS, 0, st>>>(
+      lengths_, offsets_, err_, n_streams, reinterpret_cast<const uint32_t*>(payload_),
+      host_meta_dev_ + slot * meta_slot_words_, reinterpret_cast<uint32_t*>(out_dev));
+  CRA5_CUDA(cudaGetLastError());
+}
+
+size_t RansCoder::encode_end(cudaStream_t st, int slot, int n_channels, int L, int spc, uint8_t* host_mapped,
+                             size_t host_cap) {
+  const int n_streams = n_channels * spc;
+  const size_t head = CR5B_HEADER + 4 * (size_t)n_streams;
+  uint32_t* meta = host_meta_ + slot * meta_slot_words_;
   uint32_t total = 0;
   if (n_streams > 0 && L > 0) {
-    rans_encode(st, sym, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, n_channels, L, spc, L > 0 ? L : 1,
-                scratch_, cap_words, lengths_, offsets_, payload_, err_);
-    CRA5_CUDA(cudaMemcpyAsync(host_meta_, lengths_, (size_t)n_streams * 4, cudaMemcpyDeviceToHost, st));
-    CRA5_CUDA(cudaMemcpyAsync(host_meta_ + n_streams, offsets_ + n_streams, 4, cudaMemcpyDeviceToHost, st));
-    CRA5_CUDA(cudaMemcpyAsync(host_meta_ + n_streams + 1, err_, 4, cudaMemcpyDeviceToHost, st));
-    CRA5_CUDA(cudaStreamSynchronize(st));
-    if (host_meta_[n_streams + 1] != 0) {
+    if (meta[n_streams + 1] != 0) {
       CRA5_CUDA(cudaMemsetAsync(err_, 0, sizeof(int), st));
       throw Error(ERR_INTERNAL, "rans_encode: per-stream scratch overflow");
     }
-    total = host_meta_[n_streams];
+    total = meta[n_streams];
   } else {
-    for (int s = 0; s < n_streams; ++s) host_meta_[s] = 0;
+    for (int s = 0; s < n_streams; ++s) meta[s] = 0;
   }
   CRA5_CHECK(host_cap >= head + total, ERR_INVALID, "rans_encode: output buffer too small");
-  memcpy(host_out, "CR5B", 4);
-  host_out[4] = 1;
-  host_out[5] = 0;
-  host_out[6] = host_out[7] = 0;
-  put_u32(host_out + 8, (uint32_t)n_channels);
-  put_u32(host_out + 12, (uint32_t)L);
-  put_u32(host_out + 16, (uint32_t)spc);
-  put_u32(host_out + 20, (uint32_t)n_streams);
-  memcpy(host_out + CR5B_HEADER, host_meta_, (size_t)n_streams * 4);
-  if (total > 0) {
-    CRA5_CUDA(cudaMemcpyAsync(host_out + head, payload_, total, cudaMemcpyDeviceToHost, st));
-    CRA5_CUDA(cudaStreamSynchronize(st));
-  }
+  memcpy(host_mapped, "CR5B", 4);
+  host_mapped[4] = 1;
+  host_mapped[5] = 0;
+  host_mapped[6] = host_mapped[7] = 0;
+  put_u32(host_mapped + 8, (uint32_t)n_channels);
+  put_u32(host_mapped + 12, (uint32_t)L);
+  put_u32(host_mapped + 16, (uint32_t)spc);
+  put_u32(host_mapped + 20, (uint32_t)n_streams);
+  memcpy(host_mapped + CR5B_HEADER, meta, (size_t)n_streams * 4);
   return head + total;
 }
 
@@ -158,8 +228,11 @@ void RansCoder::decode(cudaStream_t st, const uint8_t* bytes, size_t len, const 
   CRA5_CHECK(total <= payload_cap_ && len <= host_stage_cap_, ERR_BITSTREAM, "bitstream: too large");
   CRA5_CUDA(cudaStreamSynchronize(st));  // the staging buffer may still be in flight from a previous call
   memcpy(host_stage_, bytes + CR5B_HEADER, len - CR5B_HEADER);
-  CRA5_CUDA(cudaMemcpyAsync(lengths_, host_stage_, (size_t)ns * 4, cudaMemcpyHostToDevice, st));
-  CRA5_CUDA(cudaMemcpyAsync(payload_, host_stage_ + (size_t)ns * 4, total, cudaMemcpyHostToDevice, st));
+  count_launch();
+  container_from_host_kernel<<<XFER_BLOCKS, XFER_THREADS, 0, st>>>(
+      reinterpret_cast<const uint32_t*>(host_stage_dev_), (int)ns, (uint32_t)(ns + total / 4), lengths_,
+      reinterpret_cast<uint32_t*>(payload_));
+  CRA5_CUDA(cudaGetLastError());
   scan_lengths(st, lengths_, (int)ns, offsets_);
   // wide tables (GaussianConditional: up to 3133 entries per row) get a coarse inverse table; the per-channel
   // EntropyBottleneck rows are a few dozen entries and are searched directly
@@ -176,7 +249,8 @@ void RansCoder::decode(cudaStream_t st, const uint8_t* bytes, size_t len, const 
   }
   rans_decode(st, payload_, offsets_, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, lut, lut_rows,
               n_channels, L, (int)spc, L > 0 ? L : 1, sym_out, mu, median, val_out, err_);
-  CRA5_CUDA(cudaMemcpyAsync(host_meta_, err_, 4, cudaMemcpyDeviceToHost, st));
+  word_to_host_kernel<<<1, 1, 0, st>>>(err_, host_meta_dev_);
+  CRA5_CUDA(cudaGetLastError());
   CRA5_CUDA(cudaStreamSynchronize(st));
   if (host_meta_[0] != 0) {
     CRA5_CUDA(cudaMemsetAsync(err_, 0, sizeof(int), st));

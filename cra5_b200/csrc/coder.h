@@ -32,6 +32,13 @@ class RansCoder {
   // symbols/indexes on the device -> container in host memory (pinned or pageable). Returns its size.
   size_t encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx, const CdfTable& tab, int n_channels, int L,
                 int spc, uint8_t* host_out, size_t host_cap);
+  // Two-phase form for PINNED + MAPPED output buffers (cudaHostAlloc(.., cudaHostAllocMapped), at least
+  // max_container_bytes() large): encode_begin only enqueues work -- the kernels write lengths and payload straight
+  // into host memory -- so several tensors share ONE stream synchronisation; after it, encode_end checks the error
+  // word, writes the header and returns the container size. slot (0 or 1) selects the metadata slot.
+  void encode_begin(cudaStream_t st, int slot, const int32_t* sym, const uint8_t* idx, const CdfTable& tab,
+                    int n_channels, int L, int spc, uint8_t* host_mapped, size_t host_cap);
+  size_t encode_end(cudaStream_t st, int slot, int n_channels, int L, int spc, uint8_t* host_mapped, size_t host_cap);
   // container in host memory -> symbols and/or dequantised values on the device
   void invalidate_lut() { lut_for_ = nullptr; lut_rows_ = 0; }
   void decode(cudaStream_t st, const uint8_t* bytes, size_t len, const uint8_t* idx, const CdfTable& tab,
@@ -44,8 +51,11 @@ class RansCoder {
   uint8_t* payload_ = nullptr;
   size_t payload_cap_ = 0, scratch_words_ = 0;
   int* err_ = nullptr;
-  uint32_t* host_meta_ = nullptr;  // pinned: lengths + total + err
-  uint8_t* host_stage_ = nullptr;  // pinned upload staging for decode
+  uint32_t* host_meta_ = nullptr;  // pinned + mapped, two slots: lengths + total + err
+  uint8_t* host_stage_ = nullptr;  // pinned + mapped staging (decode upload; encode into pageable caller memory)
+  uint32_t* host_meta_dev_ = nullptr;  // device aliases of the two
+  uint8_t* host_stage_dev_ = nullptr;
+  size_t meta_slot_words_ = 0;
   uint16_t* lut_ = nullptr;        // coarse inverse-CDF table of the last GaussianConditional-style table seen
   const int32_t* lut_for_ = nullptr;
   int lut_rows_ = 0;

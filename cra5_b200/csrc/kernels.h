@@ -18,9 +18,14 @@ void gemm_plain(cudaStream_t st, int kind, const __nv_bfloat16* A, int lda, cons
 void gemm_simt_check(cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,
                      const float* bias, float* C, int ldc, int M, int N, int K);
 
-// fused softmax(QK^T)V, head_dim 64 (attn_tc.cu)
+// fused softmax(QK^T)V, head_dim 64. attention_tc (attn_tc4.cu) is the persistent ping-pong kernel; segments with
+// index >= q_part_from only need their first q_part_rows query rows (window-pad rows). attention_tc3 (attn_tc.cu) is
+// the previous one-tile-per-CTA kernel, kept for A/B diagnostics (CRA5_ATTN=3).
 void attention_tc(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* Vt,
-                  __nv_bfloat16* out, int ldo, int heads, int rows_total, int seg_len);
+                  __nv_bfloat16* out, int ldo, int heads, int rows_total, int seg_len, int q_part_from = 1 << 30,
+                  int q_part_rows = 0);
+void attention_tc3(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* Vt,
+                   __nv_bfloat16* out, int ldo, int heads, int rows_total, int seg_len);
 
 void attention_simt(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* Vt,
                     __nv_bfloat16* out, int ldo, int heads, int hd, int rows_total, int seg_len);

@@ -110,8 +110,8 @@ Model::Model(const cra5_config& c) : cfg_(c) {
   coder_ = new RansCoder((size_t)lat * T, std::max(lat, zc));
   host_y_cap_ = RansCoder::max_container_bytes((size_t)lat * T, lat * CR5B_MAX_SPC);
   host_z_cap_ = RansCoder::max_container_bytes((size_t)zc * Th, zc * CR5B_MAX_SPC);
-  CRA5_CUDA(cudaMallocHost(&host_y_, host_y_cap_));
-  CRA5_CUDA(cudaMallocHost(&host_z_, host_z_cap_));
+  CRA5_CUDA(cudaHostAlloc(&host_y_, host_y_cap_, cudaHostAllocMapped));   // the coder's kernels write into these
+  CRA5_CUDA(cudaHostAlloc(&host_z_, host_z_cap_, cudaHostAllocMapped));
 }
 
 Model::~Model() {
@@ -219,8 +219,16 @@ void Model::run_block(cudaStream_t st, const BlockWeights& w, const TrunkBuffers
     TagScope tag_("qkv");
     gemm_plain(st, EPI_QKV, tb.a, D, w.qkv_w, D, rows, 3 * D, D, e);
   }
-  if (hd_ == 64)
-    attention_tc(st, tb.q, tb.k, tb.vt, tb.o, D, heads, rows, seg);
+  if (hd_ == 64) {
+    // bottom-row windows of a vertically padded grid: their trailing rows are pad tokens (vit_nlc.py:229-237). They
+    // still act as keys / values, but their own outputs are cropped away (:252-256), so those query tiles are skipped.
+    int part_from = 1 << 30, part_rows = 0;
+    if (wm.enabled && Hg % wm.wh != 0 && Wg % wm.ww == 0) {
+      part_from = (wm.nWr - 1) * wm.nWc;
+      part_rows = (Hg - (wm.nWr - 1) * wm.wh) * wm.ww;
+    }
+    attention_tc(st, tb.q, tb.k, tb.vt, tb.o, D, heads, rows, seg, part_from, part_rows);
+  }
   else
     attention_simt(st, tb.q, tb.k, tb.vt, tb.o, D, heads, hd_, rows, seg);
   {
@@ -451,8 +459,17 @@ void Model::latent_to_bin(const float* y, const uint8_t** y_bytes, size_t* y_len
                     (size_t)lat * T);
   taps_["y_symbols"] = TensorRef{ysym_, CRA5_DT_I32, (int64_t)lat * T};
   taps_["y_indexes"] = TensorRef{yidx_, CRA5_DT_U8, (int64_t)lat * T};
-  *z_len = coder_->encode(st, zsym_, nullptr, eb_, zc, Th, spc_z_, host_z_, host_z_cap_);
-  *y_len = coder_->encode(st, ysym_, yidx_, gc_, lat, T, spc_y_, host_y_, host_y_cap_);
+  if (spc_y_ > 0 && spc_z_ > 0) {
+    // both containers are written into host memory by the kernels themselves: one synchronisation for the pair
+    coder_->encode_begin(st, 0, zsym_, nullptr, eb_, zc, Th, spc_z_, host_z_, host_z_cap_);
+    coder_->encode_begin(st, 1, ysym_, yidx_, gc_, lat, T, spc_y_, host_y_, host_y_cap_);
+    CRA5_CUDA(cudaStreamSynchronize(st));
+    *z_len = coder_->encode_end(st, 0, zc, Th, spc_z_, host_z_, host_z_cap_);
+    *y_len = coder_->encode_end(st, 1, lat, T, spc_y_, host_y_, host_y_cap_);
+  } else {  // reference-format single streams (interop path)
+    *z_len = coder_->encode(st, zsym_, nullptr, eb_, zc, Th, spc_z_, host_z_, host_z_cap_);
+    *y_len = coder_->encode(st, ysym_, yidx_, gc_, lat, T, spc_y_, host_y_, host_y_cap_);
+  }
   *y_bytes = host_y_;
   *z_bytes = host_z_;
 }
