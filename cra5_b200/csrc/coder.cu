@@ -56,8 +56,8 @@ RansCoder::RansCoder(size_t max_symbols, int max_channels)
   CRA5_CUDA(cudaMalloc(&lengths_, (size_t)max_streams_ * 4));
   CRA5_CUDA(cudaMalloc(&offsets_, ((size_t)max_streams_ + 1) * 4));
   CRA5_CUDA(cudaMalloc(&payload_, payload_cap_));
-  CRA5_CUDA(cudaMalloc(&err_, sizeof(int)));
-  CRA5_CUDA(cudaMemset(err_, 0, sizeof(int)));
+  CRA5_CUDA(cudaMalloc(&err_, 2 * sizeof(int)));   // [0] error flag, [1] scratch word of packed_for()
+  CRA5_CUDA(cudaMemset(err_, 0, 2 * sizeof(int)));
   meta_slot_words_ = (size_t)max_streams_ + 4;
   CRA5_CUDA(cudaHostAlloc(&host_meta_, 2 * meta_slot_words_ * 4, cudaHostAllocMapped));
   host_stage_cap_ = payload_cap_ + (size_t)max_streams_ * 4 + 64;
@@ -65,6 +65,35 @@ RansCoder::RansCoder(size_t max_symbols, int max_channels)
   host_meta_dev_ = static_cast<uint32_t*>(device_alias(host_meta_));
   host_stage_dev_ = static_cast<uint8_t*>(device_alias(host_stage_));
   CRA5_CUDA(cudaMalloc(&lut_, (size_t)256 * 257 * 2));
+  for (Packed& p : packed_) {
+    CRA5_CUDA(cudaMalloc(&p.data, ((size_t)PACK_CAP + 8) * 2));
+    CRA5_CUDA(cudaMalloc(&p.row_off, ((size_t)PACK_ROWS + 1) * 4));
+    CRA5_CUDA(cudaMalloc(&p.lut, ((size_t)PACK_ROWS * 257 + 8) * 2));
+  }
+}
+
+// the table in shared-memory form, or nullptr when it is not known to fit (row count unknown / too large)
+const RansCoder::Packed* RansCoder::packed_for(cudaStream_t st, const CdfTable& tab) {
+  if (tab.rows <= 0 || tab.rows > PACK_ROWS) return nullptr;
+  Packed* slot = nullptr;
+  for (Packed& p : packed_)
+    if (p.key == tab.cdf && p.rows == tab.rows) slot = &p;
+  if (slot == nullptr) {
+    slot = (packed_[0].stamp <= packed_[1].stamp) ? &packed_[0] : &packed_[1];
+    slot->key = tab.cdf;
+    slot->rows = tab.rows;
+    int* total_dev = err_ + 1;
+    pack_cdf(st, tab.cdf, tab.cols, tab.length, tab.rows, slot->row_off, slot->data, PACK_CAP, total_dev);
+    slot->has_lut = tab.cols > 64;   // wide rows (GaussianConditional): coarse inverse table for the decoder
+    if (slot->has_lut) build_decode_lut(st, tab.cdf, tab.cols, tab.length, tab.rows, slot->lut);
+    int total = 0;
+    CRA5_CUDA(cudaMemcpyAsync(&total, total_dev, sizeof(int), cudaMemcpyDeviceToHost, st));   // once per table
+    CRA5_CUDA(cudaStreamSynchronize(st));
+    slot->total = total;
+    slot->usable = total <= PACK_CAP && rans_tables_fit(tab.rows, total, slot->has_lut);
+  }
+  slot->stamp = ++pack_clock_;
+  return slot->usable ? slot : nullptr;
 }
 
 RansCoder::~RansCoder() {
@@ -76,6 +105,11 @@ RansCoder::~RansCoder() {
   cudaFreeHost(host_meta_);
   cudaFreeHost(host_stage_);
   cudaFree(lut_);
+  for (Packed& p : packed_) {
+    cudaFree(p.data);
+    cudaFree(p.row_off);
+    cudaFree(p.lut);
+  }
 }
 
 static void put_u32(uint8_t* p, uint32_t v) { memcpy(p, &v, 4); }
@@ -141,8 +175,12 @@ void RansCoder::encode_begin(cudaStream_t st, int slot, const int32_t* sym, cons
   const int cap_words = 2 * count_max + 6;
   CRA5_CHECK((size_t)n_streams * cap_words <= scratch_words_, ERR_INTERNAL, "rans_encode: scratch sizing");
   if (n_streams == 0 || L == 0) return;
-  rans_encode(st, sym, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, n_channels, L, spc, L > 0 ? L : 1,
-              scratch_, cap_words, lengths_, offsets_, payload_, err_);
+  if (const Packed* pk = packed_for(st, tab))
+    rans_encode_smem(st, sym, idx, idx == nullptr, pk->data, pk->row_off, tab.length, tab.offset, pk->rows, pk->total,
+                     n_channels, L, spc, L, scratch_, cap_words, lengths_, offsets_, payload_, err_);
+  else
+    rans_encode(st, sym, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, n_channels, L, spc, L > 0 ? L : 1,
+                scratch_, cap_words, lengths_, offsets_, payload_, err_);
   uint8_t* out_dev = static_cast<uint8_t*>(device_alias(host_mapped)) + head;   // 4-byte aligned: head is
   count_launch();
   container_to_host_kernel<<<XFER_BLOCKS, XFER_THREADS, 0, st>>>(
@@ -234,21 +272,27 @@ void RansCoder::decode(cudaStream_t st, const uint8_t* bytes, size_t len, const 
       reinterpret_cast<uint32_t*>(payload_));
   CRA5_CUDA(cudaGetLastError());
   scan_lengths(st, lengths_, (int)ns, offsets_);
-  // wide tables (GaussianConditional: up to 3133 entries per row) get a coarse inverse table; the per-channel
-  // EntropyBottleneck rows are a few dozen entries and are searched directly
-  const uint16_t* lut = nullptr;
-  int lut_rows = 0;
-  if (idx != nullptr && tab.rows <= 256 && tab.cols > 64) {
-    if (lut_for_ != tab.cdf || lut_rows_ != tab.rows) {
-      build_decode_lut(st, tab.cdf, tab.cols, tab.length, tab.rows, lut_);
-      lut_for_ = tab.cdf;
-      lut_rows_ = tab.rows;
+  if (const Packed* pk = packed_for(st, tab)) {
+    rans_decode_smem(st, payload_, offsets_, idx, idx == nullptr, pk->data, pk->row_off, tab.length, tab.offset,
+                     pk->has_lut ? pk->lut : nullptr, pk->rows, pk->total, n_channels, L, (int)spc, L, sym_out, mu, median,
+                     val_out, err_);
+  } else {
+    // wide tables (GaussianConditional: up to 3133 entries per row) get a coarse inverse table; the per-channel
+    // EntropyBottleneck rows are a few dozen entries and are searched directly
+    const uint16_t* lut = nullptr;
+    int lut_rows = 0;
+    if (idx != nullptr && tab.rows <= 256 && tab.cols > 64) {
+      if (lut_for_ != tab.cdf || lut_rows_ != tab.rows) {
+        build_decode_lut(st, tab.cdf, tab.cols, tab.length, tab.rows, lut_);
+        lut_for_ = tab.cdf;
+        lut_rows_ = tab.rows;
+      }
+      lut = lut_;
+      lut_rows = tab.rows;
     }
-    lut = lut_;
-    lut_rows = tab.rows;
+    rans_decode(st, payload_, offsets_, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, lut, lut_rows,
+                n_channels, L, (int)spc, L > 0 ? L : 1, sym_out, mu, median, val_out, err_);
   }
-  rans_decode(st, payload_, offsets_, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, lut, lut_rows,
-              n_channels, L, (int)spc, L > 0 ? L : 1, sym_out, mu, median, val_out, err_);
   word_to_host_kernel<<<1, 1, 0, st>>>(err_, host_meta_dev_);
   CRA5_CUDA(cudaGetLastError());
   CRA5_CUDA(cudaStreamSynchronize(st));

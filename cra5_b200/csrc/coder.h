@@ -40,11 +40,27 @@ class RansCoder {
                     int n_channels, int L, int spc, uint8_t* host_mapped, size_t host_cap);
   size_t encode_end(cudaStream_t st, int slot, int n_channels, int L, int spc, uint8_t* host_mapped, size_t host_cap);
   // container in host memory -> symbols and/or dequantised values on the device
-  void invalidate_lut() { lut_for_ = nullptr; lut_rows_ = 0; }
+  void invalidate_lut() { lut_for_ = nullptr; lut_rows_ = 0; packed_[0].key = packed_[1].key = nullptr; }
   void decode(cudaStream_t st, const uint8_t* bytes, size_t len, const uint8_t* idx, const CdfTable& tab,
               int n_channels, int L, int32_t* sym_out, const float* mu, const float* median, float* val_out);
 
  private:
+  // CDF table repacked for the shared-memory kernels (uint16 rows back to back + coarse inverse table), cached per
+  // table pointer: the model alternates between two tables (EntropyBottleneck, GaussianConditional)
+  struct Packed {
+    const int32_t* key = nullptr;
+    int rows = 0, total = 0;
+    bool usable = false, has_lut = false;
+    uint16_t* data = nullptr;
+    int32_t* row_off = nullptr;
+    uint16_t* lut = nullptr;
+    uint64_t stamp = 0;
+  };
+  const Packed* packed_for(cudaStream_t st, const CdfTable& tab);
+  static constexpr int PACK_CAP = 96 * 1024;   // entries
+  static constexpr int PACK_ROWS = 256;
+  Packed packed_[2];
+  uint64_t pack_clock_ = 0;
   size_t max_symbols_;
   int max_streams_;
   uint32_t *scratch_ = nullptr, *lengths_ = nullptr, *offsets_ = nullptr;

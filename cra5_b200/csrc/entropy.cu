@@ -559,6 +559,352 @@ void rans_decode(cudaStream_t st, const uint8_t* payload, const uint32_t* offset
   CRA5_CUDA(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------------ shared-memory tables
+// The serial chain of a sub-stream is bound by the latency of its table lookups, and the int32 CDF matrix (64 x 3133
+// for the GaussianConditional) only fits L2. Packed row after row as uint16 it is 27 256 entries = 54 KB (the final
+// 65536 of each row wraps to 0 and is recovered from `freq = (next - start) & 0xffff`), so every CTA keeps the whole
+// table -- plus the coarse inverse table for decoding -- in shared memory and a lookup costs ~30 cycles instead of an
+// L2 round trip. Stream words are prefetched one ahead, index / mean loads one batch ahead.
+__global__ void __launch_bounds__(256)
+pack_cdf_kernel(const int32_t* __restrict__ cdf, int cdf_stride, const int32_t* __restrict__ cdf_len, int rows,
+                int32_t* __restrict__ row_off, uint16_t* __restrict__ packed, int cap, int* __restrict__ total_out) {
+  __shared__ int total_s;
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int r = 0; r < rows; ++r) { row_off[r] = acc; acc += cdf_len[r]; }
+    row_off[rows] = acc;
+    total_s = acc;
+    *total_out = acc;
+  }
+  __syncthreads();
+  if (total_s > cap) return;
+  for (int r = 0; r < rows; ++r) {
+    const int n = cdf_len[r], o = row_off[r];
+    for (int v = threadIdx.x; v < n; v += blockDim.x) packed[o + v] = (uint16_t)cdf[(size_t)r * cdf_stride + v];
+  }
+}
+
+void pack_cdf(cudaStream_t st, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len, int rows, int32_t* row_off,
+              uint16_t* packed, int cap, int* total_dev) {
+  LaunchScope scope(st, "pack_cdf", 0.0, 0.0);
+  pack_cdf_kernel<<<1, 256, 0, st>>>(cdf, cdf_stride, cdf_len, rows, row_off, packed, cap, total_dev);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+constexpr int RANS_STHREADS = 64;   // two warps per CTA, each with an SM sub-partition to itself
+
+struct SmemTables {
+  const uint16_t* cdf16;   // [total] packed rows
+  const int32_t* row_off;  // [rows]
+  const int32_t* len;      // [rows]
+  const int32_t* off;      // [rows]
+  const uint16_t* lut;     // [rows][RANS_LUT] or null
+};
+// layout: cdf16 (total_pad uint16) | lut (rows * RANS_LUT uint16, optional, padded) | row_off | len | off (int32 each)
+__host__ __device__ inline size_t smem_tables_bytes(int rows, int total, bool with_lut) {
+  size_t b = (((size_t)total + 7) & ~size_t(7)) * 2;
+  if (with_lut) b += (((size_t)rows * RANS_LUT + 7) & ~size_t(7)) * 2;
+  return b + (size_t)rows * 12;
+}
+__device__ __forceinline__ SmemTables stage_tables(uint8_t* smem, const uint16_t* __restrict__ packed,
+                                                   const int32_t* __restrict__ row_off, const int32_t* __restrict__ cdf_len,
+                                                   const int32_t* __restrict__ offset, const uint16_t* __restrict__ lut_g,
+                                                   int rows, int total) {
+  const int total_pad = (total + 7) & ~7;
+  uint16_t* c16 = reinterpret_cast<uint16_t*>(smem);
+  uint16_t* lut = c16 + total_pad;
+  const int lut_pad = (lut_g != nullptr) ? ((rows * RANS_LUT + 7) & ~7) : 0;
+  int32_t* ro = reinterpret_cast<int32_t*>(lut + lut_pad);
+  int32_t* ln = ro + rows;
+  int32_t* of = ln + rows;
+  // 16-byte copies: the packed buffers are allocated with 8-entry slack
+  const uint4* src = reinterpret_cast<const uint4*>(packed);
+  for (int e = threadIdx.x; e < total_pad / 8; e += blockDim.x) reinterpret_cast<uint4*>(c16)[e] = src[e];
+  if (lut_g != nullptr) {
+    const uint4* ls = reinterpret_cast<const uint4*>(lut_g);
+    for (int e = threadIdx.x; e < lut_pad / 8; e += blockDim.x) reinterpret_cast<uint4*>(lut)[e] = ls[e];
+  }
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    ro[r] = row_off[r];
+    ln[r] = cdf_len[r];
+    of[r] = offset[r];
+  }
+  __syncthreads();
+  SmemTables t;
+  t.cdf16 = c16; t.row_off = ro; t.len = ln; t.off = of; t.lut = (lut_g != nullptr) ? lut : nullptr;
+  return t;
+}
+
+__global__ void __launch_bounds__(RANS_STHREADS)
+rans_encode_smem_kernel(const int32_t* __restrict__ sym, const uint8_t* __restrict__ idx, int index_is_channel,
+                        const uint16_t* __restrict__ packed, const int32_t* __restrict__ row_off,
+                        const int32_t* __restrict__ cdf_len, const int32_t* __restrict__ offset, int rows, int total,
+                        int n_channels, int L, int spc, int chan_len, uint32_t* __restrict__ scratch, int cap_words,
+                        uint32_t* __restrict__ lengths, int* __restrict__ err) {
+  extern __shared__ __align__(16) uint8_t tab_smem[];
+  const SmemTables T = stage_tables(tab_smem, packed, row_off, cdf_len, offset, nullptr, rows, total);
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_channels * spc) return;
+  const int c = s / spc, k = s - c * spc;
+  const int count = (L - k + spc - 1) / spc;
+  uint32_t* top = scratch + (size_t)(s + 1) * cap_words;
+  RansEnc e;
+  e.x = RANS_L;
+  e.ptr = top;
+  e.floor_ = top - cap_words + 2;
+  e.overflow = false;
+  const size_t base = (size_t)c * L + k;
+  int32_t sy[RANS_BATCH], ci[RANS_BATCH];
+  auto gather = [&](int i0) {   // symbols / indexes of the batch that ends at symbol i0 - 1 (consumed last to first)
+#pragma unroll
+    for (int b = 0; b < RANS_BATCH; ++b) {
+      const int i = max(i0 - 1 - b, 0);
+      const size_t pos = base + (size_t)i * spc;
+      sy[b] = sym[pos];
+      ci[b] = index_is_channel ? c : (int)idx[pos];
+    }
+  };
+  gather(count);
+  for (int i0 = count; i0 > 0; i0 -= RANS_BATCH) {
+    int32_t mxv[RANS_BATCH], val[RANS_BATCH];
+    uint32_t start[RANS_BATCH], freq[RANS_BATCH], raw[RANS_BATCH];
+    double rcp[RANS_BATCH];
+#pragma unroll
+    for (int b = 0; b < RANS_BATCH; ++b) {
+      const int r = ci[b];
+      mxv[b] = T.len[r] - 2;
+      const int32_t v = sy[b] - T.off[r];
+      const bool neg = v < 0, big = v >= mxv[b];
+      raw[b] = neg ? (uint32_t)(-2 * v - 1) : (big ? (uint32_t)(2 * (v - mxv[b])) : 0u);
+      val[b] = (neg || big) ? mxv[b] : v;
+      const uint16_t* row = T.cdf16 + T.row_off[r] + val[b];
+      start[b] = row[0];
+      freq[b] = ((uint32_t)row[1] - start[b]) & 0xffffu;
+      if (freq[b] == 0u) freq[b] = 65536u;
+    }
+    if (i0 - RANS_BATCH > 0) gather(i0 - RANS_BATCH);   // next batch's global loads fly during the serial phase
+#pragma unroll
+    for (int b = 0; b < RANS_BATCH; ++b) {
+      const double f = (double)freq[b];
+      double r = (double)__frcp_rn((float)freq[b]);
+      r = r * __fma_rn(-f, r, 2.0);
+      r = r * __fma_rn(-f, r, 2.0);
+      rcp[b] = r;
+    }
+#pragma unroll
+    for (int b = 0; b < RANS_BATCH; ++b) {
+      if (i0 - 1 - b >= 0) {
+        if (val[b] == mxv[b]) {
+          int32_t nb = 0;
+          while (nb < 8 && (raw[b] >> (nb * RANS_BYPASS_BITS)) != 0) ++nb;
+          for (int32_t j = nb - 1; j >= 0; --j)
+            e.put_bits((raw[b] >> (j * RANS_BYPASS_BITS)) & RANS_BYPASS_MAX, RANS_BYPASS_BITS);
+          e.put_bits((uint32_t)nb, RANS_BYPASS_BITS);
+        }
+        e.put(start[b], freq[b], rcp[b]);
+      }
+    }
+  }
+  e.ptr -= 2;
+  e.ptr[0] = (uint32_t)e.x;
+  e.ptr[1] = (uint32_t)(e.x >> 32);
+  lengths[s] = (uint32_t)(top - e.ptr) * 4u;
+  if (e.overflow) atomicExch(err, 1);
+}
+
+struct RansDecP {   // decoder state; the caller peeks the next stream word at the top of each symbol
+  uint64_t x;
+  const uint32_t* ptr;
+  const uint32_t* end;
+  bool underflow;
+  __device__ __forceinline__ void init(const uint32_t* p, const uint32_t* e) { ptr = p; end = e; underflow = false; }
+  // the address does not depend on the coder state of this symbol, so the load overlaps the state update; it lands in
+  // a fresh register (a conditional refill of a persistent look-ahead register makes the compiler wait on the load at
+  // the end of the conditional block)
+  __device__ __forceinline__ uint32_t peek() const { return (ptr < end) ? __ldg(ptr) : 0u; }
+  __device__ __forceinline__ void renorm(uint32_t peeked) {   // x < L: take the peeked word
+    if (ptr >= end) underflow = true;
+    x = (x << 32) | peeked;
+    ++ptr;
+  }
+  __device__ __forceinline__ uint32_t next() {
+    if (ptr < end) return __ldg(ptr++);
+    underflow = true;
+    return 0u;
+  }
+  __device__ __forceinline__ uint32_t get_bits(uint32_t nbits) {
+    const uint32_t val = (uint32_t)(x & ((1u << nbits) - 1));
+    x >>= nbits;
+    if (x < RANS_L) x = (x << 32) | next();
+    return val;
+  }
+};
+
+__global__ void __launch_bounds__(RANS_STHREADS)
+rans_decode_smem_kernel(const uint8_t* __restrict__ payload, const uint32_t* __restrict__ offsets,
+                        const uint8_t* __restrict__ idx, int index_is_channel, const uint16_t* __restrict__ packed,
+                        const int32_t* __restrict__ row_off, const int32_t* __restrict__ cdf_len,
+                        const int32_t* __restrict__ offset, const uint16_t* __restrict__ lut_g, int rows, int total,
+                        int n_channels, int L, int spc, int chan_len, int32_t* __restrict__ sym_out,
+                        const float* __restrict__ mu, const float* __restrict__ median, float* __restrict__ val_out,
+                        int* __restrict__ err) {
+  extern __shared__ __align__(16) uint8_t tab_smem[];
+  const SmemTables T = stage_tables(tab_smem, packed, row_off, cdf_len, offset, lut_g, rows, total);
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_channels * spc) return;
+  const int c = s / spc, k = s - c * spc;
+  const int count = (L - k + spc - 1) / spc;
+  RansDecP d;
+  d.init(reinterpret_cast<const uint32_t*>(payload + offsets[s]), reinterpret_cast<const uint32_t*>(payload + offsets[s + 1]));
+  {
+    const uint32_t lo = d.next(), hi = d.next();
+    d.x = (uint64_t)lo | ((uint64_t)hi << 32);
+  }
+  const size_t base = (size_t)c * L + k;
+  const float med = (val_out != nullptr && mu == nullptr) ? median[c] : 0.f;
+  int ci[RANS_BATCH], ci_n[RANS_BATCH];
+  float mean[RANS_BATCH], mean_n[RANS_BATCH];
+  auto gather = [&](int i0, int (&cc)[RANS_BATCH], float (&mm)[RANS_BATCH]) {
+#pragma unroll
+    for (int b = 0; b < RANS_BATCH; ++b) {
+      const int i = min(i0 + b, count - 1);
+      const size_t pos = base + (size_t)i * spc;
+      cc[b] = index_is_channel ? c : (int)idx[pos];
+      mm[b] = (val_out == nullptr) ? 0.f : ((mu != nullptr) ? mu[pos] : med);
+    }
+  };
+  gather(0, ci, mean);
+  for (int i0 = 0; i0 < count; i0 += RANS_BATCH) {
+    if (i0 + RANS_BATCH < count) gather(i0 + RANS_BATCH, ci_n, mean_n);
+    int32_t outv[RANS_BATCH];
+#pragma unroll
+    for (int b = 0; b < RANS_BATCH; ++b) {
+      outv[b] = 0;
+      if (i0 + b >= count) break;
+      const int r = ci[b];
+      const uint32_t peeked = d.peek();
+      const uint16_t* row = T.cdf16 + T.row_off[r];
+      const int32_t n_entries = T.len[r];
+      const int32_t max_value = n_entries - 2;
+      const uint32_t cum = (uint32_t)(d.x & 0xffffu);
+      int lo, hi;   // last v in [0, n_entries-1) with row[v] <= cum  (row[n_entries-1] = 65536 is stored as 0, never probed)
+      if (T.lut != nullptr) {
+        const uint16_t* lr = T.lut + r * RANS_LUT + (cum >> 8);
+        lo = lr[0];
+        hi = lr[1];
+      } else {
+        lo = 0;
+        hi = n_entries - 2;
+      }
+      if (hi - lo <= 4) {
+        // the usual case (a 256-wide bucket of the inverse table spans a handful of symbols except in the far tails):
+        // four independent probes, no dependent chain, no divergence. The row is increasing, so the hits form a prefix.
+        const uint16_t* pr = row + lo;
+        const int c1 = (lo + 1 <= hi) & ((uint32_t)pr[1] <= cum);
+        const int c2 = (lo + 2 <= hi) & ((uint32_t)pr[2] <= cum);
+        const int c3 = (lo + 3 <= hi) & ((uint32_t)pr[3] <= cum);
+        const int c4 = (lo + 4 <= hi) & ((uint32_t)pr[4] <= cum);
+        lo += c1 + c2 + c3 + c4;
+      } else {
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if ((uint32_t)row[mid] <= cum) lo = mid; else hi = mid - 1;
+        }
+      }
+      const uint32_t start = row[lo];
+      uint32_t freq = ((uint32_t)row[lo + 1] - start) & 0xffffu;
+      if (freq == 0u) freq = 65536u;
+      d.x = (uint64_t)freq * (d.x >> RANS_PRECISION) + cum - start;
+      if (d.x < RANS_L) d.renorm(peeked);
+      int32_t value = lo;
+      if (value == max_value) {  // bypass, rans_interface.cpp:256-278
+        int32_t val = (int32_t)d.get_bits(RANS_BYPASS_BITS);
+        int32_t nb = val;
+        while (val == RANS_BYPASS_MAX && !d.underflow) {
+          val = (int32_t)d.get_bits(RANS_BYPASS_BITS);
+          nb += val;
+        }
+        uint32_t raw = 0;
+        for (int32_t j = 0; j < nb; ++j) {
+          val = (int32_t)d.get_bits(RANS_BYPASS_BITS);
+          if (j < 8) raw |= (uint32_t)val << (j * RANS_BYPASS_BITS);
+          if (d.underflow) break;
+        }
+        value = (int32_t)(raw >> 1);
+        if (raw & 1u) value = -value - 1; else value += max_value;
+      }
+      outv[b] = value + T.off[r];
+    }
+#pragma unroll
+    for (int b = 0; b < RANS_BATCH; ++b) {
+      const int i = i0 + b;
+      if (i < count) {
+        const size_t pos = base + (size_t)i * spc;
+        if (sym_out != nullptr) sym_out[pos] = outv[b];
+        if (val_out != nullptr) val_out[pos] = __fadd_rn((float)outv[b], mean[b]);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < RANS_BATCH; ++b) { ci[b] = ci_n[b]; mean[b] = mean_n[b]; }
+  }
+  if (d.underflow) atomicExch(err, 2);
+}
+
+// smem-table variants of rans_encode / rans_decode: `packed` / `row_off` from pack_cdf (total entries), optional coarse
+// inverse table `lut` for decoding. Return false (nothing launched) when the tables do not fit shared memory.
+bool rans_tables_fit(int rows, int total, bool with_lut) {
+  return smem_tables_bytes(rows, total, with_lut) <= 200 * 1024;
+}
+
+void rans_encode_smem(cudaStream_t st, const int32_t* sym, const uint8_t* idx, bool index_is_channel,
+                      const uint16_t* packed, const int32_t* row_off, const int32_t* cdf_len, const int32_t* offset,
+                      int rows, int total, int n_channels, int L, int spc, int chan_len, uint32_t* scratch, int cap_words,
+                      uint32_t* lengths, uint32_t* offsets, uint8_t* payload, int* err) {
+  const int n_streams = n_channels * spc;
+  if (n_streams == 0) return;
+  const size_t smem = smem_tables_bytes(rows, total, false);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    CRA5_CUDA(cudaFuncSetAttribute(rans_encode_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  {
+    LaunchScope scope(st, "rans_encode", 0.0, (double)n_channels * L * (index_is_channel ? 4.0 : 5.0));
+    rans_encode_smem_kernel<<<(n_streams + RANS_STHREADS - 1) / RANS_STHREADS, RANS_STHREADS, smem, st>>>(
+        sym, idx, index_is_channel ? 1 : 0, packed, row_off, cdf_len, offset, rows, total, n_channels, L, spc, chan_len,
+        scratch, cap_words, lengths, err);
+  }
+  CRA5_CUDA(cudaGetLastError());
+  {
+    LaunchScope scope(st, "scan_lengths", 0.0, 8.0 * n_streams);
+    scan_lengths_kernel<<<1, 1024, 0, st>>>(lengths, n_streams, offsets);
+  }
+  CRA5_CUDA(cudaGetLastError());
+  LaunchScope scope(st, "compact_streams", 0.0, 0.0);
+  compact_streams_kernel<<<(n_streams * 32 + 255) / 256, 256, 0, st>>>(scratch, cap_words, lengths, offsets, n_streams,
+                                                                       payload);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+void rans_decode_smem(cudaStream_t st, const uint8_t* payload, const uint32_t* offsets, const uint8_t* idx,
+                      bool index_is_channel, const uint16_t* packed, const int32_t* row_off, const int32_t* cdf_len,
+                      const int32_t* offset, const uint16_t* lut, int rows, int total, int n_channels, int L, int spc,
+                      int chan_len, int32_t* sym_out, const float* mu, const float* median, float* val_out, int* err) {
+  const int n_streams = n_channels * spc;
+  if (n_streams == 0) return;
+  const size_t smem = smem_tables_bytes(rows, total, lut != nullptr);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    CRA5_CUDA(cudaFuncSetAttribute(rans_decode_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  LaunchScope scope(st, "rans_decode", 0.0, (double)n_channels * L * (index_is_channel ? 4.0 : 9.0));
+  rans_decode_smem_kernel<<<(n_streams + RANS_STHREADS - 1) / RANS_STHREADS, RANS_STHREADS, smem, st>>>(
+      payload, offsets, idx, index_is_channel ? 1 : 0, packed, row_off, cdf_len, offset, lut, rows, total, n_channels, L,
+      spc, chan_len, sym_out, mu, median, val_out, err);
+  CRA5_CUDA(cudaGetLastError());
+}
+
 void scan_lengths(cudaStream_t st, const uint32_t* lengths, int n, uint32_t* offsets) {
   LaunchScope scope(st, "scan_lengths", 0.0, 8.0 * n);
   scan_lengths_kernel<<<1, 1024, 0, st>>>(lengths, n, offsets);

@@ -62,5 +62,17 @@ void rans_decode(cudaStream_t st, const uint8_t* payload, const uint32_t* offset
 void build_decode_lut(cudaStream_t st, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len, int rows,
                       uint16_t* lut);
 void scan_lengths(cudaStream_t st, const uint32_t* lengths, int n, uint32_t* offsets);
+// shared-memory-table variants (CDF rows packed as uint16, see entropy.cu)
+void pack_cdf(cudaStream_t st, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len, int rows, int32_t* row_off,
+              uint16_t* packed, int cap, int* total_dev);
+bool rans_tables_fit(int rows, int total, bool with_lut);
+void rans_encode_smem(cudaStream_t st, const int32_t* sym, const uint8_t* idx, bool index_is_channel,
+                      const uint16_t* packed, const int32_t* row_off, const int32_t* cdf_len, const int32_t* offset,
+                      int rows, int total, int n_channels, int L, int spc, int chan_len, uint32_t* scratch, int cap_words,
+                      uint32_t* lengths, uint32_t* offsets, uint8_t* payload, int* err);
+void rans_decode_smem(cudaStream_t st, const uint8_t* payload, const uint32_t* offsets, const uint8_t* idx,
+                      bool index_is_channel, const uint16_t* packed, const int32_t* row_off, const int32_t* cdf_len,
+                      const int32_t* offset, const uint16_t* lut, int rows, int total, int n_channels, int L, int spc,
+                      int chan_len, int32_t* sym_out, const float* mu, const float* median, float* val_out, int* err);
 
 }  // namespace cra5
