@@ -97,6 +97,22 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    captures (profiles/r1_traffic.json; a number measured under the profiler, so it is read, never re-measured here)"""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return None, "no capture committed"
+    t = json.load(open(p))
+    sites = {"gemm_tc": ["qkv", "proj", "fc1", "fc2"], "attn_tc": ["attn_global"], "rans_decode": ["rans_dec"],
+             "rans_encode": ["rans_enc"], "gc_quantize_index": ["quantize"], "layernorm_bf16": ["layernorm"]}.get(kernel, [])
+    vals = [t[s]["dram_bytes_per_launch"] for s in sites if s in t]
+    if not vals:
+        return None, "no capture of this kernel"
+    return sum(vals) / len(vals), ("profiles/r1_traffic.json: mean over the captured launches " + "/".join(s for s in sites if s in t)
+                                   + " (one trunk block; cold-cache single launches under ncu)")
+
+
 def workload(cfg):
     return (f"full encode->rANS bin->decode round trip, {cfg.in_chans}x721x1440 frame, vaeformer quality={cfg.in_chans} "
             f"(BASELINE.json configs[2]), one frame per step per GPU")
@@ -278,17 +294,20 @@ def run_b200(args):
                 a[f] += k[f]
         top = max(by_kernel.items(), key=lambda kv: kv[1]["ms"])
         tname, tk = top
+        traffic, traffic_src = ncu_traffic(tname)
         if tk["flops"] > 0:
             achieved = tk["flops"] / (tk["ms"] / 1e3) / 1e12
             roofline = {"kernel": tname, "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"],
-                        "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"], "traffic": None,
+                        "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"], "traffic": traffic,
+                        "traffic_source": traffic_src, "algorithmic_bytes_per_launch": tk["bytes"] / tk["launches"],
                         "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
                         "share_of_step": tk["ms"] / tot, "launches_per_step": tk["launches"] / 2,
                         "avg_launch_ms": tk["ms"] / tk["launches"]}
         else:
             achieved = tk["bytes"] / (tk["ms"] / 1e3) / 1e9
             roofline = {"kernel": tname, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                        "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                        "peak_source": peaks["source"],
                         "share_of_step": tk["ms"] / tot}
         sites = {n: {"ms_per_step": round(k["ms"] / 2, 4), "launches_per_step": k["launches"] / 2,
                      "tflops": round(k["flops"] / (k["ms"] / 1e3) / 1e12, 1) if k["flops"] and k["ms"] else None}
