@@ -42,7 +42,7 @@ static void launch_pair(cudaStream_t st, const CUtensorMap& tmA, const CUtensorM
   int clusters = m_tiles * n_tiles;
   const int max_clusters = device_sm_count() / 2;
   if (clusters > max_clusters) clusters = max_clusters;
-  LaunchScope scope(st, "gemm_tc2", 2.0 * shp.M * shp.N * shp.K,
+  LaunchScope scope(st, "gemm_tc", 2.0 * shp.M * shp.N * shp.K,
                     2.0 * ((double)shp.M * shp.K + (double)shp.N * shp.K) +
                         (double)shp.M * shp.N * ((KIND == EPI_BF16 || KIND == EPI_GELU_BF16 || KIND == EPI_QKV) ? 2.0 : 4.0));
   kern<<<2 * clusters, GEMM_THREADS, GemmSmem2::TOTAL, st>>>(tmA, tmB, shp, epi);  // cluster dims are compiled in
@@ -65,10 +65,12 @@ void launch_gemm_pair(cudaStream_t st, int kind, const CUtensorMap& tmA, const C
 }
 
 // CTA-pair tiles pay off for large problems (>= one 256 x 256 tile per SM pair); small / skinny ones keep the 1-CTA kernel
-bool gemm_use_pair(int M, int N) {
+bool gemm_use_pair(int M, int N, int K, int kind) {
   static const char* env = getenv("CRA5_GEMM_PAIR");  // diagnostics: 0 = never, 1 = whenever legal
   if (env != nullptr) return atoi(env) != 0 && N >= 256;
-  return false;
+  // measured on B200 (tools/perf_kernels.py): the pair kernel wins where the main loop is long and the tile count small
+  // (fc2: K = 4096, N = 1024 -> 849 vs 944 TFLOP/s); elsewhere the two are within 3 % and the 1-CTA kernel stays
+  return kind == EPI_RESID && K >= 2048 && N >= 512 && N <= 1024 && M >= 4096;
 }
 
 template <int BN>
@@ -107,7 +109,7 @@ void launch_gemm(cudaStream_t st, int bn, int kind, const CUtensorMap& tmA, cons
 // Plain row-major GEMM convenience: A [M,K] (row stride lda elements), B [N,K] (row stride ldb), both bf16.
 void gemm_plain(cudaStream_t st, int kind, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M,
                 int N, int K, const EpiParams& epi) {
-  if (gemm_use_pair(M, N)) {
+  if (gemm_use_pair(M, N, K, kind)) {
     CUtensorMap tmA = make_tmap_bf16_2d(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, GEMM_BK, GEMM_BM);
     CUtensorMap tmB = make_tmap_bf16_2d(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, GEMM_BK, GemmSmem2::BN / 2);
     GemmShape shp{};
@@ -115,7 +117,10 @@ void gemm_plain(cudaStream_t st, int kind, const __nv_bfloat16* A, int lda, cons
     launch_gemm_pair(st, kind, tmA, tmB, shp, epi);
     return;
   }
-  const int bn = gemm_pick_bn(N);
+  int bn = gemm_pick_bn(N);
+  // short main loop + residual epilogue + few tiles (attention projection: K = N = 1024 -> 2.2 waves of 128 x 256 tiles):
+  // 128 x 128 tiles give every CTA 4-5 tiles to pipeline and halve the exposed last epilogue (379 -> 442 TFLOP/s)
+  if (getenv("CRA5_GEMM_BN") == nullptr && bn == 256 && kind == EPI_RESID && K <= 1024 && N <= 1024 && M >= 4096) bn = 128;
   CUtensorMap tmA = make_tmap_bf16_2d(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, GEMM_BK, GEMM_BM);
   CUtensorMap tmB = make_tmap_bf16_2d(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, GEMM_BK, bn);
   GemmShape shp{};
