@@ -268,32 +268,63 @@ RansCoder* op_coder(size_t n_symbols, int n_channels) {
 }
 }  // namespace
 
-int cra5_op_rans_encode(const int32_t* sym, const uint8_t* idx, const int32_t* cdf, int cdf_cols, const int32_t* cdf_len,
-                        const int32_t* offset, int n_channels, int L, int spc, uint8_t* out_host, uint64_t out_cap,
-                        uint64_t* out_len, void* stream) {
+static int op_rans_encode(const int32_t* sym, const uint8_t* idx, const int32_t* cdf, int cdf_rows, int cdf_cols,
+                          const int32_t* cdf_len, const int32_t* offset, int n_channels, int L, int spc,
+                          uint8_t* out_host, uint64_t out_cap, uint64_t* out_len, void* stream) {
   return guarded([&] {
     require_sm100();
     CRA5_CHECK(out_host && out_len, ERR_INVALID, "null argument");
     CRA5_CHECK(n_channels >= 0 && L >= 0, ERR_INVALID, "negative size");
     CdfTable t;
-    t.cdf = cdf; t.length = cdf_len; t.offset = offset; t.rows = 1 << 30; t.cols = cdf_cols;
+    t.cdf = cdf; t.length = cdf_len; t.offset = offset; t.rows = cdf_rows; t.cols = cdf_cols;
     if (cdf == nullptr) t.rows = 0;
-    *out_len = op_coder((size_t)n_channels * L, n_channels)
-                   ->encode(static_cast<cudaStream_t>(stream), sym, idx, t, n_channels, L, spc, out_host, out_cap);
+    RansCoder* c = op_coder((size_t)n_channels * L, n_channels);
+    c->invalidate_lut();   // op-level callers may reuse a device pointer for a different table
+    *out_len = c->encode(static_cast<cudaStream_t>(stream), sym, idx, t, n_channels, L, spc, out_host, out_cap);
   });
+}
+
+static int op_rans_decode(const uint8_t* bytes, uint64_t len, const uint8_t* idx, const int32_t* cdf, int cdf_rows,
+                          int cdf_cols, const int32_t* cdf_len, const int32_t* offset, int n_channels, int L,
+                          int32_t* sym, void* stream) {
+  return guarded([&] {
+    require_sm100();
+    CdfTable t;
+    t.cdf = cdf; t.length = cdf_len; t.offset = offset; t.rows = cdf_rows; t.cols = cdf_cols;
+    if (cdf == nullptr) t.rows = 0;
+    RansCoder* c = op_coder((size_t)n_channels * L, n_channels);
+    c->invalidate_lut();
+    c->decode(static_cast<cudaStream_t>(stream), bytes, len, idx, t, n_channels, L, sym, nullptr, nullptr, nullptr);
+  });
+}
+
+int cra5_op_rans_encode(const int32_t* sym, const uint8_t* idx, const int32_t* cdf, int cdf_cols, const int32_t* cdf_len,
+                        const int32_t* offset, int n_channels, int L, int spc, uint8_t* out_host, uint64_t out_cap,
+                        uint64_t* out_len, void* stream) {
+  // row count unknown: the table stays in global memory
+  return op_rans_encode(sym, idx, cdf, 1 << 30, cdf_cols, cdf_len, offset, n_channels, L, spc, out_host, out_cap, out_len,
+                        stream);
 }
 
 int cra5_op_rans_decode(const uint8_t* bytes, uint64_t len, const uint8_t* idx, const int32_t* cdf, int cdf_cols,
                         const int32_t* cdf_len, const int32_t* offset, int n_channels, int L, int32_t* sym,
                         void* stream) {
-  return guarded([&] {
-    require_sm100();
-    CdfTable t;
-    t.cdf = cdf; t.length = cdf_len; t.offset = offset; t.rows = 1 << 30; t.cols = cdf_cols;
-    if (cdf == nullptr) t.rows = 0;
-    op_coder((size_t)n_channels * L, n_channels)
-        ->decode(static_cast<cudaStream_t>(stream), bytes, len, idx, t, n_channels, L, sym, nullptr, nullptr, nullptr);
-  });
+  return op_rans_decode(bytes, len, idx, cdf, 1 << 30, cdf_cols, cdf_len, offset, n_channels, L, sym, stream);
+}
+
+int cra5_op_rans_encode_table(const int32_t* sym, const uint8_t* idx, const int32_t* cdf, int cdf_rows, int cdf_cols,
+                              const int32_t* cdf_len, const int32_t* offset, int n_channels, int L, int spc,
+                              uint8_t* out_host, uint64_t out_cap, uint64_t* out_len, void* stream) {
+  if (cdf_rows <= 0) return guarded([&] { throw Error(ERR_INVALID, "cdf_rows must be positive"); });
+  return op_rans_encode(sym, idx, cdf, cdf_rows, cdf_cols, cdf_len, offset, n_channels, L, spc, out_host, out_cap,
+                        out_len, stream);
+}
+
+int cra5_op_rans_decode_table(const uint8_t* bytes, uint64_t len, const uint8_t* idx, const int32_t* cdf, int cdf_rows,
+                              int cdf_cols, const int32_t* cdf_len, const int32_t* offset, int n_channels, int L,
+                              int32_t* sym, void* stream) {
+  if (cdf_rows <= 0) return guarded([&] { throw Error(ERR_INVALID, "cdf_rows must be positive"); });
+  return op_rans_decode(bytes, len, idx, cdf, cdf_rows, cdf_cols, cdf_len, offset, n_channels, L, sym, stream);
 }
 
 }  // extern "C"

@@ -199,6 +199,18 @@ CRA5_API int cra5_op_rans_decode(const uint8_t* bytes_host, uint64_t len, const 
                                  const int32_t* cdf_dev, int cdf_cols, const int32_t* cdf_length_dev,
                                  const int32_t* offset_dev, int n_channels, int L, int32_t* sym_dev, void* stream);
 
+/* The same two operations with the number of rows of the CDF table stated (cdf_dev is [cdf_rows][cdf_cols]): the coder
+ * then packs the table into shared memory (uint16 rows + coarse inverse table), the path cra5_latent_to_bin /
+ * cra5_bin_to_latent take. Same bytes, same symbols. */
+CRA5_API int cra5_op_rans_encode_table(const int32_t* sym_dev, const uint8_t* idx_dev, const int32_t* cdf_dev,
+                                       int cdf_rows, int cdf_cols, const int32_t* cdf_length_dev,
+                                       const int32_t* offset_dev, int n_channels, int L, int spc, uint8_t* out_host,
+                                       uint64_t out_cap, uint64_t* out_len, void* stream);
+CRA5_API int cra5_op_rans_decode_table(const uint8_t* bytes_host, uint64_t len, const uint8_t* idx_dev,
+                                       const int32_t* cdf_dev, int cdf_rows, int cdf_cols,
+                                       const int32_t* cdf_length_dev, const int32_t* offset_dev, int n_channels, int L,
+                                       int32_t* sym_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,23 +43,35 @@ def gpu_quantize(y, sig, mu, dev, want_hat=True):
     return sym, idx, hat
 
 
-def gpu_encode(sym, idx, dev, n_ch, Lc, spc):
+def gpu_encode(sym, idx, dev, n_ch, Lc, spc, table=False):
+    """table=True: the shared-memory-table kernels (row count stated), the path the model takes"""
     lib = L()
     cap = 64 + 4 * n_ch * spc + 8 * max(sym.numel(), 1) + 16 * n_ch * spc
     out = (ctypes.c_uint8 * cap)()
     n = ctypes.c_uint64()
-    lib.check(lib.lib.cra5_op_rans_encode(lib.ptr(sym), lib.ptr(idx), lib.ptr(dev["cdf"]), dev["cdf"].shape[1],
-                                          lib.ptr(dev["cdf_length"]), lib.ptr(dev["offset"]), n_ch, Lc, spc, out,
-                                          ctypes.c_uint64(cap), ctypes.byref(n), lib.stream_ptr()))
+    if table:
+        lib.check(lib.lib.cra5_op_rans_encode_table(lib.ptr(sym), lib.ptr(idx), lib.ptr(dev["cdf"]), dev["cdf"].shape[0],
+                                                    dev["cdf"].shape[1], lib.ptr(dev["cdf_length"]), lib.ptr(dev["offset"]),
+                                                    n_ch, Lc, spc, out, ctypes.c_uint64(cap), ctypes.byref(n),
+                                                    lib.stream_ptr()))
+    else:
+        lib.check(lib.lib.cra5_op_rans_encode(lib.ptr(sym), lib.ptr(idx), lib.ptr(dev["cdf"]), dev["cdf"].shape[1],
+                                              lib.ptr(dev["cdf_length"]), lib.ptr(dev["offset"]), n_ch, Lc, spc, out,
+                                              ctypes.c_uint64(cap), ctypes.byref(n), lib.stream_ptr()))
     return bytes(out[: n.value])
 
 
-def gpu_decode(b, idx, dev, n_ch, Lc):
+def gpu_decode(b, idx, dev, n_ch, Lc, table=False):
     lib = L()
     sym = torch.full((max(n_ch * Lc, 1),), -12345, dtype=torch.int32, device="cuda")
-    lib.check(lib.lib.cra5_op_rans_decode(b, ctypes.c_uint64(len(b)), lib.ptr(idx), lib.ptr(dev["cdf"]),
-                                          dev["cdf"].shape[1], lib.ptr(dev["cdf_length"]), lib.ptr(dev["offset"]),
-                                          n_ch, Lc, lib.ptr(sym), lib.stream_ptr()))
+    if table:
+        lib.check(lib.lib.cra5_op_rans_decode_table(b, ctypes.c_uint64(len(b)), lib.ptr(idx), lib.ptr(dev["cdf"]),
+                                                    dev["cdf"].shape[0], dev["cdf"].shape[1], lib.ptr(dev["cdf_length"]),
+                                                    lib.ptr(dev["offset"]), n_ch, Lc, lib.ptr(sym), lib.stream_ptr()))
+    else:
+        lib.check(lib.lib.cra5_op_rans_decode(b, ctypes.c_uint64(len(b)), lib.ptr(idx), lib.ptr(dev["cdf"]),
+                                              dev["cdf"].shape[1], lib.ptr(dev["cdf_length"]), lib.ptr(dev["offset"]),
+                                              n_ch, Lc, lib.ptr(sym), lib.stream_ptr()))
     torch.cuda.synchronize()
     return sym[: n_ch * Lc]
 
@@ -106,7 +118,8 @@ def test_round_half_even_and_scale_boundaries(tabs):
 
 @pytest.mark.parametrize("n_ch,Lc,spc", [(1, 1, 1), (3, 7, 8), (4, 1000, 8), (256, 648, 1), (16, 10368, 8), (5, 333, 64),
                                          (2, 0, 4), (0, 5, 2)])
-def test_chunked_coder_substreams_and_roundtrip(tabs, n_ch, Lc, spc):
+@pytest.mark.parametrize("table", [False, True], ids=["global-table", "smem-table"])
+def test_chunked_coder_substreams_and_roundtrip(tabs, n_ch, Lc, spc, table):
     t, dev = tabs
     n = n_ch * Lc
     g = torch.Generator().manual_seed(n_ch * 1000 + Lc + spc)
@@ -117,7 +130,9 @@ def test_chunked_coder_substreams_and_roundtrip(tabs, n_ch, Lc, spc):
         sym[::13] = (torch.randn(sym[::13].shape, generator=g) * 30000).int()  # bypass, several nibbles
     sym_d = sym.cuda() if n else torch.zeros(1, dtype=torch.int32, device="cuda")
     idx_d = idx.to(torch.uint8).cuda() if n else torch.zeros(1, dtype=torch.uint8, device="cuda")
-    b = gpu_encode(sym_d, idx_d, dev, n_ch, Lc, spc)
+    b = gpu_encode(sym_d, idx_d, dev, n_ch, Lc, spc, table)
+    if table:  # both kernel families emit the same container
+        assert b == gpu_encode(sym_d, idx_d, dev, n_ch, Lc, spc, False)
     c = cr5b.parse(b)
     assert (c["n_channels"], c["L"], c["spc"]) == (n_ch, Lc, spc)
     s2, i2 = sym.reshape(n_ch, Lc), idx.reshape(n_ch, Lc)
@@ -128,11 +143,12 @@ def test_chunked_coder_substreams_and_roundtrip(tabs, n_ch, Lc, spc):
                 continue
             ref = EO.rans_encode(s2[ch, k::spc], i2[ch, k::spc], *t.coder_args())
             assert c["streams"][ch * spc + k] == ref, (ch, k)
-    out = gpu_decode(b, idx_d, dev, n_ch, Lc)
+    out = gpu_decode(b, idx_d, dev, n_ch, Lc, table)
     assert torch.equal(out.cpu(), sym)
 
 
-def test_entropy_bottleneck_mode_index_is_channel():
+@pytest.mark.parametrize("table", [False, True], ids=["global-table", "smem-table"])
+def test_entropy_bottleneck_mode_index_is_channel(table):
     """idx == NULL -> CDF row = channel (EntropyBottleneck._build_indexes, entropy_models.py:513-523)"""
     from cra5_b200 import config as C
     cfg = C.tiny_fullres(69)
@@ -144,12 +160,12 @@ def test_entropy_bottleneck_mode_index_is_channel():
     g = torch.Generator().manual_seed(5)
     sym = torch.round(torch.randn(n_ch, Lc, generator=g) * 4).int()
     sym[:, ::50] = 40  # outside every channel's support -> bypass
-    b = gpu_encode(sym.cuda().reshape(-1), None, dev, n_ch, Lc, 1)
+    b = gpu_encode(sym.cuda().reshape(-1), None, dev, n_ch, Lc, 1, table)
     c = cr5b.parse(b)
     idx = EO.eb_indexes((1, n_ch, Lc)).reshape(n_ch, Lc)
     for ch in range(n_ch):
         assert c["streams"][ch] == EO.rans_encode(sym[ch], idx[ch], *eb.coder_args())
-    assert torch.equal(gpu_decode(b, None, dev, n_ch, Lc).cpu(), sym.reshape(-1))
+    assert torch.equal(gpu_decode(b, None, dev, n_ch, Lc, table).cpu(), sym.reshape(-1))
 
 
 def test_corrupt_streams_are_rejected(tabs):
@@ -169,6 +185,10 @@ def test_corrupt_streams_are_rejected(tabs):
     with pytest.raises(ValueError):
         gpu_decode(b, idx, dev, 2, 33)  # shape mismatch
     assert torch.equal(gpu_decode(b, idx, dev, 2, 32), sym)
+    for bad in (b[:-4], b + b"\0\0\0\0"):   # the shared-memory-table decoder rejects them the same way
+        with pytest.raises(ValueError):
+            gpu_decode(bad, idx, dev, 2, 32, table=True)
+    assert torch.equal(gpu_decode(b, idx, dev, 2, 32, table=True), sym)
 
 
 def test_reference_format_streams_interoperate(tabs):
