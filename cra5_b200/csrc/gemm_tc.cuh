@@ -477,6 +477,33 @@ __device__ __forceinline__ void epilogue_bf16_fast(const uint32_t (&acc)[32], co
   __syncwarp();
 }
 
+// V^T (EPI_QKV, chunk wholly inside one head of V): the same idea transposed -- the row owner drops its 32 values into
+// a [dim][row] bf16 staging tile (2-byte stores, one contiguous 64-byte line per dim), then the warp writes 16-byte
+// pieces = 8 consecutive rows of one dim of V^T[head][dim][rows_total].
+__device__ __forceinline__ void epilogue_vt_fast(const uint32_t (&acc)[32], const float* __restrict__ bias, int col0,
+                                                 uint8_t* stage, __nv_bfloat16* vt_d0_row0, size_t rows_total,
+                                                 int rows_valid, int lane) {
+  __nv_bfloat16* st16 = reinterpret_cast<__nv_bfloat16*>(stage);
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
+    st16[(i + 0) * 32 + lane] = __float2bfloat16(__uint_as_float(acc[i]) + b.x);
+    st16[(i + 1) * 32 + lane] = __float2bfloat16(__uint_as_float(acc[i + 1]) + b.y);
+    st16[(i + 2) * 32 + lane] = __float2bfloat16(__uint_as_float(acc[i + 2]) + b.z);
+    st16[(i + 3) * 32 + lane] = __float2bfloat16(__uint_as_float(acc[i + 3]) + b.w);
+  }
+  __syncwarp();
+  const int c = lane & 3;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int d = it * 8 + (lane >> 2);
+    const uint4 u = *reinterpret_cast<const uint4*>(stage + d * 64 + c * 16);
+    if (c * 8 < rows_valid) *reinterpret_cast<uint4*>(vt_d0_row0 + (size_t)d * rows_total + c * 8) = u;
+  }
+  __syncwarp();
+}
+
 // kinds whose natural store direction is along the ROWS (thread = row): written straight from registers
 template <int KIND>
 __device__ __forceinline__ constexpr bool epi_is_direct() { return KIND == EPI_T_F32 || KIND == EPI_PIXSHUF; }
@@ -671,6 +698,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __nv_bfloat16* base = (which == 0 ? epi.q : epi.k) + ((size_t)head * epi.rows_total + row_base) * epi.hd + d0;
             epilogue_bf16_fast<KIND>(acc, epi.bias, col0, which == 0 ? epi.qscale : 1.0f, reinterpret_cast<uint8_t*>(stg),
                                      base, (size_t)epi.hd, min(32, shp.M - row_base), lane);
+          }
+        }
+        if constexpr (KIND == EPI_QKV) {   // a chunk wholly inside one head of V: transposed store
+          if (!fast && direct && (((epi.D | epi.hd) & 31) == 0) && ((epi.rows_total & 7) == 0) && ((shp.M & 7) == 0) &&
+              ((reinterpret_cast<uintptr_t>(epi.vt) & 15) == 0) &&
+              (epi.bias == nullptr || (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0)) {
+            const int within = col0 - 2 * epi.D;
+            const int head = within / epi.hd, d0 = within - head * epi.hd;
+            epilogue_vt_fast(acc, epi.bias, col0, reinterpret_cast<uint8_t*>(stg),
+                             epi.vt + ((size_t)head * epi.hd + d0) * epi.rows_total + row_base, (size_t)epi.rows_total,
+                             min(32, shp.M - row_base), lane);
+            fast = true;
           }
         }
         if (fast) {
@@ -900,6 +939,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             __nv_bfloat16* base = (which == 0 ? epi.q : epi.k) + ((size_t)head * epi.rows_total + row_base) * epi.hd + d0;
             epilogue_bf16_fast<KIND>(acc, epi.bias, col0, which == 0 ? epi.qscale : 1.0f, reinterpret_cast<uint8_t*>(stg),
                                      base, (size_t)epi.hd, min(32, shp.M - row_base), lane);
+          }
+        }
+        if constexpr (KIND == EPI_QKV) {   // a chunk wholly inside one head of V: transposed store
+          if (!fast && direct && (((epi.D | epi.hd) & 31) == 0) && ((epi.rows_total & 7) == 0) && ((shp.M & 7) == 0) &&
+              ((reinterpret_cast<uintptr_t>(epi.vt) & 15) == 0) &&
+              (epi.bias == nullptr || (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0)) {
+            const int within = col0 - 2 * epi.D;
+            const int head = within / epi.hd, d0 = within - head * epi.hd;
+            epilogue_vt_fast(acc, epi.bias, col0, reinterpret_cast<uint8_t*>(stg),
+                             epi.vt + ((size_t)head * epi.hd + d0) * epi.rows_total + row_base, (size_t)epi.rows_total,
+                             min(32, shp.M - row_base), lane);
+            fast = true;
           }
         }
         if (fast) {
