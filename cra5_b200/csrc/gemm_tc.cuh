@@ -504,6 +504,69 @@ __device__ __forceinline__ void epilogue_vt_fast(const uint32_t (&acc)[32], cons
   __syncwarp();
 }
 
+// fp32 outputs with an fp32 addend (EPI_RESID: residual stream, rows scattered through the window map; EPI_F32: bias +
+// pos-embed): same scheme at 128 bytes per row. Phase 1 (before the accumulator is read, so the DRAM / L2 latency
+// overlaps it): every lane fetches the 16-byte piece of the addend it will need in phase 2. Phase 2: the row owner
+// parks its 32 floats as eight swizzled 16-byte pieces; the warp then adds and writes four whole 128-byte row
+// segments per instruction. The addend may alias the output: each element is read and written by the same lane.
+struct F32Fast {
+  float4 add[8];
+  float4 bias;
+  int my_t;      // output row of the accumulator row this lane owns, -1: none
+  bool on;
+};
+template <int KIND>
+__device__ __forceinline__ void epilogue_f32_prefetch(const EpiParams& p, int row_base, int col0, int lane, int M, int N,
+                                                      F32Fast& f) {
+  const float* src = (KIND == EPI_RESID) ? p.resid : p.add;
+  const int ld_src = (KIND == EPI_RESID) ? p.ldo : p.lda;
+  f.on = (col0 + 32 <= N) && ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0) &&
+         (src == nullptr || (((ld_src & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0))) &&
+         (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) &&
+         (KIND != EPI_RESID || p.out_bf16 == nullptr ||
+          ((((p.ld_bf16 | p.bf16_col0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_bf16) & 7) == 0)));
+  if (!f.on) return;
+  const int row = row_base + lane;
+  f.my_t = (row < M) ? ((KIND == EPI_RESID) ? p.wm.to_token(row) : row) : -1;
+  const int piece = lane & 7;
+  f.bias = (p.bias != nullptr) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + piece * 4))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int t = __shfl_sync(0xffffffffu, f.my_t, it * 4 + (lane >> 3));
+    f.add[it] = (src != nullptr)
+                    ? *reinterpret_cast<const float4*>(src + (size_t)max(t, 0) * ld_src + col0 + piece * 4)
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+template <int KIND>
+__device__ __forceinline__ void epilogue_f32_finish(const EpiParams& p, const uint32_t (&acc)[32], uint8_t* stage,
+                                                    int col0, int lane, const F32Fast& f) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<uint4*>(stage + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+        make_uint4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+  __syncwarp();
+  const int piece = lane & 7;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3);
+    const int t = __shfl_sync(0xffffffffu, f.my_t, r);
+    const float4 u = *reinterpret_cast<const float4*>(stage + r * 128 + ((piece ^ (r & 7)) << 4));
+    if (t >= 0) {
+      const float4 v = make_float4(u.x + f.bias.x + f.add[it].x, u.y + f.bias.y + f.add[it].y,
+                                   u.z + f.bias.z + f.add[it].z, u.w + f.bias.w + f.add[it].w);
+      *reinterpret_cast<float4*>(p.out_f32 + (size_t)t * p.ldo + col0 + piece * 4) = v;
+      if constexpr (KIND == EPI_RESID) {
+        if (p.out_bf16 != nullptr)
+          *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)t * p.ld_bf16 + p.bf16_col0 + col0 + piece * 4) =
+              make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // kinds whose natural store direction is along the ROWS (thread = row): written straight from registers
 template <int KIND>
 __device__ __forceinline__ constexpr bool epi_is_direct() { return KIND == EPI_T_F32 || KIND == EPI_PIXSHUF; }
@@ -671,10 +734,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (col0 >= shp.N) break;  // warp-uniform
         float rv[32];
         int my_t = -1;
-        if constexpr (KIND == EPI_RESID) epilogue_resid_load(epi, row_base, col0, lane, shp.M, shp.N, rv, my_t);
+        F32Fast ff;
+        ff.on = false;
+        if constexpr (KIND == EPI_RESID || KIND == EPI_F32) epilogue_f32_prefetch<KIND>(epi, row_base, col0, lane, shp.M, shp.N, ff);
+        if constexpr (KIND == EPI_RESID) {
+          if (!ff.on) epilogue_resid_load(epi, row_base, col0, lane, shp.M, shp.N, rv, my_t);
+        }
         uint32_t acc[32];
         tmem_ld_32x32(taddr + c, acc);
         tmem_ld_wait();
+        if constexpr (KIND == EPI_RESID || KIND == EPI_F32) {
+          if (ff.on) {   // warp-uniform
+            epilogue_f32_finish<KIND>(epi, acc, reinterpret_cast<uint8_t*>(stg), col0, lane, ff);
+            continue;
+          }
+        }
         bool direct = epi_is_direct<KIND>();
         if constexpr (KIND == EPI_QKV)  // a chunk that lies wholly inside V is written transposed, thread = row
           direct = (col0 >= 2 * epi.D) && (col0 + 32 <= shp.N);
@@ -913,10 +987,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (col0 >= shp.N) break;  // warp-uniform
         float rv[32];
         int my_t = -1;
-        if constexpr (KIND == EPI_RESID) epilogue_resid_load(epi, row_base, col0, lane, shp.M, shp.N, rv, my_t);
+        F32Fast ff;
+        ff.on = false;
+        if constexpr (KIND == EPI_RESID || KIND == EPI_F32) epilogue_f32_prefetch<KIND>(epi, row_base, col0, lane, shp.M, shp.N, ff);
+        if constexpr (KIND == EPI_RESID) {
+          if (!ff.on) epilogue_resid_load(epi, row_base, col0, lane, shp.M, shp.N, rv, my_t);
+        }
         uint32_t acc[32];
         tmem_ld_32x32(taddr + c, acc);
         tmem_ld_wait();
+        if constexpr (KIND == EPI_RESID || KIND == EPI_F32) {
+          if (ff.on) {   // warp-uniform
+            epilogue_f32_finish<KIND>(epi, acc, reinterpret_cast<uint8_t*>(stg), col0, lane, ff);
+            continue;
+          }
+        }
         bool direct = epi_is_direct<KIND>();
         if constexpr (KIND == EPI_QKV) direct = (col0 >= 2 * epi.D) && (col0 + 32 <= shp.N);
         bool fast = false;
