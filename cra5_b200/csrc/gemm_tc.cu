@@ -70,6 +70,8 @@ bool gemm_use_pair(int M, int N, int K, int kind) {
   if (env != nullptr) return atoi(env) != 0 && N >= 256;
   // measured on B200 (tools/perf_kernels.py): the pair kernel wins where the main loop is long and the tile count small
   // (fc2: K = 4096, N = 1024 -> 849 vs 944 TFLOP/s); elsewhere the two are within 3 % and the 1-CTA kernel stays
+  // ... and, with the light bf16 epilogues, for the widest plain shape (qkv: N = 3072 -> 1137 vs 1224 TFLOP/s)
+  if (kind == EPI_QKV && N >= 3072 && M >= 4096) return true;
   return kind == EPI_RESID && K >= 2048 && N >= 512 && N <= 1024 && M >= 4096;
 }
 
