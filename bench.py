@@ -260,7 +260,9 @@ def run_b200(args):
         e2e_run(2)
         barrier()
         t0 = time.perf_counter()
-        n_e2e = max(4, min(args.steps, 12))
+        # enough frames that the un-overlapped pipeline fill (first H2D) and drain (last D2H), ~45 ms together, stop
+        # dominating a PCIe-bound steady state of ~25 ms per frame
+        n_e2e = max(8, min(3 * args.steps, 48))
         e2e_run(n_e2e)
         barrier()
         dt = time.perf_counter() - t0
