@@ -323,6 +323,45 @@ def run_b200(args):
             if n in kernels and kernels[n]["gbs"]:
                 kernels[n]["hbm_frac"] = kernels[n]["gbs"] / peaks["hbm_gbs"]
 
+    # ---- the fused quantise + scale-index kernel at B = 8 (at B = 1 its 45 MB launch lasts 15 us and is
+    #      launch-latency bound; BASELINE.json configs[4] batches 8 frames per GPU): 8 frames' latents in one launch,
+    #      17 algorithmic bytes per element (read y, sigma, mu; write int32 symbol + uint8 index), working set 361 MB > L2
+    entropy_b8 = None
+    if not args.no_kernel_profile and rank == 0:
+        try:
+            from cra5_b200.entropy_tables import get_scale_table
+            n8 = 8 * cfg.latent_chans * cfg.tokens
+            g8 = torch.Generator(device=dev).manual_seed(5)
+            y8 = torch.randn(n8, device=dev, generator=g8) * 4.0
+            s8 = torch.rand(n8, device=dev, generator=g8) * 4.0
+            m8 = torch.randn(n8, device=dev, generator=g8)
+            sym8 = torch.empty(n8, dtype=torch.int32, device=dev)
+            idx8 = torch.empty(n8, dtype=torch.uint8, device=dev)
+            tab8 = get_scale_table().to(device=dev, dtype=torch.float32).contiguous()
+
+            def q8():
+                _lib.check(_lib.lib.cra5_op_gc_quantize(_lib.ptr(y8), _lib.ptr(s8), _lib.ptr(m8), _lib.ptr(tab8), int(tab8.numel()),
+                                                        ctypes.c_float(0.11), _lib.ptr(sym8), _lib.ptr(idx8), _lib.ptr(None),
+                                                        ctypes.c_uint64(n8), _lib.stream_ptr()))
+            for _ in range(3):
+                q8()
+            a8, b8 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            a8.record()
+            for _ in range(10):
+                q8()
+            b8.record()
+            torch.cuda.synchronize(dev)
+            ms8 = a8.elapsed_time(b8) / 10
+            gbs8 = n8 * 17.0 / (ms8 / 1e3) / 1e9
+            pk = measured_peaks()
+            entropy_b8 = {"kernel": "gc_quantize_index", "frames_per_launch": 8, "elements": n8, "ms_per_launch": ms8,
+                          "achieved": gbs8, "unit": "GB/s", "peak": pk["hbm_gbs"], "frac": gbs8 / pk["hbm_gbs"],
+                          "bound": "hbm", "algorithmic_bytes_per_element": 17}
+            del y8, s8, m8, sym8, idx8
+        except Exception as e:  # an extra, never a reason to lose the bench line
+            entropy_b8 = {"error": repr(e)}
+
     # ---- CPU baseline (oracle port on the host cores), rank 0, N == 1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -349,7 +388,7 @@ def run_b200(args):
                        "bytes_per_frame": nbytes, "coder": "CR5B chunk-parallel rANS, 16 sub-streams per y channel, 4 per z channel"},
             "gb_era5_per_s": fps * frame_bytes / 1e9,
             "e2e": e2e, "gpu_launches": int(lc1.value - lc0.value), "clocks": clock_info,
-            "roofline": roofline, "kernels": kernels, "kernel_sites": sites if kernels else None, "cpu_baseline": cpu,
+            "roofline": roofline, "entropy_b8": entropy_b8, "kernels": kernels, "kernel_sites": sites if kernels else None, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
