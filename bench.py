@@ -40,52 +40,139 @@ def parse():
 
 # ------------------------------------------------------------------------------------------------ helpers
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)"""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md clocks line).
+
+    Two sources run side by side: an NVML polling thread (one sample every `period_s`, so a 0.2 s timed region still
+    yields ~20 samples; NVML calls release the GIL) and the recipe's `nvidia-smi -lms 100` loop as the fall-back when
+    NVML cannot be loaded. `stop()` reports the median SM clock under load, the maximum SM clock, the union of the
+    slow-down reasons seen, and which source the numbers came from."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # NVML nvmlClocksEventReason* bit masks (nvml.h)
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, pci_bus_id=None, period_s=0.02, nvml=None):
         self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.bus = pci_bus_id
+        self.period = period_s
+        self.nvml = nvml
+        self.f = None
         self.p = None
+        self.thread = None
+        self.stop_flag = None
+        self.samples = []     # (sm_mhz, reasons bit mask, power_w)
+        self.max_mhz = None
+
+    # ---- NVML thread
+    def _nvml_open(self):
+        try:
+            nv = self.nvml
+            if nv is None:
+                import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if self.bus:
+                try:
+                    h = nv.nvmlDeviceGetHandleByPciBusId(self.bus.encode() if isinstance(self.bus, str) else self.bus)
+                except Exception:
+                    h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            return nv, h
+        except Exception:
+            return None, None
+
+    def _poll(self, nv, h):
+        reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self.stop_flag.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(reasons(h)) if reasons is not None else 0
+                try:
+                    watts = nv.nvmlDeviceGetPowerUsage(h) / 1e3
+                except Exception:
+                    watts = None
+                self.samples.append((mhz, mask, watts))
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
 
     def start(self):
+        import threading
+        nv, h = self._nvml_open()
+        if nv is not None:
+            self.stop_flag = threading.Event()
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
         try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
                                        "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
+    def _stop_smi(self):
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 9:
-                continue
+        if self.p is not None:
+            self.p.terminate()
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, parts[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        os.unlink(self.f.name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+        if self.f is not None:
+            try:
+                self.f.flush()
+                self.f.seek(0)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for line in self.f.read().splitlines():
+                    parts = [p.strip() for p in line.split(",")]
+                    if len(parts) < 9:
+                        continue
+                    try:
+                        sm.append(float(parts[1]))
+                        mx.append(float(parts[2]))
+                    except ValueError:
+                        continue
+                    for n, v in zip(names, parts[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(n)
+                self.f.close()
+                os.unlink(self.f.name)
+            except Exception:
+                pass
+        return sm, mx, reasons
+
+    def stop(self):
+        try:
+            if self.thread is not None:
+                self.stop_flag.set()
+                self.thread.join(timeout=2)
+            sm, mx, reasons = self._stop_smi()
+            if self.samples:
+                mhz = [s[0] for s in self.samples]
+                mask = 0
+                for s in self.samples:
+                    mask |= s[1]
+                watts = [s[2] for s in self.samples if s[2] is not None]
+                out = {"sm_mhz": statistics.median(mhz), "sm_max_mhz": self.max_mhz or (max(mx) if mx else max(mhz)),
+                       "reasons": sorted(set(n for n, b in self.BITS.items() if mask & b) | reasons),
+                       "samples": len(mhz), "sm_mhz_min": min(mhz), "source": f"nvml, one sample per {self.period * 1e3:.0f} ms"}
+                if watts:
+                    out["power_w_max"] = max(watts)
+                if sm:
+                    out["nvidia_smi"] = {"sm_mhz": statistics.median(sm), "samples": len(sm)}
+                return out
+            if sm:
+                return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                        "samples": len(sm), "source": "nvidia-smi -lms 100"}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples (neither NVML nor nvidia-smi answered)"]}
+        except Exception as e:  # the clocks line is evidence, never a reason to lose the bench line
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"clock sampler failed: {e!r}"]}
 
 
 def measured_peaks():
@@ -247,7 +334,12 @@ def run_b200(args):
     # ---- timed region: device-resident inputs
     lc0 = ctypes.c_uint64()
     lc1 = ctypes.c_uint64()
-    clocks = ClockSampler(local)
+    try:  # NVML enumerates physical devices: address this rank's GPU by PCI bus id (robust to CUDA_VISIBLE_DEVICES)
+        pr = torch.cuda.get_device_properties(dev)
+        bus_id = f"{pr.pci_domain_id:08X}:{pr.pci_bus_id:02X}:{pr.pci_device_id:02X}.0"
+    except Exception:
+        bus_id = None
+    clocks = ClockSampler(local, pci_bus_id=bus_id)
     barrier()
     clocks.start()
     _lib.check(_lib.lib.cra5_launch_count(ctypes.byref(lc0)))
@@ -386,9 +478,11 @@ def run_b200(args):
             "metric": "ERA5 frames/s (268x721x1440) encode+decode", "value": fps, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 tensor-core operands, fp32 accumulate/residual/softmax; int32/u8 entropy stage",
+            "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": workload(cfg),
+                       "precision": "bf16 tensor-core operands, fp32 accumulate / residual stream / softmax / LayerNorm; "
+                                    "fp32 quantise + scale index; int32 / u8 / u64 entropy coder (bit-exact)",
                        "l2": "inputs larger than L2: two alternating 1.1 GB frames, every kernel's working set is re-streamed",
                        "weights": "random init of the named architecture (seed 1234), CDF tables from update(force=True)",
                        "bytes_per_frame": nbytes, "coder": "CR5B chunk-parallel rANS, 16 sub-streams per y channel, 4 per z channel"},

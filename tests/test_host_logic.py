@@ -150,3 +150,59 @@ def test_frame_sharding_world_size_2_gloo():
     assert stream.shard_frames(5, 0, 1) == [0, 1, 2, 3, 4] and stream.max_over_ranks(3.5) == 3.5
     with pytest.raises(ValueError):
         stream.shard_frames(5, 2, 2)
+
+
+class _FakeNvml:
+    """stands in for pynvml: a clock that sags under load and a power-cap flag on the later samples"""
+    NVML_CLOCK_SM = 1
+
+    def __init__(self):
+        self.n = 0
+        self.bus = None
+
+    def nvmlInit(self):
+        pass
+
+    def nvmlDeviceGetHandleByPciBusId(self, bus):
+        self.bus = bus
+        return "h"
+
+    def nvmlDeviceGetHandleByIndex(self, i):
+        return "h"
+
+    def nvmlDeviceGetMaxClockInfo(self, h, kind):
+        return 1965
+
+    def nvmlDeviceGetClockInfo(self, h, kind):
+        self.n += 1
+        return 1965 if self.n < 3 else 1400
+
+    def nvmlDeviceGetCurrentClocksEventReasons(self, h):
+        return 0x4 if self.n > 4 else 0
+
+    def nvmlDeviceGetPowerUsage(self, h):
+        return 987000
+
+
+def test_bench_clock_sampler_and_reference_arm_ranks(monkeypatch, capsys):
+    """bench.py host logic: the clocks line takes many samples inside a short timed region (NVML thread), reports the
+    median under load / the maximum clock / the union of slow-down reasons, degrades to 'no samples' without a driver;
+    the reference arm prints nothing on ranks other than 0."""
+    import time
+    import types
+    import bench
+    nv = _FakeNvml()
+    c = bench.ClockSampler(0, pci_bus_id="00000000:1B:00.0", period_s=0.005, nvml=nv)
+    c.start()
+    time.sleep(0.15)
+    r = c.stop()
+    assert nv.bus == b"00000000:1B:00.0"
+    assert r["samples"] >= 10 and r["sm_mhz"] == 1400.0 and r["sm_max_mhz"] == 1965.0
+    assert r["reasons"] == ["sw_power_cap"] and r["power_w_max"] == 987.0 and r["source"].startswith("nvml")
+    if not torch.cuda.is_available():
+        r = bench.ClockSampler(0).stop()                     # never started, no driver: still a well-formed dict
+        assert r["sm_mhz"] is None and r["reasons"]
+    monkeypatch.setenv("RANK", "1")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    bench.run_reference(types.SimpleNamespace(channels=268, steps=1, warmup=1, gpus=2))
+    assert capsys.readouterr().out == ""
