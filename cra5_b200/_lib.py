@@ -3,7 +3,9 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcra5b200.so")
+# CRA5_PDL=1 selects the build variant whose kernel chain uses programmatic dependent launch (cra5_b200/build.py)
+VARIANT = "pdl" if os.environ.get("CRA5_PDL", "0") not in ("", "0") else ""
+LIB_PATH = os.path.join(_HERE, "lib", f"libcra5b200{'_' + VARIANT if VARIANT else ''}.so")
 
 
 class Cra5Error(RuntimeError):

@@ -214,6 +214,7 @@ attn_mma_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __rest
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.z, seg = blockIdx.y;
   const size_t row0 = (size_t)seg * S;
+  pdl_grid_sync();
   // ---- stage K rows [0, S) and V^T columns [0, S) of this (segment, head); zero the padding
   {
     const uint8_t* kg = reinterpret_cast<const uint8_t*>(K + ((size_t)head * rows_total + row0) * HD);
@@ -381,8 +382,7 @@ static bool launch_attn_mma(cudaStream_t st, const __nv_bfloat16* Q, const __nv_
   }
   dim3 grid((S + AM_QPB - 1) / AM_QPB, rows_total / S, heads);
   LaunchScope scope(st, "attn_small", 4.0 * heads * (double)rows_total * S * HD, 4.0 * 2.0 * heads * (double)rows_total * HD);
-  attn_mma_kernel<HD><<<grid, AM_WARPS * 32, smem, st>>>(Q, K, Vt, out, ldo, rows_total, S, s_pad, sv);
-  CRA5_CUDA(cudaGetLastError());
+  launch_chained(attn_mma_kernel<HD>, grid, dim3(AM_WARPS * 32), smem, st, Q, K, Vt, out, ldo, rows_total, S, s_pad, sv);
   return true;
 }
 

@@ -210,6 +210,7 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();
 
   if (warp < 4) {
     reg_dec<64>();    // the pool setmaxnreg draws from is what the launch allocated: 384 x 168 >= 128 x 64 + 256 x 216
@@ -489,8 +490,7 @@ void attention_tc(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* 
   const int grid = n_items < device_sm_count() ? n_items : device_sm_count();
   LaunchScope scope(st, "attn_tc", 4.0 * heads * (double)rows_total * seg_len * A4_HD,
                     4.0 * 2.0 * heads * (double)rows_total * A4_HD);
-  kern<<<grid, A4_THREADS, A4Smem::TOTAL, st>>>(tmQ, tmK, tmVt, p);
-  CRA5_CUDA(cudaGetLastError());
+  launch_chained(kern, dim3(grid), dim3(A4_THREADS), A4Smem::TOTAL, st, tmQ, tmK, tmVt, p);
 }
 
 }  // namespace cra5

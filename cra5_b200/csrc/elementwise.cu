@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __rest
                                                              const float* __restrict__ beta, float eps,
                                                              __nv_bfloat16* __restrict__ out, int rows_out, int D,
                                                              WinMap wm) {
+  pdl_grid_sync();  // reads x and overwrites `out`, which the previous kernels may still be using
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows_out) return;
@@ -163,6 +164,7 @@ template <int NV>  // NV = D / 128 float4 groups per lane
 __global__ void __launch_bounds__(256) layernorm_bf16_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, float eps,
                                                                  __nv_bfloat16* __restrict__ out, int rows_out, WinMap wm) {
+  pdl_grid_sync();
   constexpr int D = NV * 128;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -211,23 +213,21 @@ void layernorm_bf16(cudaStream_t st, const float* x, const float* gamma, const f
   const int blocks = (rows_out + 7) / 8;
   LaunchScope scope(st, "layernorm_bf16", 0.0, 6.0 * rows_out * (double)D);
   if (D == 1024) {
-    layernorm_bf16_vec_kernel<8><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, rows_out, wm);
-    CRA5_CUDA(cudaGetLastError());
+    launch_chained(layernorm_bf16_vec_kernel<8>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, out, rows_out, wm);
     return;
   }
   if (D == 128) {
-    layernorm_bf16_vec_kernel<1><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, rows_out, wm);
-    CRA5_CUDA(cudaGetLastError());
+    launch_chained(layernorm_bf16_vec_kernel<1>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, out, rows_out, wm);
     return;
   }
   if (D <= 128)
-    layernorm_bf16_kernel<4><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, rows_out, D, wm);
+    launch_chained(layernorm_bf16_kernel<4>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, out, rows_out, D, wm);
   else if (D <= 512)
-    layernorm_bf16_kernel<16><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, rows_out, D, wm);
+    launch_chained(layernorm_bf16_kernel<16>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, out, rows_out, D, wm);
   else if (D <= 1024)
-    layernorm_bf16_kernel<32><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, rows_out, D, wm);
+    launch_chained(layernorm_bf16_kernel<32>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, out, rows_out, D, wm);
   else if (D <= 2048)
-    layernorm_bf16_kernel<64><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, rows_out, D, wm);
+    launch_chained(layernorm_bf16_kernel<64>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, out, rows_out, D, wm);
   else
     throw Error(ERR_INVALID, "layernorm: width > 2048 unsupported");
   CRA5_CUDA(cudaGetLastError());

@@ -24,8 +24,7 @@ static void launch_one(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMa
   LaunchScope scope(st, "gemm_tc", 2.0 * shp.M * shp.N * shp.K,
                     2.0 * ((double)shp.M * shp.K + (double)shp.N * shp.K) +
                         (double)shp.M * shp.N * ((KIND == EPI_BF16 || KIND == EPI_GELU_BF16 || KIND == EPI_QKV) ? 2.0 : 4.0));
-  kern<<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, st>>>(tmA, tmB, shp, epi);
-  CRA5_CUDA(cudaGetLastError());
+  launch_chained(kern, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN>::TOTAL, st, tmA, tmB, shp, epi);
 }
 
 template <int KIND>
@@ -45,8 +44,7 @@ static void launch_pair(cudaStream_t st, const CUtensorMap& tmA, const CUtensorM
   LaunchScope scope(st, "gemm_tc", 2.0 * shp.M * shp.N * shp.K,
                     2.0 * ((double)shp.M * shp.K + (double)shp.N * shp.K) +
                         (double)shp.M * shp.N * ((KIND == EPI_BF16 || KIND == EPI_GELU_BF16 || KIND == EPI_QKV) ? 2.0 : 4.0));
-  kern<<<2 * clusters, GEMM_THREADS, GemmSmem2::TOTAL, st>>>(tmA, tmB, shp, epi);  // cluster dims are compiled in
-  CRA5_CUDA(cudaGetLastError());
+  launch_chained(kern, dim3(2 * clusters), dim3(GEMM_THREADS), GemmSmem2::TOTAL, st, tmA, tmB, shp, epi);  // cluster dims are compiled in
 }
 
 void launch_gemm_pair(cudaStream_t st, int kind, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp,

@@ -624,6 +624,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();  // everything above overlaps the previous kernel's tail in the CRA5_PDL build
 
   if (warp == 0) {
     if (lane == 0) {
@@ -881,6 +882,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();
 
   if (warp == 0) {
     if (lane == 0) {

@@ -73,4 +73,30 @@ struct TagScope {
 };
 void require_sm100();
 
+// Launch of a kernel on the per-frame chain (LayerNorm -> GEMM -> attention -> GEMM ...). Default build: a plain
+// stream launch. -DCRA5_PDL=1 build: programmatic stream serialisation, i.e. the kernel may become resident while its
+// predecessor drains; such a kernel MUST call pdl_grid_sync() (ptx.cuh) before touching global memory.
+#ifndef CRA5_PDL
+#define CRA5_PDL 0
+#endif
+template <typename... KArgs, typename... Args>
+inline void launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+#if CRA5_PDL
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  CRA5_CUDA(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+#else
+  kern<<<grid, block, smem, st>>>(args...);
+  CRA5_CUDA(cudaGetLastError());
+#endif
+}
+
 }  // namespace cra5

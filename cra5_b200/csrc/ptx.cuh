@@ -24,6 +24,25 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Compiled in only with -DCRA5_PDL=1 (the libcra5b200_pdl.so build variant, selected at load time by CRA5_PDL=1);
+// in the default build these are empty, so the default library's SASS does not change.
+// Contract: a kernel launched through launch_chained() (host_util.h) calls pdl_grid_sync() with EVERY thread after its
+// prologue (barrier init, TMEM allocation, descriptor prefetch -- nothing that touches memory another kernel writes)
+// and before its first global-memory access. `wait` returns once the preceding grid in the stream has completed and its
+// writes are visible; `launch_dependents` then lets the NEXT kernel's CTAs become resident and run their own prologue
+// while this grid computes (they block in their own `wait`). Triggering only after the wait bounds the look-ahead to
+// one kernel.
+#ifndef CRA5_PDL
+#define CRA5_PDL 0
+#endif
+__device__ __forceinline__ void pdl_grid_sync() {
+#if CRA5_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -68,6 +68,14 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(_lib.lib, n), f"{n} declared in include/cra5_b200.h but not exported"
     assert _lib.lib.cra5_abi_version() >= 1
+    # every build variant (cra5_b200/build.py) exports the same ABI
+    from cra5_b200 import build as B
+    for variant in B.VARIANTS:
+        path = B.lib_path(variant)
+        assert os.path.exists(path), f"{path} missing: run python -m cra5_b200.build"
+        v = ctypes.CDLL(path)
+        for n_ in names:
+            assert hasattr(v, n_), f"{n_} not exported by {os.path.basename(path)}"
 
 
 def test_cdf_tables_through_c_abi_match_oracle():
