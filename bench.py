@@ -33,6 +33,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--channels", type=int, default=268, help="268 (headline), 159 or 69")
+    ap.add_argument("--lanes", type=int, default=1,
+                    help="codec lanes per GPU (cra5_b200.stream.CodecLanes; experimental, default 1 = one stream)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true")
     return ap.parse_args()
@@ -343,14 +345,31 @@ def run_b200(args):
     barrier()
     clocks.start()
     _lib.check(_lib.lib.cra5_launch_count(ctypes.byref(lc0)))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
-    barrier()
+    lane_launches = None
+    if args.lanes > 1:
+        # experimental: frames alternate between L codec lanes (own handle + stream + host thread each, shared weights)
+        from cra5_b200.stream import CodecLanes
+        lanes = CodecLanes(net, lanes=args.lanes)
+
+        def lane_step(codec, i):
+            o = codec.compress(frames[i % n_frames])
+            codec.decompress(o["strings"], o["z_shape"])
+            return len(o["strings"][0][0]) + len(o["strings"][1][0])
+
+        lanes.run(lane_step, 2 * args.lanes)     # every lane warms its own workspace / tables
+        barrier()
+        _, ms_total = lanes.run(lane_step, args.steps, timed=True)
+        barrier()
+        lane_launches = lanes.launches()
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
     _lib.check(_lib.lib.cra5_launch_count(ctypes.byref(lc1)))
-    ms_total = e0.elapsed_time(e1)
     clock_info = clocks.stop()
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
@@ -485,9 +504,11 @@ def run_b200(args):
                                     "fp32 quantise + scale index; int32 / u8 / u64 entropy coder (bit-exact)",
                        "l2": "inputs larger than L2: two alternating 1.1 GB frames, every kernel's working set is re-streamed",
                        "weights": "random init of the named architecture (seed 1234), CDF tables from update(force=True)",
-                       "bytes_per_frame": nbytes, "coder": "CR5B chunk-parallel rANS, 16 sub-streams per y channel, 4 per z channel"},
+                       "bytes_per_frame": nbytes, "coder": "CR5B chunk-parallel rANS, 16 sub-streams per y channel, 4 per z channel",
+                       "lanes": args.lanes, "build": _lib.VARIANT or "default"},
             "gb_era5_per_s": fps * frame_bytes / 1e9,
-            "e2e": e2e, "gpu_launches": int(lc1.value - lc0.value), "clocks": clock_info,
+            "e2e": e2e, "gpu_launches": int(lane_launches if lane_launches is not None else lc1.value - lc0.value),
+            "clocks": clock_info,
             "roofline": roofline, "entropy_b8": entropy_b8, "kernels": kernels, "kernel_sites": sites if kernels else None, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

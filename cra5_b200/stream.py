@@ -50,6 +50,109 @@ def stream_frames(codec, frames: Iterable, rank: int, world: int, n_frames: int)
         yield i, out["strings"], rec["x_hat"]
 
 
+class CodecLanes:
+    """Several codec lanes on ONE GPU (experimental until timed on a B200; bench.py --lanes, tools/check_overlap.py).
+
+    Lane k = its own library handle (`VAEformer.replica()`: own workspace and bitstream buffers, shared weights) on its
+    own CUDA stream, driven by its own host thread; item i runs on lane i mod L. Frames are independent units, so the
+    lanes never exchange data and every item's result is bit-identical to the single-lane result. What the lanes buy
+    is occupancy: a persistent GEMM with 2.2 waves of tiles leaves most SMs idle during its last wave, and
+    `latent_to_bin` synchronises the host on the bitstream length -- with a second lane queued, the block scheduler
+    fills those holes with the other frame's kernels. The library is re-entrant across handles (thread-local error
+    and profiler state, per-handle buffers); ctypes releases the GIL during each call, so the lanes' launches overlap.
+
+        lanes = CodecLanes(net, lanes=2)
+        results, ms = lanes.run(lambda codec, i: roundtrip(codec, frames[i % 2]), n_items=10, timed=True)
+    """
+
+    def __init__(self, net, lanes: int = 2, streams=None):
+        if lanes < 1:
+            raise ValueError("lanes must be >= 1")
+        self.nets = [net] + [net.replica() for _ in range(lanes - 1)]
+        self.device = getattr(net, "device", None)
+        if streams is None:
+            import torch
+            streams = [torch.cuda.Stream(self.device) for _ in range(lanes)]
+        if len(streams) != lanes:
+            raise ValueError("one stream per lane")
+        self.streams = streams
+
+    @staticmethod
+    def _enter(stream):
+        import contextlib
+        if stream is None:                 # CPU tests of the orchestration: no CUDA streams
+            return contextlib.nullcontext()
+        import torch
+        return torch.cuda.stream(stream)
+
+    def launches(self) -> int:
+        """kernel launches counted by the library on the lanes' host threads during the last run()"""
+        return int(sum(self._launches))
+
+    def run(self, fn, n_items: int, timed: bool = False):
+        """fn(codec, i) for i in range(n_items), item i on lane i mod L; returns the results in item order (and, with
+        timed=True, the device time in ms between a start event every lane waits for and an end event recorded after
+        every lane has finished -- CUDA events, not wall clock)."""
+        import threading
+        L = len(self.nets)
+        results = [None] * n_items
+        errors = [None] * L
+        self._launches = [0] * L
+        cuda = self.streams[0] is not None
+        start = end = cur = None
+        if cuda:
+            import torch
+            cur = torch.cuda.current_stream(self.device)
+            if timed:
+                start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                start.record(cur)
+            for s in self.streams:
+                s.wait_stream(cur)         # inputs produced on the caller's stream are visible to every lane
+
+        def lane(k):
+            try:
+                if cuda:
+                    import torch
+                    torch.cuda.set_device(self.device)   # a new host thread starts on device 0
+                with self._enter(self.streams[k]):
+                    n0 = self._count()
+                    for i in range(k, n_items, L):
+                        results[i] = fn(self.nets[k], i)
+                    self._launches[k] = self._count() - n0
+            except BaseException as e:  # re-raised on the caller's thread
+                errors[k] = e
+
+        threads = [threading.Thread(target=lane, args=(k,), name=f"cra5-lane-{k}") for k in range(1, L)]
+        for t in threads:
+            t.start()
+        lane(0)                            # lane 0 runs on the caller's thread
+        for t in threads:
+            t.join()
+        if cuda:
+            for s in self.streams:
+                cur.wait_stream(s)         # results are ordered before whatever the caller enqueues next
+        for e in errors:
+            if e is not None:
+                raise e
+        if timed:
+            if not cuda:
+                return results, 0.0
+            end.record(cur)
+            end.synchronize()
+            return results, start.elapsed_time(end)
+        return results
+
+    def _count(self) -> int:
+        """the library's launch counter is per host thread"""
+        if self.streams[0] is None:
+            return 0
+        import ctypes
+        from cra5_b200 import _lib
+        c = ctypes.c_uint64()
+        _lib.check(_lib.lib.cra5_launch_count(ctypes.byref(c)))
+        return int(c.value)
+
+
 class FramePipeline:
     """Host-to-host streaming of frames through one GPU with the PCIe copies hidden behind compute.
 

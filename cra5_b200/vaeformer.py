@@ -157,6 +157,35 @@ class VAEformer:
         except Exception:
             pass
 
+    def replica(self):
+        """A second codec lane on the same GPU (additive extension; see cra5_b200.stream.CodecLanes): a new library
+        handle -- own activation workspace, own bitstream buffers -- that points at THIS model's device weights and CDF
+        tables (nothing is copied; the handle only keeps pointers, the tensors stay alive in both objects). Frames
+        are independent, so two lanes on two CUDA streams give the same bytes as one lane; the second lane's kernels
+        fill the SMs the first lane leaves idle (partial last waves, launch gaps, the host synchronisation in
+        latent_to_bin)."""
+        r = object.__new__(type(self))
+        r.cfg, r.device, r._spc, r.training = self.cfg, self.device, self._spc, self.training
+        r._sd, r._cdf, r.scale_table = self._sd, dict(self._cdf), self.scale_table
+        r._dev = {}
+        r._handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            cc = _c_config(self.cfg, *self._spc)
+            _lib.check(_lib.lib.cra5_model_create(ctypes.byref(cc), ctypes.byref(r._handle)))
+            for name, t in self._dev.items():
+                if isinstance(t, dict):   # "<module>.tables": the three int32 CDF tensors of an entropy model
+                    which = 0 if name.startswith("entropy_bottleneck") else 1
+                    r._dev[name] = t
+                    _lib.check(_lib.lib.cra5_model_set_cdf(r._handle, which, _lib.ptr(t["quantized_cdf"]),
+                                                           _lib.ptr(t["cdf_length"]), _lib.ptr(t["offset"]),
+                                                           t["quantized_cdf"].shape[0], t["quantized_cdf"].shape[1]))
+                else:
+                    r._dev[name] = t
+                    _lib.check(_lib.lib.cra5_model_set_tensor(r._handle, name.encode(), _lib.ptr(t), _DT[t.dtype],
+                                                              ctypes.c_int64(t.numel())))
+            _lib.check(_lib.lib.cra5_model_set_coder(r._handle, *self._spc))
+        return r
+
     # ------------------------------------------------------------------ parameters
     def _set(self, name: str, t: torch.Tensor):
         t = t.detach().to(self.device).contiguous()

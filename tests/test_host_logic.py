@@ -214,3 +214,49 @@ def test_bench_clock_sampler_and_reference_arm_ranks(monkeypatch, capsys):
     monkeypatch.setenv("WORLD_SIZE", "2")
     bench.run_reference(types.SimpleNamespace(channels=268, steps=1, warmup=1, gpus=2))
     assert capsys.readouterr().out == ""
+
+
+class _FakeCodec:
+    def __init__(self, tag="lane0"):
+        self.tag = tag
+        self.device = None
+
+    def replica(self):
+        return _FakeCodec("lane%d" % (int(self.tag[4:]) + 1))
+
+
+def test_codec_lanes_orchestration():
+    """CodecLanes host logic (no CUDA: streams=None): item i runs on lane i mod L, results come back in item order, the
+    lanes run concurrently on their own host threads, a failing item's exception reaches the caller."""
+    import threading
+    import time
+    from cra5_b200.stream import CodecLanes
+    lanes = CodecLanes(_FakeCodec(), lanes=2, streams=[None, None])
+    assert [n.tag for n in lanes.nets] == ["lane0", "lane0".replace("0", "1")]
+    seen = []
+    both = threading.Barrier(2, timeout=20)
+
+    def work(codec, i):
+        if i < 2:
+            both.wait()                     # items 0 and 1 must be in flight at the same time (two threads)
+        seen.append((codec.tag, i, threading.current_thread().name))
+        time.sleep(0.001)
+        return i * i
+
+    res, ms = lanes.run(work, 7, timed=True)
+    assert res == [i * i for i in range(7)] and ms == 0.0
+    assert all(tag == f"lane{i % 2}" for tag, i, _ in seen)
+    assert {name for tag, _, name in seen if tag == "lane1"} == {"cra5-lane-1"}
+    assert lanes.run(lambda c, i: c.tag, 3) == ["lane0", "lane1", "lane0"]
+    assert lanes.launches() == 0
+
+    def boom(codec, i):
+        if i == 3:
+            raise ValueError("bad frame 3")
+        return i
+
+    with pytest.raises(ValueError, match="bad frame 3"):
+        lanes.run(boom, 6)
+    assert CodecLanes(_FakeCodec(), lanes=1, streams=[None]).run(lambda c, i: i + 1, 3) == [1, 2, 3]
+    with pytest.raises(ValueError):
+        CodecLanes(_FakeCodec(), lanes=0, streams=[])

@@ -1,0 +1,134 @@
+#!/usr/bin/env python
+"""Validate and time the two overlap options on a B200 (both are off by default until this script has passed there):
+
+  * CRA5_PDL=1   the libcra5b200_pdl.so build variant: the per-frame kernel chain launched with programmatic
+                 dependent launch (each kernel's prologue overlaps its predecessor's tail);
+  * lanes = 2    cra5_b200.stream.CodecLanes: frames alternate between two codec lanes (own handle / stream / host
+                 thread, shared weights), so one frame's kernels fill the SMs the other leaves idle.
+
+    python tools/check_overlap.py            # parent: default, pdl, lanes=2, pdl+lanes=2 in four child processes
+    python tools/check_overlap.py --child [--lanes L]      # one measurement in this process, JSON on stdout
+
+Every kernel on the chain is deterministic (fixed tile order, no atomics), so each configuration must reproduce the
+default one BIT FOR BIT: same bitstreams, same reconstruction. A difference under CRA5_PDL=1 means a kernel touched
+memory before its griddepcontrol.wait (or a launch without the wait got the launch attribute); a difference with two
+lanes means the handles share mutable state. The round trips are repeated because such races are timing dependent.
+Then the 268-variable frame is timed in every configuration (CUDA events).
+Exit status 0 = all identical; the last stdout line is a JSON summary with the speed-ups.
+"""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _digest(out, rec):
+    h = hashlib.sha256()
+    h.update(out["strings"][0][0])
+    h.update(out["strings"][1][0])
+    h.update(rec.cpu().numpy().tobytes())
+    return h.hexdigest()
+
+
+def child(n_lanes):
+    import torch
+    from cra5_b200 import _lib, config as C
+    from cra5_b200.stream import CodecLanes
+    from cra5_b200.vaeformer import VAEformer
+    from oracle import weights
+    res = {"variant": _lib.VARIANT or "default", "lib": os.path.basename(_lib.LIB_PATH), "lanes": n_lanes, "digests": []}
+
+    def roundtrip(codec, x):
+        with torch.no_grad():
+            o = codec.compress(x)
+            rec = codec.decompress(o["strings"], o["z_shape"])["x_hat"]
+        return _digest(o, rec)
+
+    # ---- bit-exactness on the two parity geometries (every shape quirk incl. padded windows and the conv head)
+    for cfg, wseed, fseed in ((C.small_lowres(5), 11, 3), (C.tiny_fullres(69), 7, 1)):
+        net = VAEformer(268, cfg=cfg, init_seed=None)
+        net.load_state_dict(weights.seeded_state_dict(C.param_shapes(cfg), wseed))
+        net.update(force=True)
+        x = weights.seeded_frame(cfg, fseed).unsqueeze(0).cuda()
+        torch.cuda.synchronize()
+        if n_lanes > 1:
+            res["digests"] += CodecLanes(net, lanes=n_lanes).run(lambda codec, i: roundtrip(codec, x), 4 * n_lanes)[-4:]
+        else:
+            res["digests"] += [roundtrip(net, x) for _ in range(4)]
+        del net
+    # ---- timing on the headline frame
+    cfg = C.cra5_268()
+    net = VAEformer(268, cfg=cfg, init_seed=1234)
+    net.update(force=True)
+    g = torch.Generator(device="cuda").manual_seed(1000)
+    frames = [torch.randn(1, cfg.in_chans, 721, 1440, device="cuda", generator=g) for _ in range(2)]
+    torch.cuda.synchronize()
+    n = 12
+
+    def step(codec, i):
+        o = codec.compress(frames[i % 2])
+        codec.decompress(o["strings"], o["z_shape"])
+
+    if n_lanes > 1:
+        lanes = CodecLanes(net, lanes=n_lanes)
+        res["digests"] += lanes.run(lambda codec, i: roundtrip(codec, frames[i % 2]), 2 * n_lanes)[-2:]
+        lanes.run(step, 2 * n_lanes)
+        _, ms = lanes.run(step, n, timed=True)
+    else:
+        res["digests"] += [roundtrip(net, frames[i % 2]) for i in range(2)]
+        for i in range(3):
+            step(net, i)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(n):
+            step(net, i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+    res["ms_per_frame"] = ms / n
+    print(json.dumps(res))
+
+
+def run(env_extra, lanes):
+    env = dict(os.environ)
+    env.pop("CRA5_PDL", None)
+    env.update(env_extra)
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "--lanes", str(lanes)], env=env,
+                       capture_output=True, text=True, timeout=900)
+    if r.returncode != 0:
+        return {"error": (r.stdout[-1500:] + "\n" + r.stderr[-3000:])}
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def main():
+    base = run({}, 1)
+    if "error" in base:
+        raise SystemExit("default configuration failed:\n" + base["error"])
+    summary = {"default_ms": base["ms_per_frame"]}
+    ok = len(set(base["digests"][:4])) == 1 and len(set(base["digests"][4:8])) == 1
+    summary["default_repeatable"] = ok
+    for name, env, lanes in (("pdl", {"CRA5_PDL": "1"}, 1), ("lanes2", {}, 2), ("pdl_lanes2", {"CRA5_PDL": "1"}, 2)):
+        r = run(env, lanes)
+        if "error" in r:
+            summary[name] = {"error": r["error"][-600:]}
+            ok = False
+            continue
+        same = r["digests"] == base["digests"]
+        summary[name] = {"identical": same, "ms": r["ms_per_frame"], "speedup": base["ms_per_frame"] / r["ms_per_frame"],
+                         "lib": r["lib"]}
+        ok = ok and same
+    summary["all_identical"] = ok
+    print(json.dumps(summary))
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    if "--child" in sys.argv:
+        child(int(sys.argv[sys.argv.index("--lanes") + 1]) if "--lanes" in sys.argv else 1)
+    else:
+        sys.exit(main())
