@@ -385,14 +385,16 @@ def run_b200(args):
                        local_root=tempfile.mkdtemp(prefix="cra5b200_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None))
     api.mean.zero_()
     api.std.fill_(1.0)  # synthetic frames are already in normalised units
-    host_in = [torch.randn(cfg.in_chans, 721, 1440, generator=torch.Generator().manual_seed(7 + rank)).pin_memory()
-               for _ in range(2)] if cfg.in_chans == 268 else None
+    from cra5_b200.stream import FramePipeline, near_gpu
+    host_in, numa_bound = None, False
+    if cfg.in_chans == 268:
+        src = [torch.randn(cfg.in_chans, 721, 1440, generator=torch.Generator().manual_seed(7 + rank)) for _ in range(2)]
+        with near_gpu(dev) as numa_bound:   # pinned pages land on the NUMA node of the allocating thread
+            host_in = [t.pin_memory() for t in src]
+            host_outs = [torch.empty(cfg.in_chans, 721, 1440).pin_memory() for _ in range(2)]
+        del src
     e2e = None
     if host_in is not None:
-        host_out = torch.empty(cfg.in_chans, 721, 1440).pin_memory()
-
-        from cra5_b200.stream import FramePipeline
-        host_outs = [host_out, torch.empty(cfg.in_chans, 721, 1440).pin_memory()]
         pipe = FramePipeline(api)
 
         def e2e_run(n):
@@ -416,7 +418,7 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * n_e2e / float(t.item()), "unit": "frames/s", "h2d_bytes_per_step": frame_bytes + nbytes,
-               "d2h_bytes_per_step": frame_bytes + nbytes, "steps": n_e2e,
+               "d2h_bytes_per_step": frame_bytes + nbytes, "steps": n_e2e, "pinned_on_gpu_numa_node": bool(numa_bound),
                "path": "cra5_b200.stream.FramePipeline over cra5_api: pinned host frame -> H2D -> encode_to_latent "
                        "(normalisation fused) -> latent_to_bin -> bin strings -> bin_to_latent -> "
                        "latent_to_reconstruction -> D2H -> pinned host; copies on side streams overlap compute"}

@@ -50,6 +50,85 @@ def stream_frames(codec, frames: Iterable, rank: int, world: int, n_frames: int)
         yield i, out["strings"], rec["x_hat"]
 
 
+def parse_cpulist(text: str) -> List[int]:
+    """'0-3,8,10-11' (sysfs cpulist syntax) -> [0, 1, 2, 3, 8, 10, 11]"""
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        part = part.strip()
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-", 1)
+            cpus.extend(range(int(a), int(b) + 1))
+        else:
+            cpus.append(int(part))
+    return cpus
+
+
+def gpu_numa_cpus(pci_bus_id: str, sysfs: str = "/sys"):
+    """CPUs of the NUMA node a GPU hangs off ('0000:1b:00.0' -> [0..31]); None when the platform does not say (single
+    node, virtualised PCI topology, sysfs absent)"""
+    import os
+    try:
+        with open(os.path.join(sysfs, "bus", "pci", "devices", pci_bus_id.lower(), "numa_node")) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(os.path.join(sysfs, "devices", "system", "node", f"node{node}", "cpulist")) as f:
+            cpus = parse_cpulist(f.read())
+        return cpus or None
+    except (OSError, ValueError):
+        return None
+
+
+def cuda_pci_bus_id(device) -> str:
+    """sysfs-style PCI address of a CUDA device"""
+    import torch
+    pr = torch.cuda.get_device_properties(device)
+    return f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+
+
+class near_gpu:
+    """Context manager: run the enclosed host allocations on the NUMA node next to `device` (additive; matters for the
+    N-GPU streaming path, where every rank moves 2 x 1.1 GB per frame between pinned host memory and its GPU -- pinned
+    pages are placed on the node of the thread that allocates them, and a buffer on the far socket halves the PCIe rate
+    and loads the inter-socket link). Restores the previous CPU affinity on exit; a no-op when the topology is unknown.
+
+        with near_gpu(dev) as bound:        # bound: True if the affinity was narrowed
+            buf = torch.empty(shape).pin_memory()
+    """
+
+    def __init__(self, device=None, pci_bus_id: str = None, sysfs: str = "/sys"):
+        self.device, self.bus, self.sysfs = device, pci_bus_id, sysfs
+        self.prev = None
+
+    def __enter__(self):
+        import os
+        try:
+            bus = self.bus or cuda_pci_bus_id(self.device)
+            cpus = gpu_numa_cpus(bus, self.sysfs)
+            if not cpus:
+                return False
+            prev = os.sched_getaffinity(0)
+            want = set(cpus) & set(prev)
+            if not want or want == set(prev):
+                return False
+            os.sched_setaffinity(0, want)
+            self.prev = prev
+            return True
+        except Exception:
+            return False
+
+    def __exit__(self, *exc):
+        import os
+        if self.prev is not None:
+            try:
+                os.sched_setaffinity(0, self.prev)
+            finally:
+                self.prev = None
+        return False
+
+
 class CodecLanes:
     """Several codec lanes on ONE GPU (experimental until timed on a B200; bench.py --lanes, tools/check_overlap.py).
 

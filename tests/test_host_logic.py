@@ -260,3 +260,30 @@ def test_codec_lanes_orchestration():
     assert CodecLanes(_FakeCodec(), lanes=1, streams=[None]).run(lambda c, i: i + 1, 3) == [1, 2, 3]
     with pytest.raises(ValueError):
         CodecLanes(_FakeCodec(), lanes=0, streams=[])
+
+
+def test_numa_local_pinned_allocation_helper(tmp_path):
+    """near_gpu(): host buffers of the streaming path are allocated on the NUMA node next to the rank's GPU (sysfs
+    topology faked here); affinity is restored afterwards; unknown topologies are a no-op."""
+    from cra5_b200 import stream
+    assert stream.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11] and stream.parse_cpulist("") == []
+    bus = "0000:1b:00.0"
+    d = tmp_path / "bus" / "pci" / "devices" / bus
+    d.mkdir(parents=True)
+    prev = os.sched_getaffinity(0)
+    some = sorted(prev)[: max(1, len(prev) // 2)]
+    (d / "numa_node").write_text("1\n")
+    nd = tmp_path / "devices" / "system" / "node" / "node1"
+    nd.mkdir(parents=True)
+    (nd / "cpulist").write_text(",".join(str(c) for c in some) + "\n")
+    assert stream.gpu_numa_cpus("0000:1B:00.0", sysfs=str(tmp_path)) == some
+    with stream.near_gpu(pci_bus_id=bus, sysfs=str(tmp_path)) as bound:
+        inside = os.sched_getaffinity(0)
+    assert os.sched_getaffinity(0) == prev
+    if len(prev) > 1:
+        assert bound and inside == set(some)
+    (d / "numa_node").write_text("-1\n")                       # platform does not say: leave the affinity alone
+    with stream.near_gpu(pci_bus_id=bus, sysfs=str(tmp_path)) as bound:
+        assert not bound and os.sched_getaffinity(0) == prev
+    with stream.near_gpu(pci_bus_id="0000:ff:00.0", sysfs=str(tmp_path)) as bound:
+        assert not bound
