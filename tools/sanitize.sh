@@ -1,0 +1,20 @@
+#!/bin/bash
+# compute-sanitizer passes over the small-geometry GPU tests (run on a B200: `gpurun --timeout 1500 -- bash tools/sanitize.sh`).
+# memcheck: out-of-bounds / misaligned global + shared accesses; racecheck: shared-memory hazards; initcheck: reads of
+# uninitialised global memory. The full-size tests are skipped (the tools slow kernels down 10-100x).
+# Summaries land in gpurun_out/sanitize_<tool>.log; exit status is non-zero if any tool reported an error.
+set -u
+mkdir -p gpurun_out
+SEL='tests/test_gpu_kernels.py tests/test_gpu_entropy.py'
+MODEL='tests/test_gpu_model.py -k small'
+rc=0
+for tool in memcheck racecheck initcheck; do
+  log=gpurun_out/sanitize_${tool}.log
+  timeout 1200 compute-sanitizer --tool ${tool} --error-exitcode 7 --print-limit 20 \
+      python -m pytest ${SEL} ${MODEL} -m gpu -x -q > ${log} 2>&1
+  st=$?
+  echo "${tool}: exit ${st}; $(grep -c 'ERROR SUMMARY' ${log}) summaries; $(grep 'ERROR SUMMARY' ${log} | tail -1)"
+  tail -3 ${log}
+  [ ${st} -ne 0 ] && rc=1
+done
+exit ${rc}
