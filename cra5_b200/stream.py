@@ -151,6 +151,9 @@ class CodecLanes:
         self.device = getattr(net, "device", None)
         if streams is None:
             import torch
+            # resolve "cuda" to an index on the caller's thread: a new host thread starts on device 0
+            idx = self.device.index if getattr(self.device, "index", None) is not None else torch.cuda.current_device()
+            self.device = torch.device("cuda", idx)
             streams = [torch.cuda.Stream(self.device) for _ in range(lanes)]
         if len(streams) != lanes:
             raise ValueError("one stream per lane")
