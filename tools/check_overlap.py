@@ -27,14 +27,15 @@ sys.path.insert(0, ROOT)
 
 
 def _digest(out, rec):
+    """'<sha of the two bitstreams>:<sha of the reconstruction>:<bytes>'"""
     h = hashlib.sha256()
     h.update(out["strings"][0][0])
     h.update(out["strings"][1][0])
-    h.update(rec.cpu().numpy().tobytes())
-    return h.hexdigest()
+    g = hashlib.sha256(rec.cpu().numpy().tobytes())
+    return f"{h.hexdigest()}:{g.hexdigest()}:{len(out['strings'][0][0]) + len(out['strings'][1][0])}"
 
 
-def child(n_lanes):
+def child(n_lanes, spc_y=16):
     import torch
     from cra5_b200 import _lib, config as C
     from cra5_b200.stream import CodecLanes
@@ -53,6 +54,7 @@ def child(n_lanes):
         net = VAEformer(268, cfg=cfg, init_seed=None)
         net.load_state_dict(weights.seeded_state_dict(C.param_shapes(cfg), wseed))
         net.update(force=True)
+        net.set_coder(spc_y, 4)
         x = weights.seeded_frame(cfg, fseed).unsqueeze(0).cuda()
         torch.cuda.synchronize()
         if n_lanes > 1:
@@ -63,7 +65,12 @@ def child(n_lanes):
     # ---- timing on the headline frame
     cfg = C.cra5_268()
     net = VAEformer(268, cfg=cfg, init_seed=1234)
+    sd = {k: v for k, v in net.state_dict().items() if k in C.param_shapes(cfg)}
+    sd["quant_conv.weight"] = sd["quant_conv.weight"] * 6.0      # bench.py's entropy regime
+    sd["h_s.final.weight"] = sd["h_s.final.weight"] * 12.0
+    net.load_state_dict(sd)
     net.update(force=True)
+    net.set_coder(spc_y, 4)
     g = torch.Generator(device="cuda").manual_seed(1000)
     frames = [torch.randn(1, cfg.in_chans, 721, 1440, device="cuda", generator=g) for _ in range(2)]
     torch.cuda.synchronize()
@@ -94,11 +101,11 @@ def child(n_lanes):
     print(json.dumps(res))
 
 
-def run(env_extra, lanes):
+def run(env_extra, lanes, spc_y=16):
     env = dict(os.environ)
     env.pop("CRA5_PDL", None)
     env.update(env_extra)
-    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "--lanes", str(lanes)], env=env,
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "--lanes", str(lanes), "--spc", str(spc_y)], env=env,
                        capture_output=True, text=True, timeout=900)
     if r.returncode != 0:
         return {"error": (r.stdout[-1500:] + "\n" + r.stderr[-3000:])}
@@ -122,6 +129,19 @@ def main():
         summary[name] = {"identical": same, "ms": r["ms_per_frame"], "speedup": base["ms_per_frame"] / r["ms_per_frame"],
                          "lib": r["lib"]}
         ok = ok and same
+    # not an overlap option but timed here because it is one call away: 32 instead of 16 rANS sub-streams per latent
+    # channel (serial chains half as long, about 10 more bytes per sub-stream). The containers differ by construction;
+    # the coder is lossless, so the RECONSTRUCTIONS must still be identical.
+    r = run({}, 1, spc_y=32)
+    if "error" in r:
+        summary["spc32"] = {"error": r["error"][-600:]}
+    else:
+        rec = lambda d: [x.split(":")[1] for x in d["digests"]]
+        size = lambda d: int(d["digests"][-1].split(":")[2])
+        summary["spc32"] = {"same_reconstruction": rec(r) == rec(base), "ms": r["ms_per_frame"],
+                            "speedup": base["ms_per_frame"] / r["ms_per_frame"],
+                            "bytes_per_frame": size(r), "bytes_per_frame_spc16": size(base)}
+        ok = ok and summary["spc32"]["same_reconstruction"]
     summary["all_identical"] = ok
     print(json.dumps(summary))
     return 0 if ok else 1
@@ -129,6 +149,7 @@ def main():
 
 if __name__ == "__main__":
     if "--child" in sys.argv:
-        child(int(sys.argv[sys.argv.index("--lanes") + 1]) if "--lanes" in sys.argv else 1)
+        child(int(sys.argv[sys.argv.index("--lanes") + 1]) if "--lanes" in sys.argv else 1,
+              int(sys.argv[sys.argv.index("--spc") + 1]) if "--spc" in sys.argv else 16)
     else:
         sys.exit(main())
