@@ -9,6 +9,8 @@ Build variants (same sources, extra -D flags, own object directory, own library 
   "pdl"  libcra5b200_pdl.so   -DCRA5_PDL=1: the per-frame kernel chain launched with programmatic dependent launch
                               (ptx.cuh pdl_grid_sync / host_util.h launch_chained); loaded only when CRA5_PDL=1 is set
                               in the environment (cra5_b200/_lib.py). Experimental until validated on a B200.
+  "tune" libcra5b200_tune.so  "pdl" + -DCRA5_ARRIVE_CTA_SCOPE=1 (CTA-pair GEMM: CTA-scope release on the epilogue's
+                              accumulator-free arrive instead of a cluster-scope membar); loaded under CRA5_VARIANT=tune.
 """
 import hashlib
 import os
@@ -20,7 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libcra5b200.so")
-VARIANTS = {"": [], "pdl": ["-DCRA5_PDL=1"]}
+VARIANTS = {"": [], "pdl": ["-DCRA5_PDL=1"], "tune": ["-DCRA5_PDL=1", "-DCRA5_ARRIVE_CTA_SCOPE=1"]}
 
 
 def lib_path(variant=""):

@@ -210,8 +210,21 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+// Arrive on a barrier that may live in the peer CTA of the pair. The default build uses release semantics at cluster
+// scope, which ptxas implements with ERRBAR + a cluster-scope membar in front of the arrive: the arriving epilogue warp
+// first drains its own global stores. The only consumer of these arrivals is the MMA issuer, which needs the TMEM READS
+// to have retired (tcgen05.wait::ld + tcgen05.fence::before_thread_sync order those) and never looks at the stores, so
+// -DCRA5_ARRIVE_CTA_SCOPE=1 (the experimental "tune" build variant) uses the unqualified form -- release at CTA scope, the
+// form CUTLASS's ClusterBarrier::arrive(cta_id) emits -- which needs no membar.
+#ifndef CRA5_ARRIVE_CTA_SCOPE
+#define CRA5_ARRIVE_CTA_SCOPE 0
+#endif
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+#if CRA5_ARRIVE_CTA_SCOPE
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
 }
 // TMA load whose completion bytes are credited to an mbarrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,

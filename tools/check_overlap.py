@@ -4,7 +4,8 @@
   * CRA5_PDL=1   the libcra5b200_pdl.so build variant: the per-frame kernel chain launched with programmatic
                  dependent launch (each kernel's prologue overlaps its predecessor's tail);
   * lanes = 2    cra5_b200.stream.CodecLanes: frames alternate between two codec lanes (own handle / stream / host
-                 thread, shared weights), so one frame's kernels fill the SMs the other leaves idle.
+                 thread, shared weights), so one frame's kernels fill the SMs the other leaves idle;
+  * CRA5_VARIANT=tune   libcra5b200_tune.so: PDL + the CTA-pair GEMM's accumulator-free arrive at CTA scope (no membar).
 
     python tools/check_overlap.py            # parent: default, pdl, lanes=2, pdl+lanes=2 in four child processes
     python tools/check_overlap.py --child [--lanes L]      # one measurement in this process, JSON on stdout
@@ -104,6 +105,7 @@ def child(n_lanes, spc_y=16):
 def run(env_extra, lanes, spc_y=16):
     env = dict(os.environ)
     env.pop("CRA5_PDL", None)
+    env.pop("CRA5_VARIANT", None)
     env.update(env_extra)
     r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "--lanes", str(lanes), "--spc", str(spc_y)], env=env,
                        capture_output=True, text=True, timeout=900)
@@ -119,7 +121,8 @@ def main():
     summary = {"default_ms": base["ms_per_frame"]}
     ok = len(set(base["digests"][:4])) == 1 and len(set(base["digests"][4:8])) == 1
     summary["default_repeatable"] = ok
-    for name, env, lanes in (("pdl", {"CRA5_PDL": "1"}, 1), ("lanes2", {}, 2), ("pdl_lanes2", {"CRA5_PDL": "1"}, 2)):
+    for name, env, lanes in (("pdl", {"CRA5_PDL": "1"}, 1), ("lanes2", {}, 2), ("pdl_lanes2", {"CRA5_PDL": "1"}, 2),
+                             ("tune", {"CRA5_VARIANT": "tune"}, 1), ("tune_lanes2", {"CRA5_VARIANT": "tune"}, 2)):
         r = run(env, lanes)
         if "error" in r:
             summary[name] = {"error": r["error"][-600:]}
