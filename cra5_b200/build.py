@@ -10,7 +10,9 @@ Build variants (same sources, extra -D flags, own object directory, own library 
                               (ptx.cuh pdl_grid_sync / host_util.h launch_chained); loaded only when CRA5_PDL=1 is set
                               in the environment (cra5_b200/_lib.py). Experimental until validated on a B200.
   "tune" libcra5b200_tune.so  "pdl" + -DCRA5_ARRIVE_CTA_SCOPE=1 (CTA-pair GEMM: CTA-scope release on the epilogue's
-                              accumulator-free arrive instead of a cluster-scope membar); loaded under CRA5_VARIANT=tune.
+                              accumulator-free arrive instead of a cluster-scope membar) + -DCRA5_TUNE=1 (epilogue
+                              index arithmetic: window map once per tile, multiply-shift divisions, incremental
+                              un-patchify rows); loaded under CRA5_VARIANT=tune.
 """
 import hashlib
 import os
@@ -22,7 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libcra5b200.so")
-VARIANTS = {"": [], "pdl": ["-DCRA5_PDL=1"], "tune": ["-DCRA5_PDL=1", "-DCRA5_ARRIVE_CTA_SCOPE=1"]}
+VARIANTS = {"": [], "pdl": ["-DCRA5_PDL=1"], "tune": ["-DCRA5_PDL=1", "-DCRA5_ARRIVE_CTA_SCOPE=1", "-DCRA5_TUNE=1"]}
 
 
 def lib_path(variant=""):

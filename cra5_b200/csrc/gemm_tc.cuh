@@ -43,12 +43,66 @@ struct GemmShape {
   int cc_shift;  // row shift for the second half
 };
 
+// CRA5_TUNE=1 (the experimental "tune" build variant, cra5_b200/build.py) removes index arithmetic from the epilogues
+// without changing a single result: the window map of a residual tile row is computed once per tile instead of once
+// per 32-column chunk, its four integer divisions (about 20 instructions each: I2F, MUFU.RCP, F2I, fix-up) become
+// multiply-high + shift by host-precomputed constants, the QKV head split uses compares and a shift, and the
+// un-patchify / pixel-shuffle epilogues advance (i, j) incrementally instead of dividing per row.
+#ifndef CRA5_TUNE
+#define CRA5_TUNE 0
+#endif
+
+// n / d for 0 <= n < 2^31 and a positive divisor fixed at launch time (the CUTLASS FastDivmod construction:
+// m = ceil(2^(31 + ceil(log2 d)) / d); verified exhaustively for the divisors that occur here)
+struct FastDiv {
+  uint32_t mul, shr;
+  int d;
+  static FastDiv make(int d) {
+    FastDiv f;
+    f.d = d;
+    f.mul = 0;
+    f.shr = 0;
+    if (d > 1) {
+      int l = 0;
+      while ((1u << l) < (uint32_t)d) ++l;   // ceil(log2 d)
+      const int p = 31 + l;
+      f.mul = (uint32_t)(((1ull << p) + (uint64_t)d - 1) / (uint64_t)d);
+      f.shr = (uint32_t)(p - 32);
+    }
+    return f;
+  }
+  __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shr); }
+};
+
 // maps a row of the "attention order" (window-partitioned, zero-padded) token list back to the raster token
 struct WinMap {
   int enabled;
   int H, W;        // token grid
   int wh, ww;      // window
   int nWr, nWc;    // windows per column / row after padding
+#if CRA5_TUNE
+  FastDiv f_wsz, f_ww, f_pf, f_nwc;
+  void finish() {   // host: call after the integer fields are set
+    f_wsz = FastDiv::make(wh * ww);
+    f_ww = FastDiv::make(ww);
+    f_pf = FastDiv::make(nWr * nWc);
+    f_nwc = FastDiv::make(nWc);
+  }
+  __device__ __forceinline__ int to_token(int a) const {  // -1 for a pad row
+    if (!enabled) return a;
+    const int wsz = wh * ww;
+    int wi = f_wsz.div(a), within = a - wi * wsz;
+    int r = f_ww.div(within), c = within - r * ww;
+    int per_frame = nWr * nWc;
+    int b = f_pf.div(wi);
+    wi -= b * per_frame;
+    int wr = f_nwc.div(wi), wc = wi - wr * nWc;
+    int h = wr * wh + r, w = wc * ww + c;
+    if (h >= H || w >= W) return -1;
+    return (b * H + h) * W + w;
+  }
+#else
+  void finish() {}
   __device__ __forceinline__ int to_token(int a) const {  // -1 for a pad row
     if (!enabled) return a;
     const int wsz = wh * ww;
@@ -62,7 +116,26 @@ struct WinMap {
     if (h >= H || w >= W) return -1;
     return (b * H + h) * W + w;
   }
+#endif
 };
+
+// QKV column -> (which of q|k|v, head, dim): divisions by the model width and the head width (EPI_QKV epilogues)
+struct QkvSplit { int which, head, d; };
+__device__ __forceinline__ QkvSplit qkv_split(int col, int D, int hd) {
+  QkvSplit q;
+#if CRA5_TUNE
+  q.which = (col >= 2 * D) ? 2 : (col >= D ? 1 : 0);
+  const int within = col - q.which * D;
+  q.head = ((hd & (hd - 1)) == 0) ? (within >> (31 - __clz(hd))) : within / hd;   // warp-uniform choice
+  q.d = within - q.head * hd;
+#else
+  q.which = col / D;
+  const int within = col - q.which * D;
+  q.head = within / hd;
+  q.d = within - q.head * hd;
+#endif
+  return q;
+}
 
 enum EpiKind : int {
   EPI_F32 = 0,        // out_f32 = acc + bias (+ add)
@@ -390,6 +463,15 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& p, const float* s
     const int rk = col / p.ct_CS, cs = col - rk * p.ct_CS;
     const int c = cs / p.ct_pw, s_ = cs - c * p.ct_pw;
     float* plane = p.out_f32 + (size_t)c * p.ct_Himg * p.ct_Wimg + s_;
+#if CRA5_TUNE
+    int i_ = row_base / p.ct_Wp, j_ = row_base - i_ * p.ct_Wp;   // one division per chunk; (i, j) advance with the row
+#pragma unroll 8
+    for (int rr = 0; rr < rows_valid; ++rr) {
+      const int h = p.ct_sh * i_ + p.ct_r0 + rk;
+      if (h < p.ct_Himg) plane[(size_t)h * p.ct_Wimg + p.ct_pw * j_] = stg[rr * STG_LD + lane];
+      if (++j_ == p.ct_Wp) { j_ = 0; ++i_; }
+    }
+#else
 #pragma unroll 8
     for (int rr = 0; rr < rows_valid; ++rr) {
       const int row = row_base + rr;
@@ -397,17 +479,24 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& p, const float* s
       const int h = p.ct_sh * i_ + p.ct_r0 + rk;
       if (h < p.ct_Himg) plane[(size_t)h * p.ct_Wimg + p.ct_pw * j_] = stg[rr * STG_LD + lane];
     }
+#endif
   }
 }
 
 // EPI_RESID, phase 1: issue the 32 residual loads of this chunk (clamped, unconditional addresses) -- called BEFORE the
 // accumulator is read out of TMEM and staged, so the DRAM/L2 latency overlaps that work. resid may alias out.
 __device__ __forceinline__ void epilogue_resid_load(const EpiParams& p, int row_base, int col0, int lane, int M, int N,
-                                                    float (&rv)[32], int& my_t) {
+                                                    float (&rv)[32], int& my_t, int tile_tok) {
   const int rows_valid = min(32, M - row_base);
   const int col = col0 + lane;
   const int colc = (col < N) ? col : 0;
+#if CRA5_TUNE
+  (void)rows_valid;
+  my_t = tile_tok;   // lane < rows_valid <=> row_base + lane < M, which is how tile_tok was guarded
+#else
+  (void)tile_tok;
   my_t = (lane < rows_valid) ? p.wm.to_token(row_base + lane) : -1;
+#endif
 #pragma unroll
   for (int rr = 0; rr < 32; ++rr) {
     const int t = __shfl_sync(0xffffffffu, my_t, rr);
@@ -517,7 +606,7 @@ struct F32Fast {
 };
 template <int KIND>
 __device__ __forceinline__ void epilogue_f32_prefetch(const EpiParams& p, int row_base, int col0, int lane, int M, int N,
-                                                      F32Fast& f) {
+                                                      F32Fast& f, int tile_tok) {
   const float* src = (KIND == EPI_RESID) ? p.resid : p.add;
   const int ld_src = (KIND == EPI_RESID) ? p.ldo : p.lda;
   f.on = (col0 + 32 <= N) && ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_f32) & 15) == 0) &&
@@ -527,7 +616,12 @@ __device__ __forceinline__ void epilogue_f32_prefetch(const EpiParams& p, int ro
           ((((p.ld_bf16 | p.bf16_col0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_bf16) & 7) == 0)));
   if (!f.on) return;
   const int row = row_base + lane;
+#if CRA5_TUNE
+  f.my_t = (KIND == EPI_RESID) ? tile_tok : ((row < M) ? row : -1);   // tile_tok is -1 for rows >= M and for pad rows
+#else
+  (void)tile_tok;
   f.my_t = (row < M) ? ((KIND == EPI_RESID) ? p.wm.to_token(row) : row) : -1;
+#endif
   const int piece = lane & 7;
   f.bias = (p.bias != nullptr) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + piece * 4))
                                : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -711,11 +805,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = (tile % n_tiles) * BN;
       const uint32_t as = tl & 1;
       const uint32_t aph = (tl >> 1) & 1;
+      int tile_tok = -1;   // CRA5_TUNE: the window map of this lane's accumulator row, computed once per tile
       if constexpr (KIND == EPI_RESID) {
         // pull this warp's share of the residual tile (32 rows x BN/2 fp32) towards L2 while the main loop of the tile
         // is still running: the epilogue is otherwise bound by four serial DRAM round trips per tile
         const int prow = m0 + quarter * 32 + lane;
         const int pt = (prow < shp.M) ? epi.wm.to_token(prow) : -1;
+        tile_tok = pt;
         if (pt >= 0) {
           const float* pr = epi.resid + (size_t)pt * epi.ldo + n0 + half * (BN / 2);
 #pragma unroll
@@ -737,9 +833,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int my_t = -1;
         F32Fast ff;
         ff.on = false;
-        if constexpr (KIND == EPI_RESID || KIND == EPI_F32) epilogue_f32_prefetch<KIND>(epi, row_base, col0, lane, shp.M, shp.N, ff);
+        if constexpr (KIND == EPI_RESID || KIND == EPI_F32)
+          epilogue_f32_prefetch<KIND>(epi, row_base, col0, lane, shp.M, shp.N, ff, tile_tok);
         if constexpr (KIND == EPI_RESID) {
-          if (!ff.on) epilogue_resid_load(epi, row_base, col0, lane, shp.M, shp.N, rv, my_t);
+          if (!ff.on) epilogue_resid_load(epi, row_base, col0, lane, shp.M, shp.N, rv, my_t, tile_tok);
         }
         uint32_t acc[32];
         tmem_ld_32x32(taddr + c, acc);
@@ -767,9 +864,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                  (((reinterpret_cast<uintptr_t>(epi.q) | reinterpret_cast<uintptr_t>(epi.k)) & 15) == 0) &&
                  (epi.bias == nullptr || (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0);
           if (fast) {
-            const int which = col0 / epi.D;
-            const int within = col0 - which * epi.D;
-            const int head = within / epi.hd, d0 = within - head * epi.hd;
+            const QkvSplit qs = qkv_split(col0, epi.D, epi.hd);
+            const int which = qs.which, head = qs.head, d0 = qs.d;
             __nv_bfloat16* base = (which == 0 ? epi.q : epi.k) + ((size_t)head * epi.rows_total + row_base) * epi.hd + d0;
             epilogue_bf16_fast<KIND>(acc, epi.bias, col0, which == 0 ? epi.qscale : 1.0f, reinterpret_cast<uint8_t*>(stg),
                                      base, (size_t)epi.hd, min(32, shp.M - row_base), lane);
@@ -779,8 +875,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (!fast && direct && (((epi.D | epi.hd) & 31) == 0) && ((epi.rows_total & 7) == 0) && ((shp.M & 7) == 0) &&
               ((reinterpret_cast<uintptr_t>(epi.vt) & 15) == 0) &&
               (epi.bias == nullptr || (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0)) {
+#if CRA5_TUNE
+            const QkvSplit qs = qkv_split(col0, epi.D, epi.hd);
+            const int head = qs.head, d0 = qs.d;
+#else
             const int within = col0 - 2 * epi.D;
             const int head = within / epi.hd, d0 = within - head * epi.hd;
+#endif
             epilogue_vt_fast(acc, epi.bias, col0, reinterpret_cast<uint8_t*>(stg),
                              epi.vt + ((size_t)head * epi.hd + d0) * epi.rows_total + row_base, (size_t)epi.rows_total,
                              min(32, shp.M - row_base), lane);
@@ -967,9 +1068,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int n0 = (tile % n_tiles) * BN;
       const uint32_t as = tl & 1;
       const uint32_t aph = (tl >> 1) & 1;
+      int tile_tok = -1;
       if constexpr (KIND == EPI_RESID) {
         const int prow = m0 + quarter * 32 + lane;
         const int pt = (prow < shp.M) ? epi.wm.to_token(prow) : -1;
+        tile_tok = pt;
         if (pt >= 0) {
           const float* pr = epi.resid + (size_t)pt * epi.ldo + n0 + half * (BN / 2);
 #pragma unroll
@@ -991,9 +1094,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int my_t = -1;
         F32Fast ff;
         ff.on = false;
-        if constexpr (KIND == EPI_RESID || KIND == EPI_F32) epilogue_f32_prefetch<KIND>(epi, row_base, col0, lane, shp.M, shp.N, ff);
+        if constexpr (KIND == EPI_RESID || KIND == EPI_F32)
+          epilogue_f32_prefetch<KIND>(epi, row_base, col0, lane, shp.M, shp.N, ff, tile_tok);
         if constexpr (KIND == EPI_RESID) {
-          if (!ff.on) epilogue_resid_load(epi, row_base, col0, lane, shp.M, shp.N, rv, my_t);
+          if (!ff.on) epilogue_resid_load(epi, row_base, col0, lane, shp.M, shp.N, rv, my_t, tile_tok);
         }
         uint32_t acc[32];
         tmem_ld_32x32(taddr + c, acc);
@@ -1020,9 +1124,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                  (((reinterpret_cast<uintptr_t>(epi.q) | reinterpret_cast<uintptr_t>(epi.k)) & 15) == 0) &&
                  (epi.bias == nullptr || (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0);
           if (fast) {
-            const int which = col0 / epi.D;
-            const int within = col0 - which * epi.D;
-            const int head = within / epi.hd, d0 = within - head * epi.hd;
+            const QkvSplit qs = qkv_split(col0, epi.D, epi.hd);
+            const int which = qs.which, head = qs.head, d0 = qs.d;
             __nv_bfloat16* base = (which == 0 ? epi.q : epi.k) + ((size_t)head * epi.rows_total + row_base) * epi.hd + d0;
             epilogue_bf16_fast<KIND>(acc, epi.bias, col0, which == 0 ? epi.qscale : 1.0f, reinterpret_cast<uint8_t*>(stg),
                                      base, (size_t)epi.hd, min(32, shp.M - row_base), lane);
@@ -1032,8 +1135,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (!fast && direct && (((epi.D | epi.hd) & 31) == 0) && ((epi.rows_total & 7) == 0) && ((shp.M & 7) == 0) &&
               ((reinterpret_cast<uintptr_t>(epi.vt) & 15) == 0) &&
               (epi.bias == nullptr || (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0)) {
+#if CRA5_TUNE
+            const QkvSplit qs = qkv_split(col0, epi.D, epi.hd);
+            const int head = qs.head, d0 = qs.d;
+#else
             const int within = col0 - 2 * epi.D;
             const int head = within / epi.hd, d0 = within - head * epi.hd;
+#endif
             epilogue_vt_fast(acc, epi.bias, col0, reinterpret_cast<uint8_t*>(stg),
                              epi.vt + ((size_t)head * epi.hd + d0) * epi.rows_total + row_base, (size_t)epi.rows_total,
                              min(32, shp.M - row_base), lane);

@@ -198,6 +198,7 @@ WinMap Model::make_winmap(int wh, int ww) const {
   m.H = Hg; m.W = Wg; m.wh = wh; m.ww = ww;
   m.nWr = ceil_div(Hg, wh);
   m.nWc = ceil_div(Wg, ww);
+  m.finish();   // CRA5_TUNE: multiply-shift constants for the four divisions of to_token()
   return m;
 }
 
