@@ -106,6 +106,7 @@ def run(env_extra, lanes, spc_y=16):
     env = dict(os.environ)
     env.pop("CRA5_PDL", None)
     env.pop("CRA5_VARIANT", None)
+    env.pop("CRA5_GEMM_PAIR", None)
     env.update(env_extra)
     r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "--lanes", str(lanes), "--spc", str(spc_y)], env=env,
                        capture_output=True, text=True, timeout=900)
@@ -145,6 +146,15 @@ def main():
                             "speedup": base["ms_per_frame"] / r["ms_per_frame"],
                             "bytes_per_frame": size(r), "bytes_per_frame_spc16": size(base)}
         ok = ok and summary["spc32"]["same_reconstruction"]
+    # tile-shape heuristics were tuned single-lane, where a partial last wave is pure loss (proj runs 128 x 128 tiles for
+    # that reason although they are operand-bandwidth bound); with a second lane filling the tails the CTA-pair kernel
+    # may win everywhere. Informative only (identity reported, not required).
+    for name, env in (("lanes2_pair_everywhere", {"CRA5_GEMM_PAIR": "1"}),
+                      ("tune_lanes2_pair_everywhere", {"CRA5_GEMM_PAIR": "1", "CRA5_VARIANT": "tune"})):
+        r = run(env, 2)
+        summary[name] = ({"error": r["error"][-600:]} if "error" in r else
+                         {"identical": r["digests"] == base["digests"], "ms": r["ms_per_frame"],
+                          "speedup": base["ms_per_frame"] / r["ms_per_frame"]})
     summary["all_identical"] = ok
     print(json.dumps(summary))
     return 0 if ok else 1
