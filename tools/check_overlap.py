@@ -25,6 +25,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+CHILD_TIMEOUT_S = 420   # first import of torch on a fresh box ~1 min, three model builds, ~40 frames
 
 
 def _digest(out, rec):
@@ -108,8 +109,13 @@ def run(env_extra, lanes, spc_y=16):
     env.pop("CRA5_VARIANT", None)
     env.pop("CRA5_GEMM_PAIR", None)
     env.update(env_extra)
-    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "--lanes", str(lanes), "--spc", str(spc_y)], env=env,
-                       capture_output=True, text=True, timeout=900)
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "--lanes", str(lanes), "--spc", str(spc_y)],
+                           env=env, capture_output=True, text=True, timeout=CHILD_TIMEOUT_S)
+    except subprocess.TimeoutExpired:
+        # a hang (e.g. a dependent launch that never gets its trigger) must not eat the GPU budget: the child is killed,
+        # the configuration is reported as failed and the remaining ones still run
+        return {"error": f"timed out after {CHILD_TIMEOUT_S} s (killed)"}
     if r.returncode != 0:
         return {"error": (r.stdout[-1500:] + "\n" + r.stderr[-3000:])}
     return json.loads(r.stdout.strip().splitlines()[-1])
