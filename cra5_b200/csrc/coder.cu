@@ -245,6 +245,20 @@ void RansCoder::decode(cudaStream_t st, const uint8_t* bytes, size_t len, const 
     }
     return;
   }
+  if (decode_cr5b(st, bytes, len, idx, tab, n_channels, L, sym_out, mu, median, val_out, 0, true)) decode_finish(st);
+}
+
+// CR5B container -> device: validates the header, stages lengths + payload in the pinned buffer at `stage_off` (a
+// multiple of 16) and enqueues the upload, the length scan and the decode kernel. Returns false when there is nothing
+// to decode (no GPU work enqueued). With sync_before the stream is drained first, because the staging buffer may still
+// be in flight from a previous call; a caller that stages two containers at disjoint offsets inside one call passes
+// false for the second (CRA5_TUNE: Model::bin_to_latent). Errors found by the kernels are collected by decode_finish().
+bool RansCoder::decode_cr5b(cudaStream_t st, const uint8_t* bytes, size_t len, const uint8_t* idx, const CdfTable& tab,
+                            int n_channels, int L, int32_t* sym_out, const float* mu, const float* median,
+                            float* val_out, size_t stage_off, bool sync_before) {
+  CRA5_CHECK(tab.ready(), ERR_STATE, "Uninitialized CDFs. Run update() first");
+  CRA5_CHECK(bytes != nullptr && len >= 8 && memcmp(bytes, "CR5B", 4) == 0, ERR_BITSTREAM, "bitstream: not a CR5B container");
+  CRA5_CHECK((stage_off & 15) == 0, ERR_INTERNAL, "decode: staging offset");
   CRA5_CHECK(len >= CR5B_HEADER, ERR_BITSTREAM, "bitstream: truncated header");
   CRA5_CHECK(bytes[4] == 1, ERR_BITSTREAM, "bitstream: unsupported version");
   const uint32_t nc = get_u32(bytes + 8), l = get_u32(bytes + 12), spc = get_u32(bytes + 16),
@@ -262,13 +276,13 @@ void RansCoder::decode(cudaStream_t st, const uint8_t* bytes, size_t len, const 
     total += ls;
   }
   CRA5_CHECK(head + total == len, ERR_BITSTREAM, "bitstream: payload size mismatch");
-  if (ns == 0 || l == 0) return;
-  CRA5_CHECK(total <= payload_cap_ && len <= host_stage_cap_, ERR_BITSTREAM, "bitstream: too large");
-  CRA5_CUDA(cudaStreamSynchronize(st));  // the staging buffer may still be in flight from a previous call
-  memcpy(host_stage_, bytes + CR5B_HEADER, len - CR5B_HEADER);
+  if (ns == 0 || l == 0) return false;
+  CRA5_CHECK(total <= payload_cap_ && stage_off + len <= host_stage_cap_, ERR_BITSTREAM, "bitstream: too large");
+  if (sync_before) CRA5_CUDA(cudaStreamSynchronize(st));  // the staging buffer may still be in flight from a previous call
+  memcpy(host_stage_ + stage_off, bytes + CR5B_HEADER, len - CR5B_HEADER);
   count_launch();
   container_from_host_kernel<<<XFER_BLOCKS, XFER_THREADS, 0, st>>>(
-      reinterpret_cast<const uint32_t*>(host_stage_dev_), (int)ns, (uint32_t)(ns + total / 4), lengths_,
+      reinterpret_cast<const uint32_t*>(host_stage_dev_ + stage_off), (int)ns, (uint32_t)(ns + total / 4), lengths_,
       reinterpret_cast<uint32_t*>(payload_));
   CRA5_CUDA(cudaGetLastError());
   scan_lengths(st, lengths_, (int)ns, offsets_);
@@ -293,6 +307,11 @@ void RansCoder::decode(cudaStream_t st, const uint8_t* bytes, size_t len, const 
     rans_decode(st, payload_, offsets_, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, lut, lut_rows,
                 n_channels, L, (int)spc, L > 0 ? L : 1, sym_out, mu, median, val_out, err_);
   }
+  return true;
+}
+
+// one synchronisation for everything decode_cr5b() enqueued: fetches the kernels' error word
+void RansCoder::decode_finish(cudaStream_t st) {
   word_to_host_kernel<<<1, 1, 0, st>>>(err_, host_meta_dev_);
   CRA5_CUDA(cudaGetLastError());
   CRA5_CUDA(cudaStreamSynchronize(st));
@@ -301,5 +320,7 @@ void RansCoder::decode(cudaStream_t st, const uint8_t* bytes, size_t len, const 
     throw Error(ERR_BITSTREAM, "bitstream: sub-stream exhausted while decoding (corrupt data)");
   }
 }
+
+void RansCoder::reset_error(cudaStream_t st) { cudaMemsetAsync(err_, 0, sizeof(int), st); }
 
 }  // namespace cra5

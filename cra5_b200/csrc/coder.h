@@ -43,6 +43,14 @@ class RansCoder {
   void invalidate_lut() { lut_for_ = nullptr; lut_rows_ = 0; packed_[0].key = packed_[1].key = nullptr; }
   void decode(cudaStream_t st, const uint8_t* bytes, size_t len, const uint8_t* idx, const CdfTable& tab,
               int n_channels, int L, int32_t* sym_out, const float* mu, const float* median, float* val_out);
+  // the two halves of decode() for CR5B containers: enqueue only (false: nothing to decode) / one synchronisation + the
+  // kernels' error word. Several containers staged at disjoint, 16-byte aligned offsets can share one decode_finish().
+  bool decode_cr5b(cudaStream_t st, const uint8_t* bytes, size_t len, const uint8_t* idx, const CdfTable& tab,
+                   int n_channels, int L, int32_t* sym_out, const float* mu, const float* median, float* val_out,
+                   size_t stage_off, bool sync_before);
+  void decode_finish(cudaStream_t st);
+  void reset_error(cudaStream_t st);
+  size_t stage_capacity() const { return host_stage_cap_; }
 
  private:
   // CDF table repacked for the shared-memory kernels (uint16 rows back to back + coarse inverse table), cached per
