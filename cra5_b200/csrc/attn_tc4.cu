@@ -332,21 +332,47 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&s_full[x], cnt & 1);
         tc_fence_after();
         uint32_t s[NC];
-#pragma unroll
-        for (int c = 0; c < NC; c += 32) tmem_ld_32x32(t_s + c, *reinterpret_cast<uint32_t(*)[32]>(&s[c]));
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&s_empty[x]);                  // S of the next step may overwrite the buffer now
-        if (valid < NC) {                          // warp-uniform: keys beyond the segment do not exist
-#pragma unroll
-          for (int i = 0; i < NC; ++i)
-            if (i >= valid) s[i] = 0xff800000u;    // -inf
-        }
         float mt0 = -INFINITY, mt1 = -INFINITY;
+#if CRA5_TUNE
+        // (experimental "tune" build variant) full tiles read S in two halves: the row maximum of columns 0..63 is
+        // taken while the TMEM load of columns 64..127 is in flight. Same values, same maximum.
+        if (valid >= NC) {
+          tmem_ld_32x32(t_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+          tmem_ld_32x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+          tmem_ld_wait();
+          tmem_ld_32x32(t_s + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+          tmem_ld_32x32(t_s + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
 #pragma unroll
-        for (int i = 0; i < NC; i += 4) {
-          mt0 = fmaxf(mt0, fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
-          mt1 = fmaxf(mt1, fmaxf(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])));
+          for (int i = 0; i < NC / 2; i += 4) {
+            mt0 = fmaxf(mt0, fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
+            mt1 = fmaxf(mt1, fmaxf(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])));
+          }
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&s_empty[x]);                // S of the next step may overwrite the buffer now
+#pragma unroll
+          for (int i = NC / 2; i < NC; i += 4) {
+            mt0 = fmaxf(mt0, fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
+            mt1 = fmaxf(mt1, fmaxf(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])));
+          }
+        } else
+#endif
+        {
+#pragma unroll
+          for (int c = 0; c < NC; c += 32) tmem_ld_32x32(t_s + c, *reinterpret_cast<uint32_t(*)[32]>(&s[c]));
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&s_empty[x]);                // S of the next step may overwrite the buffer now
+          if (valid < NC) {                        // warp-uniform: keys beyond the segment do not exist
+#pragma unroll
+            for (int i = 0; i < NC; ++i)
+              if (i >= valid) s[i] = 0xff800000u;  // -inf
+          }
+#pragma unroll
+          for (int i = 0; i < NC; i += 4) {
+            mt0 = fmaxf(mt0, fmaxf(__uint_as_float(s[i]), __uint_as_float(s[i + 1])));
+            mt1 = fmaxf(mt1, fmaxf(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])));
+          }
         }
         const float mt = fmaxf(mt0, mt1);
         if (j == 0) {
