@@ -3,11 +3,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# CRA5_PDL=1 selects the build variant whose kernel chain uses programmatic dependent launch (cra5_b200/build.py)
-#  CRA5_VARIANT=<name> selects any variant by name ("pdl", "tune")
-VARIANT = os.environ.get("CRA5_VARIANT", "") or ("pdl" if os.environ.get("CRA5_PDL", "0") not in ("", "0") else "")
-if VARIANT not in ("", "pdl", "tune"):
-    raise ImportError(f'unknown CRA5_VARIANT "{VARIANT}" (build variants: "", "pdl", "tune")')
+VARIANT = ""   # build variants (cra5_b200/build.py VARIANTS) -- none at present
 LIB_PATH = os.path.join(_HERE, "lib", f"libcra5b200{'_' + VARIANT if VARIANT else ''}.so")
 
 

@@ -48,6 +48,7 @@ class cra5_api:
             from ..zoo import vaeformer_pretrained
             net = vaeformer_pretrained(quality=268, pretrained=checkpoint is None, checkpoint=checkpoint, device=device)
         self.net = net.eval().to(device)
+        self._fused_norm = None
 
     # ------------------------------------------------------------------ data access
     @property
@@ -93,10 +94,16 @@ class cra5_api:
         """normalisation fused into the codec's first kernel when the model supports it (same arithmetic, one pass
         less over the 1.1 GB frame); otherwise normalise first like the reference does (cra5_api.py:62)."""
         x = frame.unsqueeze(0)
-        try:
+        if self._fused_norm is None:   # decided once from the signature, never by catching TypeError from the call
+            import inspect
+            try:
+                params = inspect.signature(self.net.encode_latent).parameters
+                self._fused_norm = "mean" in params and "std" in params
+            except (TypeError, ValueError):
+                self._fused_norm = False
+        if self._fused_norm:
             return self.net.encode_latent(x, type=type, mean=self.mean.reshape(-1), std=self.std.reshape(-1))
-        except TypeError:
-            return self.net.encode_latent(self.normalization(frame).unsqueeze(0), type=type)
+        return self.net.encode_latent(self.normalization(frame).unsqueeze(0), type=type)
 
     def encode_to_latent(self, time_stamp: str = None, save_root=None, latent_type="float", data=None):
         frame = self._frame(time_stamp, data)

@@ -3,16 +3,6 @@
     python -m cra5_b200.build [--force]
 
 The shared library lands in cra5_b200/lib/ (git-ignored; it travels to the GPU box with the snapshot).
-
-Build variants (same sources, extra -D flags, own object directory, own library name):
-  ""     libcra5b200.so       the default: what the tests, smoke() and bench.py load
-  "pdl"  libcra5b200_pdl.so   -DCRA5_PDL=1: the per-frame kernel chain launched with programmatic dependent launch
-                              (ptx.cuh pdl_grid_sync / host_util.h launch_chained); loaded only when CRA5_PDL=1 is set
-                              in the environment (cra5_b200/_lib.py). Experimental until validated on a B200.
-  "tune" libcra5b200_tune.so  "pdl" + -DCRA5_ARRIVE_CTA_SCOPE=1 (CTA-pair GEMM: CTA-scope release on the epilogue's
-                              accumulator-free arrive instead of a cluster-scope membar) + -DCRA5_TUNE=1 (epilogue
-                              index arithmetic: window map once per tile, multiply-shift divisions, incremental
-                              un-patchify rows); loaded under CRA5_VARIANT=tune.
 """
 import hashlib
 import os
@@ -24,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libcra5b200.so")
-VARIANTS = {"": [], "pdl": ["-DCRA5_PDL=1"], "tune": ["-DCRA5_PDL=1", "-DCRA5_ARRIVE_CTA_SCOPE=1", "-DCRA5_TUNE=1"]}
+VARIANTS = {"": []}   # extra -D flag sets build libcra5b200_<name>.so next to the default (none at present)
 
 
 def lib_path(variant=""):

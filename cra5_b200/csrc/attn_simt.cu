@@ -214,7 +214,6 @@ attn_mma_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __rest
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.z, seg = blockIdx.y;
   const size_t row0 = (size_t)seg * S;
-  pdl_grid_sync();
   // ---- stage K rows [0, S) and V^T columns [0, S) of this (segment, head); zero the padding
   {
     const uint8_t* kg = reinterpret_cast<const uint8_t*>(K + ((size_t)head * rows_total + row0) * HD);
@@ -375,11 +374,7 @@ static bool launch_attn_mma(cudaStream_t st, const __nv_bfloat16* Q, const __nv_
   const int sv = s_pad + 8;   // (sv / 2) % 8 == 4: the 8 rows of an ldmatrix phase fall into distinct bank groups
   const size_t smem = ((size_t)s_pad * HD + (size_t)HD * sv) * 2;
   if (smem > 227 * 1024) return false;
-  static bool configured = false;
-  if (!configured) {
-    CRA5_CUDA(cudaFuncSetAttribute(attn_mma_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  ensure_dynamic_smem(attn_mma_kernel<HD>, 227 * 1024);
   dim3 grid((S + AM_QPB - 1) / AM_QPB, rows_total / S, heads);
   LaunchScope scope(st, "attn_small", 4.0 * heads * (double)rows_total * S * HD, 4.0 * 2.0 * heads * (double)rows_total * HD);
   launch_chained(attn_mma_kernel<HD>, grid, dim3(AM_WARPS * 32), smem, st, Q, K, Vt, out, ldo, rows_total, S, s_pad, sv);
@@ -401,11 +396,7 @@ void attention_simt(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16
     const int kv_words = (int)((std::max((size_t)seg_len * kw, (size_t)hd * vw) + 1) & ~size_t(1));  // keeps sc 8-byte aligned
     const size_t smem2 = (size_t)kv_words * 4 + ((size_t)AS_WARPS * AS2_QPW * seg_len + (size_t)AS_WARPS * AS2_QPW * hd) * 4;
     if (smem2 <= 227 * 1024) {
-      static size_t configured2 = 0;
-      if (smem2 > 48 * 1024 && smem2 > configured2) {
-        CRA5_CUDA(cudaFuncSetAttribute(attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        configured2 = smem2;
-      }
+      ensure_dynamic_smem(attn_small_kernel, smem2);
       dim3 grid((seg_len + AS2_QPB - 1) / AS2_QPB, rows_total / seg_len, heads);
       LaunchScope scope(st, "attn_small", 4.0 * heads * (double)rows_total * seg_len * hd,
                         4.0 * 2.0 * heads * (double)rows_total * hd);
@@ -417,11 +408,7 @@ void attention_simt(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16
   }
   const size_t smem = ((size_t)AS_WARPS * seg_len + (size_t)AS_WARPS * hd) * sizeof(float);
   CRA5_CHECK(smem <= 200 * 1024, ERR_INVALID, "attention_simt: segment too long for the generic kernel");
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    CRA5_CUDA(cudaFuncSetAttribute(attn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  ensure_dynamic_smem(attn_simt_kernel, smem);
   dim3 grid((seg_len + AS_WARPS - 1) / AS_WARPS, rows_total / seg_len, heads);
   LaunchScope scope(st, "attn_simt", 4.0 * heads * (double)rows_total * seg_len * hd,
                     4.0 * 2.0 * heads * (double)rows_total * hd);

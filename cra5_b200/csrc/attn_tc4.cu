@@ -1,8 +1,8 @@
 // attn_tc4.cu -- persistent, ping-pong fused softmax(Q K^T) V on tcgen05 tensor cores for head_dim 64.
 //
-// Same contract as attn_tc.cu (reference: WindowAttention.forward vit_nlc.py:219-258 incl. the un-masked zero-pad
-// tokens, and Attention.forward vit_nlc.py:94-112; token list in "attention order", a segment = seg_len contiguous
-// rows, Q pre-multiplied by head_dim^-0.5), restructured around what bounds head_dim 64 on Blackwell: the softmax, not
+// Contract (reference: WindowAttention.forward vit_nlc.py:219-258 incl. the un-masked zero-pad
+// tokens, and Attention.forward vit_nlc.py:94-112): token list in "attention order", a segment = seg_len contiguous
+// rows, Q pre-multiplied by head_dim^-0.5. Organised around what bounds head_dim 64 on Blackwell: the softmax, not
 // the MMAs (512 tensor cycles per 128x128 tile against 16 384 exponentials on 16 MUFU lanes per SM and clock).
 //
 //   * one CTA per SM, persistent over work items; an item = TWO 128-row query tiles (A, B) of one (segment, head) that
@@ -193,7 +193,7 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&q_full[s], 1);
-      mbar_init(&q_empty[s], 2);       // one arrival per query tile's MMA thread
+      mbar_init(&q_empty[s], 2);       // one arrival per query tile's MMA thread (an absent tile B still arrives)
       mbar_init(&s_full[s], 1);
       mbar_init(&s_empty[s], 128);
       mbar_init(&p_full[s], 128);
@@ -210,7 +210,6 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_grid_sync();
 
   if (warp < 4) {
     reg_dec<64>();    // the pool setmaxnreg draws from is what the launch allocated: 384 x 168 >= 128 x 64 + 256 x 216
@@ -262,8 +261,22 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t kv_first = it_kv;
         it_kv += n_kv;
         ++it_q;
-        if (x == 1 && !it.act_b) continue;
-        const int n_arrive = (x == 0 && !it.act_b) ? 2 : 1;   // tile A also signs for an absent tile B
+        if (x == 1 && !it.act_b) {
+          // Tile B is absent from this item. Its issuer still CONSUMES the item's Q buffer and K/V stages -- waits for
+          // each to fill, releases it unused -- so that its barrier phases advance in lock step with the producer. (It
+          // used to skip the item while tile A's issuer signed the releases for it. A parity wait only tells "phase
+          // n done" from "phase n+1 done": after skipping two items in a row -- padded-window segments -- this thread
+          // could be two phases behind q_full, take a Q buffer that had not landed yet as ready and release buffers
+          // that were still in use. Timing dependent: seen only with a second stream competing for the memory system.)
+          mbar_wait(&q_full[qb], q_phase);
+          for (int j = 0; j < n_kv; ++j) {
+            const int s = (kv_first + j) % A4_STAGES;
+            mbar_wait(&kv_full[s], ((kv_first + j) / A4_STAGES) & 1);
+            mbar_arrive(&kv_empty[s]);
+          }
+          mbar_arrive(&q_empty[qb]);
+          continue;
+        }
         mbar_wait(&q_full[qb], q_phase);
         tc_fence_after();
         const uint64_t qdesc = q_desc0 + (uint64_t)((qb * L::Q_BUF + x * L::Q_TILE) >> 4);
@@ -281,7 +294,7 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             umma_commit(&s_full[x]);
             ++cnt_s;
             if (j == n_kv - 1)                         // Q buffer reusable once the last S products retire
-              for (int a = 0; a < n_arrive; ++a) umma_commit(&q_empty[qb]);
+              umma_commit(&q_empty[qb]);
           }
           if (j > 0) {
             const int s = (kv_first + j - 1) % A4_STAGES;
@@ -300,7 +313,7 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             umma_bf16_ts(d_o, a_p + 56, vdesc + VH + 6, idesc_pv, 1);
             umma_commit(&pv_done[x]);
             ++cnt_p;
-            for (int a = 0; a < n_arrive; ++a) umma_commit(&kv_empty[s]);
+            umma_commit(&kv_empty[s]);
           }
         }
       }
@@ -333,9 +346,8 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_after();
         uint32_t s[NC];
         float mt0 = -INFINITY, mt1 = -INFINITY;
-#if CRA5_TUNE
-        // (experimental "tune" build variant) full tiles read S in two halves: the row maximum of columns 0..63 is
-        // taken while the TMEM load of columns 64..127 is in flight. Same values, same maximum.
+        // full tiles read S in two halves: the row maximum of columns 0..63 is taken while the TMEM load of columns
+        // 64..127 is in flight. Same values, same maximum.
         if (valid >= NC) {
           tmem_ld_32x32(t_s + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
           tmem_ld_32x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
@@ -356,7 +368,6 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mt1 = fmaxf(mt1, fmaxf(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])));
           }
         } else
-#endif
         {
 #pragma unroll
           for (int c = 0; c < NC; c += 32) tmem_ld_32x32(t_s + c, *reinterpret_cast<uint32_t(*)[32]>(&s[c]));
@@ -484,20 +495,11 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 void attention_tc(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* Vt,
                   __nv_bfloat16* out, int ldo, int heads, int rows_total, int seg_len, int q_part_from,
                   int q_part_rows) {
-  static const char* env = getenv("CRA5_ATTN");  // diagnostics: 3 = previous kernel
-  if (env != nullptr && atoi(env) == 3) {
-    attention_tc3(st, Q, K, Vt, out, ldo, heads, rows_total, seg_len);
-    return;
-  }
   CRA5_CHECK(seg_len > 0 && rows_total % seg_len == 0, ERR_INVALID, "attention: rows must be whole segments");
   CRA5_CHECK((rows_total & 7) == 0, ERR_INVALID, "attention: rows_total must be a multiple of 8 (TMA stride)");
   static const int poly = [] { const char* e = getenv("CRA5_ATTN_POLY"); return e ? atoi(e) : 3; }();
   auto kern = poly == 0 ? attn_tc4_kernel<0> : poly == 2 ? attn_tc4_kernel<2> : poly == 4 ? attn_tc4_kernel<4> : attn_tc4_kernel<3>;
-  static bool configured = false;
-  if (!configured) {
-    CRA5_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A4Smem::TOTAL));
-    configured = true;
-  }
+  ensure_dynamic_smem(kern, A4Smem::TOTAL);
   CUtensorMap tmQ = make_tmap_bf16_2d(Q, A4_HD, (uint64_t)heads * rows_total, A4_HD * 2, A4_HD, A4_BM);
   CUtensorMap tmK = make_tmap_bf16_2d(K, A4_HD, (uint64_t)heads * rows_total, A4_HD * 2, A4_HD, A4_BN);
   CUtensorMap tmVt = make_tmap_bf16_2d(Vt, (uint64_t)rows_total, (uint64_t)heads * A4_HD, (uint64_t)rows_total * 2,

@@ -137,6 +137,13 @@ int cra5_model_set_coder(cra5_model* m, int spc_y, int spc_z) {
   });
 }
 
+int cra5_model_set_precision(cra5_model* m, int level) {
+  return guarded([&] {
+    MODEL_GUARD(m);
+    m->impl->set_precision(level);
+  });
+}
+
 int cra5_encode_to_latent(cra5_model* m, const float* x, float* y, const float* mean, const float* std_, void* stream) {
   return guarded([&] {
     MODEL_GUARD(m);

@@ -252,7 +252,7 @@ void RansCoder::decode(cudaStream_t st, const uint8_t* bytes, size_t len, const 
 // multiple of 16) and enqueues the upload, the length scan and the decode kernel. Returns false when there is nothing
 // to decode (no GPU work enqueued). With sync_before the stream is drained first, because the staging buffer may still
 // be in flight from a previous call; a caller that stages two containers at disjoint offsets inside one call passes
-// false for the second (CRA5_TUNE: Model::bin_to_latent). Errors found by the kernels are collected by decode_finish().
+// false for the second (Model::bin_to_latent). Errors found by the kernels are collected by decode_finish().
 bool RansCoder::decode_cr5b(cudaStream_t st, const uint8_t* bytes, size_t len, const uint8_t* idx, const CdfTable& tab,
                             int n_channels, int L, int32_t* sym_out, const float* mu, const float* median,
                             float* val_out, size_t stage_off, bool sync_before) {

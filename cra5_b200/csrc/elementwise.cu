@@ -13,11 +13,18 @@
 
 namespace cra5 {
 
+// split-bf16 precision mode (GemmShape::a_split): v ~ hi + lo with hi = bf16(v), lo = bf16(v - hi). Every producer of a
+// GEMM A operand below takes an optional `lo` output (same layout as the bf16 output); null = plain bf16.
+__device__ __forceinline__ __nv_bfloat16 bf16_lo(float v) {
+  return __float2bfloat16(v - __bfloat162float(__float2bfloat16(v)));
+}
+
 // ------------------------------------------------------------------------------------------------ frame_to_patches
 // grid: (Wp / TOK, H, ceil(C / CH)); block 256. Stages a [CH][TOK*pw] tile through shared memory so that both the
 // NCHW reads (runs of TOK*pw floats) and the patch-major writes (runs of CH*pw bf16) are coalesced.
 template <int TOK, int CH>
 __global__ void __launch_bounds__(256) frame_to_patches_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                               __nv_bfloat16* __restrict__ out_lo,
                                                                const float* __restrict__ mean,
                                                                const float* __restrict__ std_, int C, int H, int W,
                                                                int Wp, int pw, int cs_pad) {
@@ -39,7 +46,10 @@ __global__ void __launch_bounds__(256) frame_to_patches_kernel(const float* __re
   for (int e = threadIdx.x; e < TOK * seg; e += blockDim.x) {
     const int jl = e / seg, q = e - jl * seg;
     const int cl = q / pw, s = q - cl * pw;
-    out[((size_t)h * Wp + j0 + jl) * cs_pad + (size_t)c0 * pw + q] = __float2bfloat16(tile[cl * run + jl * pw + s]);
+    const size_t o = ((size_t)h * Wp + j0 + jl) * cs_pad + (size_t)c0 * pw + q;
+    const float v = tile[cl * run + jl * pw + s];
+    out[o] = __float2bfloat16(v);
+    if (out_lo != nullptr) out_lo[o] = bf16_lo(v);
   }
 }
 
@@ -94,12 +104,12 @@ __global__ void __launch_bounds__(256) frame_to_patches_vec_kernel(const float* 
 }
 
 void frame_to_patches(cudaStream_t st, const float* x, __nv_bfloat16* out, const float* mean, const float* std_,
-                      int C, int H, int W, int Wp, int pw, int cs_pad) {
+                      int C, int H, int W, int Wp, int pw, int cs_pad, __nv_bfloat16* out_lo) {
   constexpr int TOK = 8, CH = 64;
   CRA5_CHECK(Wp % TOK == 0, ERR_INVALID, "unsupported geometry: patches per row must be a multiple of 8");
   CRA5_CHECK(Wp * pw <= W, ERR_INVALID, "frame_to_patches: geometry");
   dim3 grid(Wp / TOK, H, (C + CH - 1) / CH);
-  if (pw == 10 && (W & 3) == 0 && (cs_pad & 7) == 0) {
+  if (out_lo == nullptr && pw == 10 && (W & 3) == 0 && (cs_pad & 7) == 0) {
     LaunchScope scope(st, "frame_to_patches", 0.0, 4.0 * C * H * (double)W + 2.0 * H * (double)Wp * C * pw);
     frame_to_patches_vec_kernel<TOK, CH, 10><<<grid, 256, 0, st>>>(x, out, mean, std_, C, H, W, Wp, cs_pad);
     CRA5_CUDA(cudaGetLastError());
@@ -108,7 +118,7 @@ void frame_to_patches(cudaStream_t st, const float* x, __nv_bfloat16* out, const
   const size_t smem = (size_t)CH * TOK * pw * sizeof(float);
   CRA5_CHECK(smem <= 48 * 1024, ERR_INVALID, "unsupported geometry: patch width too large");
   LaunchScope scope(st, "frame_to_patches", 0.0, 4.0 * C * H * (double)W + 2.0 * H * (double)Wp * C * pw);
-  frame_to_patches_kernel<TOK, CH><<<grid, 256, smem, st>>>(x, out, mean, std_, C, H, W, Wp, pw, cs_pad);
+  frame_to_patches_kernel<TOK, CH><<<grid, 256, smem, st>>>(x, out, out_lo, mean, std_, C, H, W, Wp, pw, cs_pad);
   CRA5_CUDA(cudaGetLastError());
 }
 
@@ -117,16 +127,20 @@ void frame_to_patches(cudaStream_t st, const float* x, __nv_bfloat16* out, const
 template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float eps,
-                                                             __nv_bfloat16* __restrict__ out, int rows_out, int D,
+                                                             __nv_bfloat16* __restrict__ out,
+                                                             __nv_bfloat16* __restrict__ out_lo, int rows_out, int D,
                                                              WinMap wm) {
-  pdl_grid_sync();  // reads x and overwrites `out`, which the previous kernels may still be using
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows_out) return;
   __nv_bfloat16* o = out + (size_t)warp * D;
+  __nv_bfloat16* ol = out_lo != nullptr ? out_lo + (size_t)warp * D : nullptr;
   const int t = wm.to_token(warp);
   if (t < 0) {  // zero pad token (F.pad after the norm, vit_nlc.py:233)
-    for (int i = lane; i < D; i += 32) o[i] = __float2bfloat16(0.f);
+    for (int i = lane; i < D; i += 32) {
+      o[i] = __float2bfloat16(0.f);
+      if (ol != nullptr) ol[i] = __float2bfloat16(0.f);
+    }
     return;
   }
   const float* r = x + (size_t)t * D;
@@ -154,7 +168,11 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __rest
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = lane + 32 * i;
-    if (idx < D) o[idx] = __float2bfloat16((v[i] - mean) * rstd * gamma[idx] + beta[idx]);
+    if (idx < D) {
+      const float r_ = (v[i] - mean) * rstd * gamma[idx] + beta[idx];
+      o[idx] = __float2bfloat16(r_);
+      if (ol != nullptr) ol[idx] = bf16_lo(r_);
+    }
   }
 }
 
@@ -164,7 +182,6 @@ template <int NV>  // NV = D / 128 float4 groups per lane
 __global__ void __launch_bounds__(256) layernorm_bf16_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, float eps,
                                                                  __nv_bfloat16* __restrict__ out, int rows_out, WinMap wm) {
-  pdl_grid_sync();
   constexpr int D = NV * 128;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -209,34 +226,31 @@ __global__ void __launch_bounds__(256) layernorm_bf16_vec_kernel(const float* __
 }
 
 void layernorm_bf16(cudaStream_t st, const float* x, const float* gamma, const float* beta, float eps,
-                    __nv_bfloat16* out, int rows_out, int D, const WinMap& wm) {
+                    __nv_bfloat16* out, int rows_out, int D, const WinMap& wm, __nv_bfloat16* out_lo) {
   const int blocks = (rows_out + 7) / 8;
-  LaunchScope scope(st, "layernorm_bf16", 0.0, 6.0 * rows_out * (double)D);
-  if (D == 1024) {
-    launch_chained(layernorm_bf16_vec_kernel<8>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, out, rows_out, wm);
-    return;
-  }
-  if (D == 128) {
-    launch_chained(layernorm_bf16_vec_kernel<1>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, out, rows_out, wm);
-    return;
-  }
-  if (D <= 128)
-    launch_chained(layernorm_bf16_kernel<4>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, out, rows_out, D, wm);
-  else if (D <= 512)
-    launch_chained(layernorm_bf16_kernel<16>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, out, rows_out, D, wm);
-  else if (D <= 1024)
-    launch_chained(layernorm_bf16_kernel<32>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, out, rows_out, D, wm);
-  else if (D <= 2048)
-    launch_chained(layernorm_bf16_kernel<64>, dim3(blocks), dim3(256), 0, st, x, gamma, beta, eps, out, rows_out, D, wm);
-  else
+  LaunchScope scope(st, "layernorm_bf16", 0.0, (out_lo != nullptr ? 8.0 : 6.0) * rows_out * (double)D);
+  if (out_lo == nullptr && D == 1024) {
+    layernorm_bf16_vec_kernel<8><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, rows_out, wm);
+  } else if (out_lo == nullptr && D == 128) {
+    layernorm_bf16_vec_kernel<1><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, rows_out, wm);
+  } else if (D <= 128) {
+    layernorm_bf16_kernel<4><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, out_lo, rows_out, D, wm);
+  } else if (D <= 512) {
+    layernorm_bf16_kernel<16><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, out_lo, rows_out, D, wm);
+  } else if (D <= 1024) {
+    layernorm_bf16_kernel<32><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, out_lo, rows_out, D, wm);
+  } else if (D <= 2048) {
+    layernorm_bf16_kernel<64><<<blocks, 256, 0, st>>>(x, gamma, beta, eps, out, out_lo, rows_out, D, wm);
+  } else {
     throw Error(ERR_INVALID, "layernorm: width > 2048 unsupported");
+  }
   CRA5_CUDA(cudaGetLastError());
 }
 
 // ------------------------------------------------------------------------------------------------ im2col (hyper conv)
 // y [C][Hy][Wy] fp32 -> A [(i,j)][(c, r, s)] bf16 with patch == stride == (p1, p2)
-__global__ void im2col_latent_kernel(const float* __restrict__ y, __nv_bfloat16* __restrict__ A, int C, int Hy, int Wy,
-                                     int p1, int p2, int lda) {
+__global__ void im2col_latent_kernel(const float* __restrict__ y, __nv_bfloat16* __restrict__ A,
+                                     __nv_bfloat16* __restrict__ A_lo, int C, int Hy, int Wy, int p1, int p2, int lda) {
   const int Wh = Wy / p2;
   const int K = C * p1 * p2;
   const size_t total = (size_t)(Hy / p1) * Wh * K;
@@ -246,22 +260,25 @@ __global__ void im2col_latent_kernel(const float* __restrict__ y, __nv_bfloat16*
     const int i = tok / Wh, j = tok - i * Wh;
     const int c = k / (p1 * p2), rs = k - c * p1 * p2;
     const int r = rs / p2, s = rs - r * p2;
-    A[(size_t)tok * lda + k] = __float2bfloat16(y[((size_t)c * Hy + i * p1 + r) * Wy + j * p2 + s]);
+    const float v = y[((size_t)c * Hy + i * p1 + r) * Wy + j * p2 + s];
+    A[(size_t)tok * lda + k] = __float2bfloat16(v);
+    if (A_lo != nullptr) A_lo[(size_t)tok * lda + k] = bf16_lo(v);
   }
 }
 
-void im2col_latent(cudaStream_t st, const float* y, __nv_bfloat16* A, int C, int Hy, int Wy, int p1, int p2, int lda) {
+void im2col_latent(cudaStream_t st, const float* y, __nv_bfloat16* A, int C, int Hy, int Wy, int p1, int p2, int lda,
+                   __nv_bfloat16* A_lo) {
   const size_t total = (size_t)(Hy / p1) * (Wy / p2) * C * p1 * p2;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
   LaunchScope scope(st, "im2col_latent", 0.0, 6.0 * (double)total);
-  im2col_latent_kernel<<<blocks, 256, 0, st>>>(y, A, C, Hy, Wy, p1, p2, lda);
+  im2col_latent_kernel<<<blocks, 256, 0, st>>>(y, A, A_lo, C, Hy, Wy, p1, p2, lda);
   CRA5_CUDA(cudaGetLastError());
 }
 
 // ------------------------------------------------------------------------------------------------ transpose + cast
 // in [C][T] fp32 -> out [T][ldo] bf16 (columns 0..C-1)
-__global__ void transpose_cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int T,
-                                      int ldo) {
+__global__ void transpose_cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                      __nv_bfloat16* __restrict__ out_lo, int C, int T, int ldo) {
   __shared__ float tile[32][33];
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -271,14 +288,17 @@ __global__ void transpose_cast_kernel(const float* __restrict__ in, __nv_bfloat1
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int t = t0 + r, c = c0 + threadIdx.x;
-    if (t < T && c < C) out[(size_t)t * ldo + c] = __float2bfloat16(tile[threadIdx.x][r]);
+    if (t < T && c < C) {
+      out[(size_t)t * ldo + c] = __float2bfloat16(tile[threadIdx.x][r]);
+      if (out_lo != nullptr) out_lo[(size_t)t * ldo + c] = bf16_lo(tile[threadIdx.x][r]);
+    }
   }
 }
 
-void transpose_cast(cudaStream_t st, const float* in, __nv_bfloat16* out, int C, int T, int ldo) {
+void transpose_cast(cudaStream_t st, const float* in, __nv_bfloat16* out, int C, int T, int ldo, __nv_bfloat16* out_lo) {
   dim3 grid((T + 31) / 32, (C + 31) / 32), block(32, 8);
   LaunchScope scope(st, "transpose_cast", 0.0, 6.0 * C * (double)T);
-  transpose_cast_kernel<<<grid, block, 0, st>>>(in, out, C, T, ldo);
+  transpose_cast_kernel<<<grid, block, 0, st>>>(in, out, out_lo, C, T, ldo);
   CRA5_CUDA(cudaGetLastError());
 }
 
@@ -291,6 +311,32 @@ void cast_bf16(cudaStream_t st, const float* in, __nv_bfloat16* out, size_t n) {
   const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
   LaunchScope scope(st, "cast_bf16", 0.0, 6.0 * (double)n);
   cast_bf16_kernel<<<blocks, 256, 0, st>>>(in, out, n);
+  CRA5_CUDA(cudaGetLastError());
+}
+
+// fp32 rows -> split bf16 rows (hi, lo), optionally through the exact-erf GELU (nn.GELU default, vit_nlc.py:53): the
+// A-operand producer of the split-precision mode wherever the default path fuses the bf16 cast into a GEMM epilogue
+// (fc1 -> GELU -> fc2, the mean || logvar concat in front of quant_conv) or uses cast_bf16.
+__global__ void split_rows_kernel(const float* __restrict__ in, int ld_in, int rows, int cols,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld_out, int gelu) {
+  const size_t total = (size_t)rows * cols;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = e / cols;
+    const int c = (int)(e - r * cols);
+    float v = in[r * ld_in + c];
+    if (gelu) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    hi[r * ld_out + c] = __float2bfloat16(v);
+    if (lo != nullptr) lo[r * ld_out + c] = bf16_lo(v);
+  }
+}
+
+void split_rows(cudaStream_t st, const float* in, int ld_in, int rows, int cols, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                int ld_out, bool gelu) {
+  const size_t total = (size_t)rows * cols;
+  if (total == 0) return;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  LaunchScope scope(st, "split_rows", 0.0, 8.0 * (double)total);
+  split_rows_kernel<<<blocks, 256, 0, st>>>(in, ld_in, rows, cols, hi, lo, ld_out, gelu ? 1 : 0);
   CRA5_CUDA(cudaGetLastError());
 }
 

@@ -35,7 +35,8 @@ gc_quantize_index_kernel(const float* __restrict__ y, const float* __restrict__ 
                          const float* __restrict__ scale_table, int levels, float bound, int32_t* __restrict__ sym,
                          uint8_t* __restrict__ idx, float* __restrict__ y_hat, size_t n) {
   __shared__ float tab[256];
-  for (int i = threadIdx.x; i < levels; i += blockDim.x) tab[i] = scale_table[i];
+  if (scale_table != nullptr)   // only needed for the index output; callers that want symbols / y_hat alone pass null
+    for (int i = threadIdx.x; i < levels; i += blockDim.x) tab[i] = scale_table[i];
   __syncthreads();
   const size_t n4 = n >> 2;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
@@ -78,6 +79,9 @@ gc_quantize_index_kernel(const float* __restrict__ y, const float* __restrict__ 
 void gc_quantize_index(cudaStream_t st, const float* y, const float* sigma, const float* mu, const float* scale_table,
                        int levels, float bound, int32_t* sym, uint8_t* idx, float* y_hat, size_t n) {
   CRA5_CHECK(levels >= 1 && levels <= 256, ERR_INVALID, "scale table must have 1..256 levels");
+  CRA5_CHECK(idx == nullptr || (scale_table != nullptr && sigma != nullptr), ERR_INVALID,
+             "gc_quantize_index: the index output needs sigma and the scale table");
+  CRA5_CHECK(y == nullptr || mu != nullptr, ERR_INVALID, "gc_quantize_index: y needs mu");
   if (n == 0) return;
   const int blocks = (int)std::min<size_t>(((n >> 2) + 255) / 256 + 1, 148 * 8);
   // algorithmic bytes: read y, sigma, mu (12 B) + write int32 symbol and uint8 index (5 B) per element
@@ -863,11 +867,7 @@ void rans_encode_smem(cudaStream_t st, const int32_t* sym, const uint8_t* idx, b
   const int n_streams = n_channels * spc;
   if (n_streams == 0) return;
   const size_t smem = smem_tables_bytes(rows, total, false);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    CRA5_CUDA(cudaFuncSetAttribute(rans_encode_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = 200 * 1024;
-  }
+  if (smem > 48 * 1024) ensure_dynamic_smem(rans_encode_smem_kernel, 200 * 1024);
   {
     LaunchScope scope(st, "rans_encode", 0.0, (double)n_channels * L * (index_is_channel ? 4.0 : 5.0));
     rans_encode_smem_kernel<<<(n_streams + RANS_STHREADS - 1) / RANS_STHREADS, RANS_STHREADS, smem, st>>>(
@@ -893,11 +893,7 @@ void rans_decode_smem(cudaStream_t st, const uint8_t* payload, const uint32_t* o
   const int n_streams = n_channels * spc;
   if (n_streams == 0) return;
   const size_t smem = smem_tables_bytes(rows, total, lut != nullptr);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    CRA5_CUDA(cudaFuncSetAttribute(rans_decode_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = 200 * 1024;
-  }
+  if (smem > 48 * 1024) ensure_dynamic_smem(rans_decode_smem_kernel, 200 * 1024);
   LaunchScope scope(st, "rans_decode", 0.0, (double)n_channels * L * (index_is_channel ? 4.0 : 9.0));
   rans_decode_smem_kernel<<<(n_streams + RANS_STHREADS - 1) / RANS_STHREADS, RANS_STHREADS, smem, st>>>(
       payload, offsets, idx, index_is_channel ? 1 : 0, packed, row_off, cdf_len, offset, lut, rows, total, n_channels, L,

@@ -10,18 +10,15 @@ namespace cra5 {
 template <int BN, int KIND>
 static void launch_one(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp,
                        const EpiParams& epi) {
-  static bool configured = false;
   auto kern = gemm_tc_kernel<BN, KIND>;
-  if (!configured) {
-    CRA5_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL));
-    configured = true;
-  }
+  ensure_dynamic_smem(kern, GemmSmem<BN>::TOTAL);
   const int m_tiles = (shp.M + GEMM_BM - 1) / GEMM_BM;
   const int n_tiles = (shp.N + BN - 1) / BN;
   int grid = m_tiles * n_tiles;
   const int sms = device_sm_count();
   if (grid > sms) grid = sms;
-  LaunchScope scope(st, "gemm_tc", 2.0 * shp.M * shp.N * shp.K,
+  // (split-bf16 launches execute 2-3x the tensor work of their algorithmic flops; the profiler counts the algorithmic ones)
+  LaunchScope scope(st, (shp.a_split || shp.b_split) ? "gemm_tc_split" : "gemm_tc", 2.0 * shp.M * shp.N * shp.K,
                     2.0 * ((double)shp.M * shp.K + (double)shp.N * shp.K) +
                         (double)shp.M * shp.N * ((KIND == EPI_BF16 || KIND == EPI_GELU_BF16 || KIND == EPI_QKV) ? 2.0 : 4.0));
   launch_chained(kern, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN>::TOTAL, st, tmA, tmB, shp, epi);
@@ -30,12 +27,8 @@ static void launch_one(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMa
 template <int KIND>
 static void launch_pair(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& shp,
                         const EpiParams& epi) {
-  static bool configured = false;
   auto kern = gemm_tc2_kernel<KIND>;
-  if (!configured) {
-    CRA5_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem2::TOTAL));
-    configured = true;
-  }
+  ensure_dynamic_smem(kern, GemmSmem2::TOTAL);
   const int m_tiles = (shp.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
   const int n_tiles = (shp.N + GemmSmem2::BN - 1) / GemmSmem2::BN;
   int clusters = m_tiles * n_tiles;
@@ -106,10 +99,19 @@ void launch_gemm(cudaStream_t st, int bn, int kind, const CUtensorMap& tmA, cons
     throw Error(ERR_INTERNAL, "gemm: unsupported BN");
 }
 
+// 2D operand map (k, row), or 3D (k, row, half) when the operand is carried as split bf16 halves `half_elems` apart
+static CUtensorMap operand_map(const __nv_bfloat16* p, int K, int rows, int ld, int box_rows, size_t half_elems) {
+  if (half_elems == 0) return make_tmap_bf16_2d(p, (uint64_t)K, (uint64_t)rows, (uint64_t)ld * 2, GEMM_BK, box_rows);
+  uint64_t dims[3] = {(uint64_t)K, (uint64_t)rows, 2};
+  uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)half_elems * 2};
+  uint32_t box[3] = {GEMM_BK, (uint32_t)box_rows, 1};
+  return make_tmap_bf16(p, 3, dims, strides, box, true);
+}
+
 // Plain row-major GEMM convenience: A [M,K] (row stride lda elements), B [N,K] (row stride ldb), both bf16.
 void gemm_plain(cudaStream_t st, int kind, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M,
-                int N, int K, const EpiParams& epi) {
-  if (gemm_use_pair(M, N, K, kind)) {
+                int N, int K, const EpiParams& epi, const GemmSplit& split) {
+  if (!split.any() && gemm_use_pair(M, N, K, kind)) {
     CUtensorMap tmA = make_tmap_bf16_2d(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, GEMM_BK, GEMM_BM);
     CUtensorMap tmB = make_tmap_bf16_2d(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, GEMM_BK, GemmSmem2::BN / 2);
     GemmShape shp{};
@@ -120,11 +122,14 @@ void gemm_plain(cudaStream_t st, int kind, const __nv_bfloat16* A, int lda, cons
   int bn = gemm_pick_bn(N);
   // short main loop + residual epilogue + few tiles (attention projection: K = N = 1024 -> 2.2 waves of 128 x 256 tiles):
   // 128 x 128 tiles give every CTA 4-5 tiles to pipeline and halve the exposed last epilogue (379 -> 442 TFLOP/s)
-  if (getenv("CRA5_GEMM_BN") == nullptr && bn == 256 && kind == EPI_RESID && K <= 1024 && N <= 1024 && M >= 4096) bn = 128;
-  CUtensorMap tmA = make_tmap_bf16_2d(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, GEMM_BK, GEMM_BM);
-  CUtensorMap tmB = make_tmap_bf16_2d(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, GEMM_BK, bn);
+  if (getenv("CRA5_GEMM_BN") == nullptr && bn == 256 && kind == EPI_RESID && K <= 1024 && N <= 1024 && M >= 4096 &&
+      !split.any())
+    bn = 128;
+  CUtensorMap tmA = operand_map(A, K, M, lda, GEMM_BM, split.a_half);
+  CUtensorMap tmB = operand_map(B, K, N, ldb, bn, split.b_half);
   GemmShape shp{};
   shp.M = M; shp.N = N; shp.K = K; shp.a_mode = A_PLAIN;
+  shp.a_split = split.a_half != 0; shp.b_split = split.b_half != 0;
   launch_gemm(st, bn, kind, tmA, tmB, shp, epi);
 }
 

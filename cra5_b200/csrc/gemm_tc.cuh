@@ -41,16 +41,20 @@ struct GemmShape {
   // A_CONCAT
   int cc_D;      // split point in K (multiple of 64)
   int cc_shift;  // row shift for the second half
+  // split-bf16 precision ("bf16x3", 1-CTA kernel only): an fp32 operand v is carried as hi = bf16(v), lo = bf16(v - hi),
+  // stored as two halves addressed by ONE extra (outermost) tensor-map coordinate. With both operands split every
+  // k-block is issued three times -- (A_hi, B_hi), (A_lo, B_hi), (A_hi, B_lo) -- into the same fp32 accumulator, which
+  // recovers ~16 mantissa bits per operand (the dropped lo*lo term is 2^-18 relative); with only B split (A is bf16 by
+  // construction, e.g. the attention output) twice. The MMA issuer and the epilogues are unchanged: the producer
+  // simply feeds more k-blocks.
+  int a_split, b_split;
 };
 
-// CRA5_TUNE=1 (the experimental "tune" build variant, cra5_b200/build.py) removes index arithmetic from the epilogues
-// without changing a single result: the window map of a residual tile row is computed once per tile instead of once
-// per 32-column chunk, its four integer divisions (about 20 instructions each: I2F, MUFU.RCP, F2I, fix-up) become
-// multiply-high + shift by host-precomputed constants, the QKV head split uses compares and a shift, and the
-// un-patchify / pixel-shuffle epilogues advance (i, j) incrementally instead of dividing per row.
-#ifndef CRA5_TUNE
-#define CRA5_TUNE 0
-#endif
+// Epilogue index arithmetic: the window map of a residual tile row is computed once per tile (not once per 32-column
+// chunk), its four integer divisions (about 20 instructions each: I2F, MUFU.RCP, F2I, fix-up) are multiply-high + shift
+// by host-precomputed constants, the QKV head split uses compares and a shift, and the un-patchify epilogue advances
+// (i, j) incrementally instead of dividing per row. (Validated bit-identical against the division forms on a B200,
+// 2.7 % of the frame time; round 2.)
 
 // n / d for 0 <= n < 2^31 and a positive divisor fixed at launch time (the CUTLASS FastDivmod construction:
 // m = ceil(2^(31 + ceil(log2 d)) / d); verified exhaustively for the divisors that occur here)
@@ -80,7 +84,6 @@ struct WinMap {
   int H, W;        // token grid
   int wh, ww;      // window
   int nWr, nWc;    // windows per column / row after padding
-#if CRA5_TUNE
   FastDiv f_wsz, f_ww, f_pf, f_nwc;
   void finish() {   // host: call after the integer fields are set
     f_wsz = FastDiv::make(wh * ww);
@@ -101,39 +104,16 @@ struct WinMap {
     if (h >= H || w >= W) return -1;
     return (b * H + h) * W + w;
   }
-#else
-  void finish() {}
-  __device__ __forceinline__ int to_token(int a) const {  // -1 for a pad row
-    if (!enabled) return a;
-    const int wsz = wh * ww;
-    int wi = a / wsz, within = a - wi * wsz;
-    int r = within / ww, c = within - r * ww;
-    int per_frame = nWr * nWc;
-    int b = wi / per_frame;
-    wi -= b * per_frame;
-    int wr = wi / nWc, wc = wi - wr * nWc;
-    int h = wr * wh + r, w = wc * ww + c;
-    if (h >= H || w >= W) return -1;
-    return (b * H + h) * W + w;
-  }
-#endif
 };
 
 // QKV column -> (which of q|k|v, head, dim): divisions by the model width and the head width (EPI_QKV epilogues)
 struct QkvSplit { int which, head, d; };
 __device__ __forceinline__ QkvSplit qkv_split(int col, int D, int hd) {
   QkvSplit q;
-#if CRA5_TUNE
   q.which = (col >= 2 * D) ? 2 : (col >= D ? 1 : 0);
   const int within = col - q.which * D;
   q.head = ((hd & (hd - 1)) == 0) ? (within >> (31 - __clz(hd))) : within / hd;   // warp-uniform choice
   q.d = within - q.head * hd;
-#else
-  q.which = col / D;
-  const int within = col - q.which * D;
-  q.head = within / hd;
-  q.d = within - q.head * hd;
-#endif
   return q;
 }
 
@@ -463,7 +443,6 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& p, const float* s
     const int rk = col / p.ct_CS, cs = col - rk * p.ct_CS;
     const int c = cs / p.ct_pw, s_ = cs - c * p.ct_pw;
     float* plane = p.out_f32 + (size_t)c * p.ct_Himg * p.ct_Wimg + s_;
-#if CRA5_TUNE
     int i_ = row_base / p.ct_Wp, j_ = row_base - i_ * p.ct_Wp;   // one division per chunk; (i, j) advance with the row
 #pragma unroll 8
     for (int rr = 0; rr < rows_valid; ++rr) {
@@ -471,15 +450,6 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& p, const float* s
       if (h < p.ct_Himg) plane[(size_t)h * p.ct_Wimg + p.ct_pw * j_] = stg[rr * STG_LD + lane];
       if (++j_ == p.ct_Wp) { j_ = 0; ++i_; }
     }
-#else
-#pragma unroll 8
-    for (int rr = 0; rr < rows_valid; ++rr) {
-      const int row = row_base + rr;
-      const int i_ = row / p.ct_Wp, j_ = row - i_ * p.ct_Wp;
-      const int h = p.ct_sh * i_ + p.ct_r0 + rk;
-      if (h < p.ct_Himg) plane[(size_t)h * p.ct_Wimg + p.ct_pw * j_] = stg[rr * STG_LD + lane];
-    }
-#endif
   }
 }
 
@@ -490,13 +460,8 @@ __device__ __forceinline__ void epilogue_resid_load(const EpiParams& p, int row_
   const int rows_valid = min(32, M - row_base);
   const int col = col0 + lane;
   const int colc = (col < N) ? col : 0;
-#if CRA5_TUNE
   (void)rows_valid;
   my_t = tile_tok;   // lane < rows_valid <=> row_base + lane < M, which is how tile_tok was guarded
-#else
-  (void)tile_tok;
-  my_t = (lane < rows_valid) ? p.wm.to_token(row_base + lane) : -1;
-#endif
 #pragma unroll
   for (int rr = 0; rr < 32; ++rr) {
     const int t = __shfl_sync(0xffffffffu, my_t, rr);
@@ -616,12 +581,7 @@ __device__ __forceinline__ void epilogue_f32_prefetch(const EpiParams& p, int ro
           ((((p.ld_bf16 | p.bf16_col0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out_bf16) & 7) == 0)));
   if (!f.on) return;
   const int row = row_base + lane;
-#if CRA5_TUNE
   f.my_t = (KIND == EPI_RESID) ? tile_tok : ((row < M) ? row : -1);   // tile_tok is -1 for rows >= M and for pad rows
-#else
-  (void)tile_tok;
-  f.my_t = (row < M) ? ((KIND == EPI_RESID) ? p.wm.to_token(row) : row) : -1;
-#endif
   const int piece = lane & 7;
   f.bias = (p.bias != nullptr) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + piece * 4))
                                : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -697,6 +657,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int n_tiles = (shp.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = (shp.K + GEMM_BK - 1) / GEMM_BK;
+  const int split_terms = 1 + (shp.a_split ? 1 : 0) + (shp.b_split ? 1 : 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -718,7 +679,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_grid_sync();  // everything above overlaps the previous kernel's tail in the CRA5_PDL build
 
   if (warp == 0) {
     if (lane == 0) {
@@ -737,6 +697,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             pe_j0[g] = t - i * shp.pe_Wp;
             pe_h0[g] = shp.pe_sh * i;
           }
+        }
+        if (split_terms > 1) {
+          // split-bf16 operands (see GemmShape): every k-block is fed once per term, halves selected by the outermost
+          // tensor-map coordinate
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            for (int term = 0; term < split_terms; ++term, ++it) {
+              const int a_half = (shp.a_split && term == 1) ? 1 : 0;
+              const int b_half = (shp.b_split && term == split_terms - 1) ? 1 : 0;
+              const int s = it % GEMM_STAGES;
+              const uint32_t ph = (it / GEMM_STAGES) & 1;
+              mbar_wait(&empty_bar[s], ph ^ 1);
+              uint8_t* sa = smem + s * L::STAGE_BYTES;
+              uint8_t* sb = sa + L::A_BYTES;
+              mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+              const int k0 = kb * GEMM_BK;
+              if (shp.a_mode == A_PLAIN) {
+                if (shp.a_split) tma_load_3d(sa, &tmA, &full_bar[s], k0, m0, a_half);
+                else tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
+              } else if (shp.a_mode == A_PATCH) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                  if (g < pe_nbox) {
+                    if (shp.a_split)
+                      tma_load_4d(sa + g * shp.pe_box_rows * 128, &tmA, &full_bar[s], pe_cs0, pe_j0[g], pe_h0[g] + pe_r, a_half);
+                    else
+                      tma_load_3d(sa + g * shp.pe_box_rows * 128, &tmA, &full_bar[s], pe_cs0, pe_j0[g], pe_h0[g] + pe_r);
+                  }
+              } else {  // A_CONCAT
+                const int kk = (k0 < shp.cc_D) ? k0 : k0 - shp.cc_D;
+                const int mm = (k0 < shp.cc_D) ? m0 : m0 - shp.cc_shift;
+                if (shp.a_split) tma_load_3d(sa, &tmA, &full_bar[s], kk, mm, a_half);
+                else tma_load_2d(sa, &tmA, &full_bar[s], kk, mm);
+              }
+              if (shp.b_split) tma_load_3d(sb, &tmB, &full_bar[s], k0, n0, b_half);
+              else tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
+            }
+            if (shp.a_mode == A_PATCH) {
+              if (++pe_kc == shp.pe_kpr) { pe_kc = 0; pe_cs0 = 0; ++pe_r; } else { pe_cs0 += GEMM_BK; }
+            }
+          }
+          continue;
         }
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const int s = it % GEMM_STAGES;
@@ -770,13 +771,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
       uint32_t it = 0, tl = 0;
+      const int k_iters = k_blocks * split_terms;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tl) {
         const uint32_t as = tl & 1;
         const uint32_t aph = (tl >> 1) & 1;
         mbar_wait(&tempty_bar[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        for (int kb = 0; kb < k_iters; ++kb, ++it) {
           const int s = it % GEMM_STAGES;
           const uint32_t ph = (it / GEMM_STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
@@ -805,7 +807,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = (tile % n_tiles) * BN;
       const uint32_t as = tl & 1;
       const uint32_t aph = (tl >> 1) & 1;
-      int tile_tok = -1;   // CRA5_TUNE: the window map of this lane's accumulator row, computed once per tile
+      int tile_tok = -1;   // the window map of this lane's accumulator row, computed once per tile
       if constexpr (KIND == EPI_RESID) {
         // pull this warp's share of the residual tile (32 rows x BN/2 fp32) towards L2 while the main loop of the tile
         // is still running: the epilogue is otherwise bound by four serial DRAM round trips per tile
@@ -875,13 +877,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (!fast && direct && (((epi.D | epi.hd) & 31) == 0) && ((epi.rows_total & 7) == 0) && ((shp.M & 7) == 0) &&
               ((reinterpret_cast<uintptr_t>(epi.vt) & 15) == 0) &&
               (epi.bias == nullptr || (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0)) {
-#if CRA5_TUNE
             const QkvSplit qs = qkv_split(col0, epi.D, epi.hd);
             const int head = qs.head, d0 = qs.d;
-#else
-            const int within = col0 - 2 * epi.D;
-            const int head = within / epi.hd, d0 = within - head * epi.hd;
-#endif
             epilogue_vt_fast(acc, epi.bias, col0, reinterpret_cast<uint8_t*>(stg),
                              epi.vt + ((size_t)head * epi.hd + d0) * epi.rows_total + row_base, (size_t)epi.rows_total,
                              min(32, shp.M - row_base), lane);
@@ -983,7 +980,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_grid_sync();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1135,13 +1131,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (!fast && direct && (((epi.D | epi.hd) & 31) == 0) && ((epi.rows_total & 7) == 0) && ((shp.M & 7) == 0) &&
               ((reinterpret_cast<uintptr_t>(epi.vt) & 15) == 0) &&
               (epi.bias == nullptr || (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0)) {
-#if CRA5_TUNE
             const QkvSplit qs = qkv_split(col0, epi.D, epi.hd);
             const int head = qs.head, d0 = qs.d;
-#else
-            const int within = col0 - 2 * epi.D;
-            const int head = within / epi.hd, d0 = within - head * epi.hd;
-#endif
             epilogue_vt_fast(acc, epi.bias, col0, reinterpret_cast<uint8_t*>(stg),
                              epi.vt + ((size_t)head * epi.hd + d0) * epi.rows_total + row_base, (size_t)epi.rows_total,
                              min(32, shp.M - row_base), lane);

@@ -1,6 +1,8 @@
 #include "host_util.h"
 
+#include <atomic>
 #include <mutex>
+#include <utility>
 #include <map>
 #include <sstream>
 #include <vector>
@@ -51,13 +53,31 @@ CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, con
 }
 
 int device_sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    CRA5_CUDA(cudaGetDevice(&dev));
-    CRA5_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  constexpr int MAX_DEV = 64;
+  static std::atomic<int> cache[MAX_DEV];   // zero-initialised; 0 = not queried yet
+  int dev = 0;
+  CRA5_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < MAX_DEV) {
+    const int c = cache[dev].load(std::memory_order_relaxed);
+    if (c != 0) return c;
   }
+  int n = 0;
+  CRA5_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  if (dev >= 0 && dev < MAX_DEV) cache[dev].store(n, std::memory_order_relaxed);
   return n;
+}
+
+void ensure_dynamic_smem(const void* func, size_t bytes) {
+  if (bytes <= 48 * 1024) return;   // the default limit needs no attribute
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> done;
+  int dev = 0;
+  CRA5_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = done[std::make_pair(dev, func)];
+  if (bytes <= have) return;
+  CRA5_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  have = bytes;
 }
 
 void require_sm100() {

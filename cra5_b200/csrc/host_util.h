@@ -49,7 +49,14 @@ inline CUtensorMap make_tmap_bf16_2d(const void* base, uint64_t inner, uint64_t 
   return make_tmap_bf16(base, 2, dims, strides, box, true);
 }
 
-int device_sm_count();
+int device_sm_count();   // of the CURRENT device (cached per device ordinal)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (device, function): one process may drive several GPUs (the Python
+// surface takes device=), so the "already configured" state is kept per device ordinal, under a mutex (codec lanes call
+// the launchers from several host threads). Raises the limit only when `bytes` exceeds what was set before.
+void ensure_dynamic_smem(const void* func, size_t bytes);
+template <typename F>
+inline void ensure_dynamic_smem(F* func, size_t bytes) { ensure_dynamic_smem(reinterpret_cast<const void*>(func), bytes); }
 
 // ---- launch accounting + optional per-kernel CUDA-event profiler (bench.py's roofline numbers come from here)
 void count_launch(int n = 1);
@@ -73,30 +80,12 @@ struct TagScope {
 };
 void require_sm100();
 
-// Launch of a kernel on the per-frame chain (LayerNorm -> GEMM -> attention -> GEMM ...). Default build: a plain
-// stream launch. -DCRA5_PDL=1 build: programmatic stream serialisation, i.e. the kernel may become resident while its
-// predecessor drains; such a kernel MUST call pdl_grid_sync() (ptx.cuh) before touching global memory.
-#ifndef CRA5_PDL
-#define CRA5_PDL 0
-#endif
+// Launch of a kernel on the per-frame chain (LayerNorm -> GEMM -> attention -> GEMM ...): a plain stream launch.
+// (Programmatic dependent launch was tried here in round 2: 0.7 % faster and NOT bit-identical on a B200 -- removed.)
 template <typename... KArgs, typename... Args>
 inline void launch_chained(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-#if CRA5_PDL
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  CRA5_CUDA(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
-#else
   kern<<<grid, block, smem, st>>>(args...);
   CRA5_CUDA(cudaGetLastError());
-#endif
 }
 
 }  // namespace cra5

@@ -13,32 +13,39 @@ struct EpiParams;
 int gemm_pick_bn(int N);
 void launch_gemm(cudaStream_t st, int bn, int kind, const CUtensorMap& tmA, const CUtensorMap& tmB,
                  const GemmShape& shp, const EpiParams& epi);
+// split-bf16 operands: element distance from the hi half to the lo half of A / B (0 = that operand is plain bf16)
+struct GemmSplit {
+  size_t a_half = 0, b_half = 0;
+  bool any() const { return a_half != 0 || b_half != 0; }
+};
 void gemm_plain(cudaStream_t st, int kind, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M,
-                int N, int K, const EpiParams& epi);
+                int N, int K, const EpiParams& epi, const GemmSplit& split = GemmSplit());
 void gemm_simt_check(cudaStream_t st, const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb,
                      const float* bias, float* C, int ldc, int M, int N, int K);
 
 // fused softmax(QK^T)V, head_dim 64. attention_tc (attn_tc4.cu) is the persistent ping-pong kernel; segments with
-// index >= q_part_from only need their first q_part_rows query rows (window-pad rows). attention_tc3 (attn_tc.cu) is
-// the previous one-tile-per-CTA kernel, kept for A/B diagnostics (CRA5_ATTN=3).
+// index >= q_part_from only need their first q_part_rows query rows (window-pad rows).
 void attention_tc(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* Vt,
                   __nv_bfloat16* out, int ldo, int heads, int rows_total, int seg_len, int q_part_from = 1 << 30,
                   int q_part_rows = 0);
-void attention_tc3(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* Vt,
-                   __nv_bfloat16* out, int ldo, int heads, int rows_total, int seg_len);
 
 void attention_simt(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* Vt,
                     __nv_bfloat16* out, int ldo, int heads, int hd, int rows_total, int seg_len);
 
 // elementwise.cu
 struct WinMap;
+// (every A-operand producer takes an optional `lo` output for the split-bf16 precision mode: v ~ bf16 hi + bf16 lo)
 void frame_to_patches(cudaStream_t st, const float* x, __nv_bfloat16* out, const float* mean, const float* std_,
-                      int C, int H, int W, int Wp, int pw, int cs_pad);
+                      int C, int H, int W, int Wp, int pw, int cs_pad, __nv_bfloat16* out_lo = nullptr);
 void layernorm_bf16(cudaStream_t st, const float* x, const float* gamma, const float* beta, float eps,
-                    __nv_bfloat16* out, int rows_out, int D, const WinMap& wm);
-void im2col_latent(cudaStream_t st, const float* y, __nv_bfloat16* A, int C, int Hy, int Wy, int p1, int p2, int lda);
-void transpose_cast(cudaStream_t st, const float* in, __nv_bfloat16* out, int C, int T, int ldo);
+                    __nv_bfloat16* out, int rows_out, int D, const WinMap& wm, __nv_bfloat16* out_lo = nullptr);
+void im2col_latent(cudaStream_t st, const float* y, __nv_bfloat16* A, int C, int Hy, int Wy, int p1, int p2, int lda,
+                   __nv_bfloat16* A_lo = nullptr);
+void transpose_cast(cudaStream_t st, const float* in, __nv_bfloat16* out, int C, int T, int ldo,
+                    __nv_bfloat16* out_lo = nullptr);
 void cast_bf16(cudaStream_t st, const float* in, __nv_bfloat16* out, size_t n);
+void split_rows(cudaStream_t st, const float* in, int ld_in, int rows, int cols, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                int ld_out, bool gelu);
 void affine_channels(cudaStream_t st, const float* in, float* out, const float* a, const float* b, size_t hw, int C,
                      int forward);
 

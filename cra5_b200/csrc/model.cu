@@ -2,6 +2,7 @@
 #include "model.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -117,6 +118,7 @@ Model::Model(const cra5_config& c) : cfg_(c) {
 Model::~Model() {
   delete coder_;
   cudaFree(ws_);
+  cudaFree(ws2_);
   cudaFreeHost(host_y_);
   cudaFreeHost(host_z_);
 }
@@ -126,6 +128,70 @@ void* Model::alloc(size_t bytes) {
   ws_used_ += align_up(bytes, 256);
   CRA5_CHECK(ws_used_ <= ws_bytes_, ERR_INTERNAL, "workspace sizing");
   return ws_ + off;
+}
+
+void* Model::alloc2(size_t bytes) {
+  const size_t off = ws2_used_;
+  ws2_used_ += align_up(bytes, 256);
+  CRA5_CHECK(ws2_used_ <= ws2_bytes_, ERR_INTERNAL, "split workspace sizing");
+  return ws2_ + off;
+}
+
+// Precision levels (see model.h). The split-bf16 mode carries every fp32 GEMM operand as hi = bf16(v), lo = bf16(v - hi)
+// and accumulates A_hi B_hi + A_lo B_hi + A_hi B_lo in the same fp32 TMEM accumulator (gemm_tc.cuh, GemmShape::a_split):
+// ~16 mantissa bits per operand instead of 8, on the same tcgen05 pipeline, at 3x the tensor work of the covered sites.
+// Attention keeps bf16 Q, K, V and P at every level (the reference's own GPU path runs it in fp16, vit_nlc.py:105-110).
+void Model::set_precision(int level) {
+  CRA5_CHECK(level >= 0 && level <= 3, ERR_INVALID, "precision level must be 0 (bf16), 1 (tail), 2 (encoder) or 3 (all)");
+  if (level > 0 && ws2_ == nullptr) {
+    const cra5_config& c = cfg_;
+    const int D = c.dim, Dh = c.hyper_dim, mlp = c.mlp_ratio, lat = c.latent_chans, zc = c.z_chans;
+    const int hidden = std::max(1, (int)sqrt((double)(Dh / zc))) * zc;
+    const size_t kh_max = std::max<size_t>({(size_t)lat * c.hyper_patch_h * c.hyper_patch_w, (size_t)Dh, (size_t)hidden,
+                                            (size_t)zc});
+    const size_t hw = std::max<size_t>((size_t)mlp * Dh, (size_t)hidden);   // widest hyper MLP activation
+    main_.a_half = (size_t)Tpad * D;
+    main_.h_half = (size_t)T * mlp * D;
+    hyper_.a_half = (size_t)Th * std::max<size_t>(Dh, kh_max);
+    hyper_.h_half = (size_t)Th * hw;
+    cat_half_ = (size_t)T * 2 * D;
+    patches_half_ = (size_t)c.img_h * Wg * cs_pad;
+    ytok_half_ = (size_t)T * lat;
+    ztok_half_ = (size_t)Th * zc;
+    ah_half_ = (size_t)Th * kh_max;
+    size_t total = 4096;
+    for (size_t half : {main_.a_half, main_.h_half, hyper_.a_half, hyper_.h_half, cat_half_, patches_half_, ytok_half_,
+                        ztok_half_, ah_half_})
+      total += align_up(2 * half * 2, 256);
+    total += align_up((size_t)T * mlp * D * 4, 256) + align_up((size_t)Th * hw * 4, 256);
+    CRA5_CUDA(cudaMalloc(&ws2_, total));
+    ws2_bytes_ = total;
+    CRA5_CUDA(cudaMemset(ws2_, 0, total));
+    CRA5_CUDA(cudaDeviceSynchronize());   // the memset runs on the legacy stream; callers use their own streams
+    main_.a2 = (__nv_bfloat16*)alloc2(2 * main_.a_half * 2);
+    main_.h2 = (__nv_bfloat16*)alloc2(2 * main_.h_half * 2);
+    main_.f32 = (float*)alloc2((size_t)T * mlp * D * 4);
+    hyper_.a2 = (__nv_bfloat16*)alloc2(2 * hyper_.a_half * 2);
+    hyper_.h2 = (__nv_bfloat16*)alloc2(2 * hyper_.h_half * 2);
+    hyper_.f32 = (float*)alloc2((size_t)Th * hw * 4);
+    cat2_ = (__nv_bfloat16*)alloc2(2 * cat_half_ * 2);
+    patches2_ = (__nv_bfloat16*)alloc2(2 * patches_half_ * 2);
+    ytok2_ = (__nv_bfloat16*)alloc2(2 * ytok_half_ * 2);
+    ztok2_ = (__nv_bfloat16*)alloc2(2 * ztok_half_ * 2);
+    ah2_ = (__nv_bfloat16*)alloc2(2 * ah_half_ * 2);
+  }
+  precision_ = level;
+  finalized_ = false;   // block weights pick up their ".x3" copies
+}
+
+const __nv_bfloat16* Model::need_x3(const std::string& name, int64_t numel) const {
+  auto it = tensors_.find(name + ".x3");
+  CRA5_CHECK(it != tensors_.end(), ERR_STATE,
+             "precision level " + std::to_string(precision_) + " needs the split weight copy '" + name +
+                 ".x3' (VAEformer.set_precision uploads it)");
+  CRA5_CHECK(it->second.dtype == CRA5_DT_BF16 && it->second.numel == 2 * numel, ERR_INVALID,
+             "split weight '" + name + ".x3' must be bf16 [2][N][K]");
+  return (const __nv_bfloat16*)it->second.ptr;
 }
 
 void Model::set_tensor(const std::string& name, const void* ptr, int dtype, int64_t numel) {
@@ -173,6 +239,17 @@ BlockWeights Model::block_weights(const std::string& p, int D, int mlp) const {
   w.proj_w = b(".attn.proj.weight", (int64_t)D * D); w.proj_b = f(".attn.proj.bias", D);
   w.fc1_w = b(".mlp.fc1.weight", (int64_t)mlp * D * D); w.fc1_b = f(".mlp.fc1.bias", mlp * D);
   w.fc2_w = b(".mlp.fc2.weight", (int64_t)mlp * D * D); w.fc2_b = f(".mlp.fc2.bias", D);
+  auto x3 = [&](const std::string& n, int64_t ne) -> const __nv_bfloat16* {
+    auto it = tensors_.find(p + n + ".x3");
+    if (it == tensors_.end()) return nullptr;
+    CRA5_CHECK(it->second.dtype == CRA5_DT_BF16 && it->second.numel == 2 * ne, ERR_INVALID,
+               "split weight '" + p + n + ".x3' must be bf16 [2][N][K]");
+    return (const __nv_bfloat16*)it->second.ptr;
+  };
+  w.qkv_w3 = x3(".attn.qkv.weight", (int64_t)3 * D * D);
+  w.proj_w3 = x3(".attn.proj.weight", (int64_t)D * D);
+  w.fc1_w3 = x3(".mlp.fc1.weight", (int64_t)mlp * D * D);
+  w.fc2_w3 = x3(".mlp.fc2.weight", (int64_t)mlp * D * D);
   return w;
 }
 
@@ -198,19 +275,23 @@ WinMap Model::make_winmap(int wh, int ww) const {
   m.H = Hg; m.W = Wg; m.wh = wh; m.ww = ww;
   m.nWr = ceil_div(Hg, wh);
   m.nWc = ceil_div(Wg, ww);
-  m.finish();   // CRA5_TUNE: multiply-shift constants for the four divisions of to_token()
+  m.finish();   // multiply-shift constants for the four divisions of to_token()
   return m;
 }
 
 // Block.forward (vit_nlc.py:282-287): x_out = x_in + attn(LN1(x_in)); x_out += mlp(LN2(x_out))
 void Model::run_block(cudaStream_t st, const BlockWeights& w, const TrunkBuffers& tb, const float* x_in, float* x_out,
                       int T_, int D, int heads, int mlp, int win_h, int win_w, __nv_bfloat16* cat_out, int cat_col0,
-                      int cat_ld) {
+                      int cat_ld, bool precise) {
   const int hd_ = D / heads;
   WinMap wm = (T_ == T) ? make_winmap(win_h, win_w) : WinMap{};
   const int rows = wm.enabled ? wm.nWr * wm.nWc * wm.wh * wm.ww : T_;
   const int seg = wm.enabled ? wm.wh * wm.ww : T_;
-  layernorm_bf16(st, x_in, w.ln1_g, w.ln1_b, cfg_.ln_eps, tb.a, rows, D, wm);
+  if (precise) CRA5_CHECK(w.has_split() && tb.a2 != nullptr, ERR_STATE, "split weights / workspace missing for a precise block");
+  // split-bf16 mode: LayerNorm emits hi | lo halves, the GEMMs run three (proj: two) terms per k-block; the GELU and the
+  // bf16 casts that the default path fuses into GEMM epilogues run as one extra pass (split_rows) over fp32 outputs
+  __nv_bfloat16* ln_out = precise ? tb.a2 : tb.a;
+  layernorm_bf16(st, x_in, w.ln1_g, w.ln1_b, cfg_.ln_eps, ln_out, rows, D, wm, precise ? tb.a2 + tb.a_half : nullptr);
   {
     EpiParams e{};
     e.bias = w.qkv_b;
@@ -218,7 +299,10 @@ void Model::run_block(cudaStream_t st, const BlockWeights& w, const TrunkBuffers
     e.D = D; e.hd = hd_; e.rows_total = rows;
     e.qscale = 1.0f / sqrtf((float)hd_);
     TagScope tag_("qkv");
-    gemm_plain(st, EPI_QKV, tb.a, D, w.qkv_w, D, rows, 3 * D, D, e);
+    if (precise)
+      gemm_plain(st, EPI_QKV, ln_out, D, w.qkv_w3, D, rows, 3 * D, D, e, GemmSplit{tb.a_half, (size_t)3 * D * D});
+    else
+      gemm_plain(st, EPI_QKV, tb.a, D, w.qkv_w, D, rows, 3 * D, D, e);
   }
   if (hd_ == 64) {
     // bottom-row windows of a vertically padded grid: their trailing rows are pad tokens (vit_nlc.py:229-237). They
@@ -237,23 +321,55 @@ void Model::run_block(cudaStream_t st, const BlockWeights& w, const TrunkBuffers
     e.bias = w.proj_b;
     e.resid = x_in; e.out_f32 = x_out; e.ldo = D; e.wm = wm;
     TagScope tag_("proj");
-    gemm_plain(st, EPI_RESID, tb.o, D, w.proj_w, D, rows, D, D, e);
+    if (precise)   // the attention output is bf16 by construction: only the weight is split
+      gemm_plain(st, EPI_RESID, tb.o, D, w.proj_w3, D, rows, D, D, e, GemmSplit{0, (size_t)D * D});
+    else
+      gemm_plain(st, EPI_RESID, tb.o, D, w.proj_w, D, rows, D, D, e);
   }
-  layernorm_bf16(st, x_out, w.ln2_g, w.ln2_b, cfg_.ln_eps, tb.a, T_, D, WinMap{});
-  {
-    EpiParams e{};
-    e.bias = w.fc1_b;
-    e.out_bf16 = tb.h; e.ldo = mlp * D;
-    TagScope tag_("fc1");
-    gemm_plain(st, EPI_GELU_BF16, tb.a, D, w.fc1_w, D, T_, mlp * D, D, e);
+  layernorm_bf16(st, x_out, w.ln2_g, w.ln2_b, cfg_.ln_eps, ln_out, T_, D, WinMap{}, precise ? tb.a2 + tb.a_half : nullptr);
+  if (precise) {
+    {
+      EpiParams e{};
+      e.bias = w.fc1_b;
+      e.out_f32 = tb.f32; e.ldo = mlp * D;
+      TagScope tag_("fc1");
+      gemm_plain(st, EPI_F32, ln_out, D, w.fc1_w3, D, T_, mlp * D, D, e, GemmSplit{tb.a_half, (size_t)mlp * D * D});
+    }
+    split_rows(st, tb.f32, mlp * D, T_, mlp * D, tb.h2, tb.h2 + tb.h_half, mlp * D, true);
+    {
+      EpiParams e{};
+      e.bias = w.fc2_b;
+      e.resid = x_out; e.out_f32 = x_out; e.ldo = D;
+      TagScope tag_("fc2");
+      gemm_plain(st, EPI_RESID, tb.h2, mlp * D, w.fc2_w3, mlp * D, T_, D, mlp * D, e,
+                 GemmSplit{tb.h_half, (size_t)mlp * D * D});
+    }
+    if (cat_out != nullptr)   // the encoder's mean || logvar concat feeds quant_conv: cat_out = hi half of cat2_
+      split_rows(st, x_out, D, T_, D, cat_out + cat_col0, cat_out + cat_half_ + cat_col0, cat_ld, false);
+  } else {
+    {
+      EpiParams e{};
+      e.bias = w.fc1_b;
+      e.out_bf16 = tb.h; e.ldo = mlp * D;
+      TagScope tag_("fc1");
+      gemm_plain(st, EPI_GELU_BF16, tb.a, D, w.fc1_w, D, T_, mlp * D, D, e);
+    }
+    {
+      EpiParams e{};
+      e.bias = w.fc2_b;
+      e.resid = x_out; e.out_f32 = x_out; e.ldo = D;
+      e.out_bf16 = cat_out; e.bf16_col0 = cat_col0; e.ld_bf16 = cat_ld;
+      TagScope tag_("fc2");
+      gemm_plain(st, EPI_RESID, tb.h, mlp * D, w.fc2_w, mlp * D, T_, D, mlp * D, e);
+    }
   }
-  {
-    EpiParams e{};
-    e.bias = w.fc2_b;
-    e.resid = x_out; e.out_f32 = x_out; e.ldo = D;
-    e.out_bf16 = cat_out; e.bf16_col0 = cat_col0; e.ld_bf16 = cat_ld;
-    TagScope tag_("fc2");
-    gemm_plain(st, EPI_RESID, tb.h, mlp * D, w.fc2_w, mlp * D, T_, D, mlp * D, e);
+  if (T_ == T) {   // diagnostics: operand buffers of the last trunk block that ran
+    taps_["blk.q"] = TensorRef{tb.q, CRA5_DT_BF16, (int64_t)rows * D};
+    taps_["blk.k"] = TensorRef{tb.k, CRA5_DT_BF16, (int64_t)rows * D};
+    taps_["blk.vt"] = TensorRef{tb.vt, CRA5_DT_BF16, (int64_t)rows * D};
+    taps_["blk.o"] = TensorRef{tb.o, CRA5_DT_BF16, (int64_t)rows * D};
+    taps_["blk.a"] = TensorRef{tb.a, CRA5_DT_BF16, (int64_t)T_ * D};
+    taps_["blk.h"] = TensorRef{tb.h, CRA5_DT_BF16, (int64_t)T_ * mlp * D};
   }
 }
 
@@ -271,20 +387,37 @@ void Model::encode_to_latent(const float* x, float* y, const float* mean, const 
   const cra5_config& c = cfg_;
   const int D = c.dim, CS = c.in_chans * c.patch_w;
   CRA5_CHECK((mean == nullptr) == (std_ == nullptr), ERR_INVALID, "mean and std must be given together");
-  frame_to_patches(st, x, patches_, mean, std_, c.in_chans, c.img_h, c.img_w, Wg, c.patch_w, cs_pad);
+  const bool p_embed = precision_ >= 2;
+  __nv_bfloat16* patches = p_embed ? patches2_ : patches_;
+  frame_to_patches(st, x, patches, mean, std_, c.in_chans, c.img_h, c.img_w, Wg, c.patch_w, cs_pad,
+                   p_embed ? patches2_ + patches_half_ : nullptr);
   {
     // implicit-GEMM patch embedding: K ordered (kernel row r, channel, column s), zero padded per r to kpr*64
     const int Kp = c.patch_h * kpr * GEMM_BK;
-    const __nv_bfloat16* Wpe = (const __nv_bfloat16*)need("g_a.patch_embed.proj.weight", CRA5_DT_BF16, (int64_t)D * Kp);
-    uint64_t dims[3] = {(uint64_t)CS, (uint64_t)Wg, (uint64_t)c.img_h};
-    uint64_t strides[2] = {(uint64_t)cs_pad * 2, (uint64_t)Wg * cs_pad * 2};
-    uint32_t box[3] = {GEMM_BK, (uint32_t)box_rows, 1};
-    CUtensorMap tmA = make_tmap_bf16(patches_, 3, dims, strides, box, true);
     const int bn = gemm_pick_bn(D);
-    CUtensorMap tmB = make_tmap_bf16_2d(Wpe, (uint64_t)Kp, (uint64_t)D, (uint64_t)Kp * 2, GEMM_BK, bn);
+    CUtensorMap tmA, tmB;
+    if (p_embed) {   // split-bf16: one more (outermost) coordinate selects the hi / lo half of both operands
+      const __nv_bfloat16* Wpe = need_x3("g_a.patch_embed.proj.weight", (int64_t)D * Kp);
+      uint64_t dims[4] = {(uint64_t)CS, (uint64_t)Wg, (uint64_t)c.img_h, 2};
+      uint64_t strides[3] = {(uint64_t)cs_pad * 2, (uint64_t)Wg * cs_pad * 2, (uint64_t)patches_half_ * 2};
+      uint32_t box[4] = {GEMM_BK, (uint32_t)box_rows, 1, 1};
+      tmA = make_tmap_bf16(patches, 4, dims, strides, box, true);
+      uint64_t bdims[3] = {(uint64_t)Kp, (uint64_t)D, 2};
+      uint64_t bstrides[2] = {(uint64_t)Kp * 2, (uint64_t)D * Kp * 2};
+      uint32_t bbox[3] = {GEMM_BK, (uint32_t)bn, 1};
+      tmB = make_tmap_bf16(Wpe, 3, bdims, bstrides, bbox, true);
+    } else {
+      const __nv_bfloat16* Wpe = (const __nv_bfloat16*)need("g_a.patch_embed.proj.weight", CRA5_DT_BF16, (int64_t)D * Kp);
+      uint64_t dims[3] = {(uint64_t)CS, (uint64_t)Wg, (uint64_t)c.img_h};
+      uint64_t strides[2] = {(uint64_t)cs_pad * 2, (uint64_t)Wg * cs_pad * 2};
+      uint32_t box[3] = {GEMM_BK, (uint32_t)box_rows, 1};
+      tmA = make_tmap_bf16(patches, 3, dims, strides, box, true);
+      tmB = make_tmap_bf16_2d(Wpe, (uint64_t)Kp, (uint64_t)D, (uint64_t)Kp * 2, GEMM_BK, bn);
+    }
     GemmShape shp{};
     shp.M = T; shp.N = D; shp.K = Kp; shp.a_mode = A_PATCH;
     shp.pe_kpr = kpr; shp.pe_box_rows = box_rows; shp.pe_Wp = Wg; shp.pe_sh = c.stride_h;
+    shp.a_split = shp.b_split = p_embed ? 1 : 0;
     EpiParams e{};
     e.bias = (const float*)need("g_a.patch_embed.proj.bias", CRA5_DT_F32, D);
     e.add = (const float*)need("g_a.pos_embed", CRA5_DT_F32, (int64_t)T * D);
@@ -296,14 +429,18 @@ void Model::encode_to_latent(const float* x, float* y, const float* mean, const 
   taps_["tokens"] = TensorRef{main_.x, CRA5_DT_F32, (int64_t)T * D};
   const int n = (int)ga_.size();
   int wh, ww;
+  static const int debug_stop = [] { const char* e = getenv("CRA5_DEBUG_STOP_AFTER"); return e ? atoi(e) : -1; }();
   for (int i = 0; i < n - 2; ++i) {
+    if (debug_stop >= 0 && i >= debug_stop) return;   // diagnostics: leave the residual stream of block i-1 in "tokens"
     window_of(c, i, &wh, &ww);
-    run_block(st, ga_[i], main_, main_.x, main_.x, T, D, c.num_heads, c.mlp_ratio, wh, ww, nullptr, 0, 0);
+    run_block(st, ga_[i], main_, main_.x, main_.x, T, D, c.num_heads, c.mlp_ratio, wh, ww, nullptr, 0, 0, precision_ >= 2);
   }
   // the last two blocks share their input and window setting; outputs are concatenated (vit_nlc.py:467-472)
+  const bool tail = precision_ >= 1;
+  __nv_bfloat16* cat = tail ? cat2_ : cat_;
   window_of(c, n - 2, &wh, &ww);
-  run_block(st, ga_[n - 2], main_, main_.x, x1_, T, D, c.num_heads, c.mlp_ratio, wh, ww, cat_, 0, 2 * D);
-  run_block(st, ga_[n - 1], main_, main_.x, x2_, T, D, c.num_heads, c.mlp_ratio, wh, ww, cat_, D, 2 * D);
+  run_block(st, ga_[n - 2], main_, main_.x, x1_, T, D, c.num_heads, c.mlp_ratio, wh, ww, cat, 0, 2 * D, tail);
+  run_block(st, ga_[n - 1], main_, main_.x, x2_, T, D, c.num_heads, c.mlp_ratio, wh, ww, cat, D, 2 * D, tail);
   {
     // quant_conv 1x1, only the `mean` half of the moments is ever used (distributions.py:32,71-72)
     const int lat = c.latent_chans;
@@ -311,8 +448,12 @@ void Model::encode_to_latent(const float* x, float* y, const float* mean, const 
     e.bias = (const float*)need("quant_conv.bias", CRA5_DT_F32, lat);
     e.out_f32 = y; e.ldo = T;
     TagScope tag_("quant_conv");
-    gemm_plain(st, EPI_T_F32, cat_, 2 * D, (const __nv_bfloat16*)need("quant_conv.weight", CRA5_DT_BF16, (int64_t)lat * 2 * D),
-               2 * D, T, lat, 2 * D, e);
+    if (tail)
+      gemm_plain(st, EPI_T_F32, cat, 2 * D, need_x3("quant_conv.weight", (int64_t)lat * 2 * D), 2 * D, T, lat, 2 * D, e,
+                 GemmSplit{cat_half_, (size_t)lat * 2 * D});
+    else
+      gemm_plain(st, EPI_T_F32, cat_, 2 * D, (const __nv_bfloat16*)need("quant_conv.weight", CRA5_DT_BF16, (int64_t)lat * 2 * D),
+                 2 * D, T, lat, 2 * D, e);
   }
   taps_["y"] = TensorRef{y, CRA5_DT_F32, (int64_t)c.latent_chans * T};
 }
@@ -324,7 +465,9 @@ void Model::run_h_a(cudaStream_t st, const float* y) {
   const int Dh = c.hyper_dim, lat = c.latent_chans, zc = c.z_chans;
   const int Kc = lat * c.hyper_patch_h * c.hyper_patch_w;
   const int hidden = std::max(1, (int)sqrt((double)(Dh / zc))) * zc;
-  im2col_latent(st, y, ah_, lat, Hg, Wg, c.hyper_patch_h, c.hyper_patch_w, Kc);
+  const bool pr = precision_ >= 1;   // the hyperprior decides the scale indexes and means: split-bf16 from level 1 on
+  __nv_bfloat16* ah = pr ? ah2_ : ah_;
+  im2col_latent(st, y, ah, lat, Hg, Wg, c.hyper_patch_h, c.hyper_patch_w, Kc, pr ? ah2_ + ah_half_ : nullptr);
   {
     EpiParams e{};
     e.bias = (const float*)need("h_a.patch_embed.proj.bias", CRA5_DT_F32, Dh);
@@ -332,28 +475,53 @@ void Model::run_h_a(cudaStream_t st, const float* y) {
     e.lda = Dh;
     e.out_f32 = hyper_.x; e.ldo = Dh;
     TagScope tag_("h_a.patch_embed");
-    gemm_plain(st, EPI_F32, ah_, Kc, (const __nv_bfloat16*)need("h_a.patch_embed.proj.weight", CRA5_DT_BF16, (int64_t)Dh * Kc),
-               Kc, Th, Dh, Kc, e);
+    if (pr)
+      gemm_plain(st, EPI_F32, ah, Kc, need_x3("h_a.patch_embed.proj.weight", (int64_t)Dh * Kc), Kc, Th, Dh, Kc, e,
+                 GemmSplit{ah_half_, (size_t)Dh * Kc});
+    else
+      gemm_plain(st, EPI_F32, ah_, Kc, (const __nv_bfloat16*)need("h_a.patch_embed.proj.weight", CRA5_DT_BF16, (int64_t)Dh * Kc),
+                 Kc, Th, Dh, Kc, e);
   }
   for (size_t i = 0; i < ha_.size(); ++i)
-    run_block(st, ha_[i], hyper_, hyper_.x, hyper_.x, Th, Dh, c.hyper_heads, c.mlp_ratio, 0, 0, nullptr, 0, 0);
+    run_block(st, ha_[i], hyper_, hyper_.x, hyper_.x, Th, Dh, c.hyper_heads, c.mlp_ratio, 0, 0, nullptr, 0, 0, pr);
   // quan_mlp (vit_nlc.py:544-546): fc1 -> GELU -> fc2, no norm in front
-  cast_bf16(st, hyper_.x, hyper_.a, (size_t)Th * Dh);
-  {
-    EpiParams e{};
-    e.bias = (const float*)need("h_a.quan_mlp.fc1.bias", CRA5_DT_F32, hidden);
-    e.out_bf16 = hyper_.h; e.ldo = hidden;
-    TagScope tag_("h_a.quan_fc1");
-    gemm_plain(st, EPI_GELU_BF16, hyper_.a, Dh, (const __nv_bfloat16*)need("h_a.quan_mlp.fc1.weight", CRA5_DT_BF16, (int64_t)hidden * Dh),
-               Dh, Th, hidden, Dh, e);
-  }
-  {
-    EpiParams e{};
-    e.bias = (const float*)need("h_a.quan_mlp.fc2.bias", CRA5_DT_F32, zc);
-    e.out_f32 = z_; e.ldo = Th;
-    TagScope tag_("h_a.quan_fc2");
-    gemm_plain(st, EPI_T_F32, hyper_.h, hidden, (const __nv_bfloat16*)need("h_a.quan_mlp.fc2.weight", CRA5_DT_BF16, (int64_t)zc * hidden),
-               hidden, Th, zc, hidden, e);
+  if (pr) {
+    split_rows(st, hyper_.x, Dh, Th, Dh, hyper_.a2, hyper_.a2 + hyper_.a_half, Dh, false);
+    {
+      EpiParams e{};
+      e.bias = (const float*)need("h_a.quan_mlp.fc1.bias", CRA5_DT_F32, hidden);
+      e.out_f32 = hyper_.f32; e.ldo = hidden;
+      TagScope tag_("h_a.quan_fc1");
+      gemm_plain(st, EPI_F32, hyper_.a2, Dh, need_x3("h_a.quan_mlp.fc1.weight", (int64_t)hidden * Dh), Dh, Th, hidden, Dh, e,
+                 GemmSplit{hyper_.a_half, (size_t)hidden * Dh});
+    }
+    split_rows(st, hyper_.f32, hidden, Th, hidden, hyper_.h2, hyper_.h2 + hyper_.h_half, hidden, true);
+    {
+      EpiParams e{};
+      e.bias = (const float*)need("h_a.quan_mlp.fc2.bias", CRA5_DT_F32, zc);
+      e.out_f32 = z_; e.ldo = Th;
+      TagScope tag_("h_a.quan_fc2");
+      gemm_plain(st, EPI_T_F32, hyper_.h2, hidden, need_x3("h_a.quan_mlp.fc2.weight", (int64_t)zc * hidden), hidden, Th, zc,
+                 hidden, e, GemmSplit{hyper_.h_half, (size_t)zc * hidden});
+    }
+  } else {
+    cast_bf16(st, hyper_.x, hyper_.a, (size_t)Th * Dh);
+    {
+      EpiParams e{};
+      e.bias = (const float*)need("h_a.quan_mlp.fc1.bias", CRA5_DT_F32, hidden);
+      e.out_bf16 = hyper_.h; e.ldo = hidden;
+      TagScope tag_("h_a.quan_fc1");
+      gemm_plain(st, EPI_GELU_BF16, hyper_.a, Dh, (const __nv_bfloat16*)need("h_a.quan_mlp.fc1.weight", CRA5_DT_BF16, (int64_t)hidden * Dh),
+                 Dh, Th, hidden, Dh, e);
+    }
+    {
+      EpiParams e{};
+      e.bias = (const float*)need("h_a.quan_mlp.fc2.bias", CRA5_DT_F32, zc);
+      e.out_f32 = z_; e.ldo = Th;
+      TagScope tag_("h_a.quan_fc2");
+      gemm_plain(st, EPI_T_F32, hyper_.h, hidden, (const __nv_bfloat16*)need("h_a.quan_mlp.fc2.weight", CRA5_DT_BF16, (int64_t)zc * hidden),
+                 hidden, Th, zc, hidden, e);
+    }
   }
   taps_["z"] = TensorRef{z_, CRA5_DT_F32, (int64_t)zc * Th};
 }
@@ -364,36 +532,64 @@ void Model::run_h_s(cudaStream_t st, const float* z_hat) {
   const cra5_config& c = cfg_;
   const int Dh = c.hyper_dim, lat = c.latent_chans, zc = c.z_chans;
   const int hidden = std::max(1, (int)sqrt((double)(Dh / zc))) * zc;
-  transpose_cast(st, z_hat, ztok_, zc, Th, zc);
-  {
-    EpiParams e{};
-    e.bias = (const float*)need("h_s.post_quan_mlp.fc1.bias", CRA5_DT_F32, hidden);
-    e.out_bf16 = hyper_.h; e.ldo = hidden;
-    TagScope tag_("h_s.post_fc1");
-    gemm_plain(st, EPI_GELU_BF16, ztok_, zc, (const __nv_bfloat16*)need("h_s.post_quan_mlp.fc1.weight", CRA5_DT_BF16, (int64_t)hidden * zc),
-               zc, Th, hidden, zc, e);
-  }
-  {
-    EpiParams e{};
-    e.bias = (const float*)need("h_s.post_quan_mlp.fc2.bias", CRA5_DT_F32, Dh);
-    e.out_f32 = hyper_.x; e.ldo = Dh;
-    TagScope tag_("h_s.post_fc2");
-    gemm_plain(st, EPI_F32, hyper_.h, hidden, (const __nv_bfloat16*)need("h_s.post_quan_mlp.fc2.weight", CRA5_DT_BF16, (int64_t)Dh * hidden),
-               hidden, Th, Dh, hidden, e);
+  const bool pr = precision_ >= 1;
+  const int Nf = 2 * lat * c.hyper_patch_h * c.hyper_patch_w;
+  if (pr) {
+    transpose_cast(st, z_hat, ztok2_, zc, Th, zc, ztok2_ + ztok_half_);
+    {
+      EpiParams e{};
+      e.bias = (const float*)need("h_s.post_quan_mlp.fc1.bias", CRA5_DT_F32, hidden);
+      e.out_f32 = hyper_.f32; e.ldo = hidden;
+      TagScope tag_("h_s.post_fc1");
+      gemm_plain(st, EPI_F32, ztok2_, zc, need_x3("h_s.post_quan_mlp.fc1.weight", (int64_t)hidden * zc), zc, Th, hidden, zc, e,
+                 GemmSplit{ztok_half_, (size_t)hidden * zc});
+    }
+    split_rows(st, hyper_.f32, hidden, Th, hidden, hyper_.h2, hyper_.h2 + hyper_.h_half, hidden, true);
+    {
+      EpiParams e{};
+      e.bias = (const float*)need("h_s.post_quan_mlp.fc2.bias", CRA5_DT_F32, Dh);
+      e.out_f32 = hyper_.x; e.ldo = Dh;
+      TagScope tag_("h_s.post_fc2");
+      gemm_plain(st, EPI_F32, hyper_.h2, hidden, need_x3("h_s.post_quan_mlp.fc2.weight", (int64_t)Dh * hidden), hidden, Th, Dh,
+                 hidden, e, GemmSplit{hyper_.h_half, (size_t)Dh * hidden});
+    }
+  } else {
+    transpose_cast(st, z_hat, ztok_, zc, Th, zc);
+    {
+      EpiParams e{};
+      e.bias = (const float*)need("h_s.post_quan_mlp.fc1.bias", CRA5_DT_F32, hidden);
+      e.out_bf16 = hyper_.h; e.ldo = hidden;
+      TagScope tag_("h_s.post_fc1");
+      gemm_plain(st, EPI_GELU_BF16, ztok_, zc, (const __nv_bfloat16*)need("h_s.post_quan_mlp.fc1.weight", CRA5_DT_BF16, (int64_t)hidden * zc),
+                 zc, Th, hidden, zc, e);
+    }
+    {
+      EpiParams e{};
+      e.bias = (const float*)need("h_s.post_quan_mlp.fc2.bias", CRA5_DT_F32, Dh);
+      e.out_f32 = hyper_.x; e.ldo = Dh;
+      TagScope tag_("h_s.post_fc2");
+      gemm_plain(st, EPI_F32, hyper_.h, hidden, (const __nv_bfloat16*)need("h_s.post_quan_mlp.fc2.weight", CRA5_DT_BF16, (int64_t)Dh * hidden),
+                 hidden, Th, Dh, hidden, e);
+    }
   }
   for (size_t i = 0; i < hs_.size(); ++i)
-    run_block(st, hs_[i], hyper_, hyper_.x, hyper_.x, Th, Dh, c.hyper_heads, c.mlp_ratio, 0, 0, nullptr, 0, 0);
+    run_block(st, hs_[i], hyper_, hyper_.x, hyper_.x, Th, Dh, c.hyper_heads, c.mlp_ratio, 0, 0, nullptr, 0, 0, pr);
+  __nv_bfloat16* fin = pr ? hyper_.a2 : hyper_.a;
   layernorm_bf16(st, hyper_.x, (const float*)need("h_s.norm.weight", CRA5_DT_F32, Dh),
-                 (const float*)need("h_s.norm.bias", CRA5_DT_F32, Dh), c.ln_eps, hyper_.a, Th, Dh, WinMap{});
+                 (const float*)need("h_s.norm.bias", CRA5_DT_F32, Dh), c.ln_eps, fin, Th, Dh, WinMap{},
+                 pr ? hyper_.a2 + hyper_.a_half : nullptr);
   {
     // Linear(Dh, 2*latent*p1*p2, bias=False) + rearrange '(p1 p2 c)' (vit_nlc.py:741, 671-680)
-    const int Nf = 2 * lat * c.hyper_patch_h * c.hyper_patch_w;
     EpiParams e{};
     e.out_f32 = params_; e.ldo = T;
     e.ps_P1 = c.hyper_patch_h; e.ps_P2 = c.hyper_patch_w; e.ps_C = 2 * lat; e.ps_Wh = Wh;
     TagScope tag_("h_s.final");
-    gemm_plain(st, EPI_PIXSHUF, hyper_.a, Dh, (const __nv_bfloat16*)need("h_s.final.weight", CRA5_DT_BF16, (int64_t)Nf * Dh), Dh, Th,
-               Nf, Dh, e);
+    if (pr)
+      gemm_plain(st, EPI_PIXSHUF, fin, Dh, need_x3("h_s.final.weight", (int64_t)Nf * Dh), Dh, Th, Nf, Dh, e,
+                 GemmSplit{hyper_.a_half, (size_t)Nf * Dh});
+    else
+      gemm_plain(st, EPI_PIXSHUF, hyper_.a, Dh, (const __nv_bfloat16*)need("h_s.final.weight", CRA5_DT_BF16, (int64_t)Nf * Dh), Dh, Th,
+                 Nf, Dh, e);
   }
   taps_["scales"] = TensorRef{params_, CRA5_DT_F32, (int64_t)lat * T};
   taps_["means"] = TensorRef{params_ + (size_t)lat * T, CRA5_DT_F32, (int64_t)lat * T};
@@ -484,11 +680,11 @@ void Model::bin_to_latent(const uint8_t* y_bytes, size_t y_len, const uint8_t* z
   const int lat = c.latent_chans, zc = c.z_chans;
   const float* med = (const float*)need("entropy_bottleneck.medians", CRA5_DT_F32, zc);
   const float* table = scale_table_of(this, tensors_, gc_.rows);
-#if CRA5_TUNE
   // Both CR5B containers are staged up front in disjoint parts of the pinned buffer and the whole chain -- z decode,
   // h_s, scale indexes, y decode -- is enqueued without a host synchronisation in between; one synchronisation at the
-  // end fetches the error word of both decodes. The default path synchronises four times here (before and after each
-  // decode), and the GPU idles while the host copies the 5 MB y container into the staging buffer.
+  // end fetches the error word of both decodes. (The general path below synchronises four times -- before and after each
+  // decode -- and the GPU idles while the host copies the 5 MB y container into the staging buffer; it remains for
+  // reference-format streams and containers larger than the staging buffer.)
   const size_t y_off = (z_len + 255) & ~size_t(255);
   if (y_bytes != nullptr && z_bytes != nullptr && y_len >= 4 && z_len >= 4 && memcmp(y_bytes, "CR5B", 4) == 0 &&
       memcmp(z_bytes, "CR5B", 4) == 0 && y_off + y_len <= coder_->stage_capacity()) {
@@ -511,7 +707,6 @@ void Model::bin_to_latent(const uint8_t* y_bytes, size_t y_len, const uint8_t* z
     taps_["y_indexes"] = TensorRef{yidx_, CRA5_DT_U8, (int64_t)lat * T};
     return;
   }
-#endif
   coder_->decode(st, z_bytes, z_len, nullptr, eb_, zc, Th, zsym_, nullptr, med, zhat_);
   taps_["z_symbols"] = TensorRef{zsym_, CRA5_DT_I32, (int64_t)zc * Th};
   taps_["z_hat"] = TensorRef{zhat_, CRA5_DT_F32, (int64_t)zc * Th};
@@ -527,8 +722,17 @@ void Model::latent_to_reconstruction(const float* y_hat, float* x_hat, cudaStrea
   finalize();
   const cra5_config& c = cfg_;
   const int D = c.dim, lat = c.latent_chans, CS = c.in_chans * c.patch_w;
-  transpose_cast(st, y_hat, ytok_, lat, T, lat);
-  {
+  const bool pr = precision_ >= 3;   // the decoder does not influence the bitstream; split-bf16 only at the top level
+  if (pr) {
+    transpose_cast(st, y_hat, ytok2_, lat, T, lat, ytok2_ + ytok_half_);
+    EpiParams e{};
+    e.bias = (const float*)need("post_quant_conv.bias", CRA5_DT_F32, D);
+    e.out_f32 = main_.x; e.ldo = D;
+    TagScope tag_("post_quant_conv");
+    gemm_plain(st, EPI_F32, ytok2_, lat, need_x3("post_quant_conv.weight", (int64_t)D * lat), lat, T, D, lat, e,
+               GemmSplit{ytok_half_, (size_t)D * lat});
+  } else {
+    transpose_cast(st, y_hat, ytok_, lat, T, lat);
     EpiParams e{};
     e.bias = (const float*)need("post_quant_conv.bias", CRA5_DT_F32, D);
     e.out_f32 = main_.x; e.ldo = D;
@@ -540,10 +744,13 @@ void Model::latent_to_reconstruction(const float* y_hat, float* x_hat, cudaStrea
   for (int i = 0; i < n; ++i) {
     int wh, ww;
     window_of(c, c.depth / 2 + i, &wh, &ww);
-    run_block(st, gs_[i], main_, main_.x, main_.x, T, D, c.num_heads, c.mlp_ratio, wh, ww, nullptr, 0, 0);
+    run_block(st, gs_[i], main_, main_.x, main_.x, T, D, c.num_heads, c.mlp_ratio, wh, ww, nullptr, 0, 0, pr);
   }
+  __nv_bfloat16* fin = pr ? main_.a2 : main_.a;
+  const size_t fin_half = pr ? main_.a_half : 0;
   layernorm_bf16(st, main_.x, (const float*)need("g_s.norm.weight", CRA5_DT_F32, D),
-                 (const float*)need("g_s.norm.bias", CRA5_DT_F32, D), c.ln_eps, main_.a, T, D, WinMap{});
+                 (const float*)need("g_s.norm.bias", CRA5_DT_F32, D), c.ln_eps, fin, T, D, WinMap{},
+                 pr ? main_.a2 + main_.a_half : nullptr);
   const bool conv_head = (c.img_h == 721 && c.img_w == 1440);  // vit_nlc.py:628
   if (conv_head) {
     // ConvTranspose2d(k=(ph,pw), s=(sh,pw)) as two GEMMs with a scatter epilogue, no atomics:
@@ -555,19 +762,35 @@ void Model::latent_to_reconstruction(const float* y_hat, float* x_hat, cudaStrea
     if (nA > 0) {
       e.ct_r0 = nB;
       TagScope tag_("convT_A");
-      gemm_plain(st, EPI_CONVT, main_.a, D, (const __nv_bfloat16*)need("g_s.final.A", CRA5_DT_BF16, (int64_t)nA * CS * D), D, T,
-                 nA * CS, D, e);
+      if (pr)
+        gemm_plain(st, EPI_CONVT, fin, D, need_x3("g_s.final.A", (int64_t)nA * CS * D), D, T, nA * CS, D, e,
+                   GemmSplit{fin_half, (size_t)nA * CS * D});
+      else
+        gemm_plain(st, EPI_CONVT, main_.a, D, (const __nv_bfloat16*)need("g_s.final.A", CRA5_DT_BF16, (int64_t)nA * CS * D), D, T,
+                   nA * CS, D, e);
     }
     if (nB > 0) {
       e.ct_r0 = 0;
       const int M2 = (Hg + 1) * Wg, N2 = nB * CS, K2 = 2 * D;
-      const __nv_bfloat16* Wb = (const __nv_bfloat16*)need("g_s.final.B", CRA5_DT_BF16, (int64_t)N2 * K2);
       CRA5_CHECK(D % GEMM_BK == 0, ERR_INVALID, "unsupported geometry: width must be a multiple of 64 for the conv head");
       const int bn = gemm_pick_bn(N2);
-      CUtensorMap tmA = make_tmap_bf16_2d(main_.a, (uint64_t)D, (uint64_t)T, (uint64_t)D * 2, GEMM_BK, GEMM_BM);
-      CUtensorMap tmB = make_tmap_bf16_2d(Wb, (uint64_t)K2, (uint64_t)N2, (uint64_t)K2 * 2, GEMM_BK, bn);
+      CUtensorMap tmA, tmB;
+      if (pr) {
+        const __nv_bfloat16* Wb = need_x3("g_s.final.B", (int64_t)N2 * K2);
+        uint64_t ad[3] = {(uint64_t)D, (uint64_t)T, 2}, as[2] = {(uint64_t)D * 2, (uint64_t)fin_half * 2};
+        uint32_t ab[3] = {GEMM_BK, GEMM_BM, 1};
+        tmA = make_tmap_bf16(fin, 3, ad, as, ab, true);
+        uint64_t bd[3] = {(uint64_t)K2, (uint64_t)N2, 2}, bs[2] = {(uint64_t)K2 * 2, (uint64_t)N2 * K2 * 2};
+        uint32_t bb[3] = {GEMM_BK, (uint32_t)bn, 1};
+        tmB = make_tmap_bf16(Wb, 3, bd, bs, bb, true);
+      } else {
+        const __nv_bfloat16* Wb = (const __nv_bfloat16*)need("g_s.final.B", CRA5_DT_BF16, (int64_t)N2 * K2);
+        tmA = make_tmap_bf16_2d(main_.a, (uint64_t)D, (uint64_t)T, (uint64_t)D * 2, GEMM_BK, GEMM_BM);
+        tmB = make_tmap_bf16_2d(Wb, (uint64_t)K2, (uint64_t)N2, (uint64_t)K2 * 2, GEMM_BK, bn);
+      }
       GemmShape shp{};
       shp.M = M2; shp.N = N2; shp.K = K2; shp.a_mode = A_CONCAT; shp.cc_D = D; shp.cc_shift = Wg;
+      shp.a_split = shp.b_split = pr ? 1 : 0;
       TagScope tag_("convT_B");
       launch_gemm(st, bn, EPI_CONVT, tmA, tmB, shp, e);
     }
@@ -578,8 +801,12 @@ void Model::latent_to_reconstruction(const float* y_hat, float* x_hat, cudaStrea
     e.out_f32 = x_hat; e.ldo = (Hg * c.patch_h) * (Wg * c.patch_w);
     e.ps_P1 = c.patch_h; e.ps_P2 = c.patch_w; e.ps_C = c.in_chans; e.ps_Wh = Wg;
     TagScope tag_("linear_head");
-    gemm_plain(st, EPI_PIXSHUF, main_.a, D, (const __nv_bfloat16*)need("g_s.final.weight", CRA5_DT_BF16, (int64_t)Nf * D), D, T, Nf,
-               D, e);
+    if (pr)
+      gemm_plain(st, EPI_PIXSHUF, fin, D, need_x3("g_s.final.weight", (int64_t)Nf * D), D, T, Nf, D, e,
+                 GemmSplit{fin_half, (size_t)Nf * D});
+    else
+      gemm_plain(st, EPI_PIXSHUF, main_.a, D, (const __nv_bfloat16*)need("g_s.final.weight", CRA5_DT_BF16, (int64_t)Nf * D), D, T, Nf,
+                 D, e);
   }
 }
 

@@ -24,6 +24,9 @@ struct TensorRef {
 struct BlockWeights {
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *qkv_b, *proj_b, *fc1_b, *fc2_b;
   const __nv_bfloat16 *qkv_w, *proj_w, *fc1_w, *fc2_w;
+  // split-bf16 copies [2][N][K] (hi, lo) of the same weights; null unless uploaded ("<name>.x3", precision levels > 0)
+  const __nv_bfloat16 *qkv_w3 = nullptr, *proj_w3 = nullptr, *fc1_w3 = nullptr, *fc2_w3 = nullptr;
+  bool has_split() const { return qkv_w3 && proj_w3 && fc1_w3 && fc2_w3; }
 };
 
 struct CdfTable {
@@ -43,6 +46,12 @@ struct TrunkBuffers {
   __nv_bfloat16 *q, *k, *vt;  // [heads][Tpad][hd], [heads][hd][Tpad]
   __nv_bfloat16* o;         // [Tpad][D] attention output
   __nv_bfloat16* h;         // [T][mlp*D]
+  // split-bf16 precision mode (allocated by Model::set_precision): A operands carried as [2][...] hi | lo halves
+  __nv_bfloat16* a2 = nullptr;   // [2][Tpad][D]
+  size_t a_half = 0;
+  __nv_bfloat16* h2 = nullptr;   // [2][T][mlp*D]
+  size_t h_half = 0;
+  float* f32 = nullptr;          // [T][mlp*D] pre-activation of fc1 (GELU + split run as their own kernel)
 };
 
 class Model {
@@ -54,6 +63,11 @@ class Model {
   void set_tensor(const std::string& name, const void* ptr, int dtype, int64_t numel);
   void set_cdf(int which, const int32_t* cdf, const int32_t* len, const int32_t* off, int rows, int cols);
   void set_coder(int spc_y, int spc_z);
+  // 0 = bf16 operands everywhere (default); 1 = split-bf16 ("bf16x3") GEMMs on the encoder tail (last two g_a blocks,
+  // quant_conv) and the whole hyperprior; 2 = + patch-embed and every g_a block (everything that decides the symbols);
+  // 3 = + the decoder. Needs the "<name>.x3" weight copies of the sites it covers.
+  void set_precision(int level);
+  int precision() const { return precision_; }
 
   // hot path (all pointers device, fp32)
   void encode_to_latent(const float* x, float* y, const float* mean, const float* std_, cudaStream_t st);
@@ -85,7 +99,10 @@ class Model {
   BlockWeights block_weights(const std::string& prefix, int D, int mlp) const;
   WinMap make_winmap(int block_window_h, int block_window_w) const;
   void run_block(cudaStream_t st, const BlockWeights& w, const TrunkBuffers& tb, const float* x_in, float* x_out, int T_,
-                 int D, int heads, int mlp, int win_h, int win_w, __nv_bfloat16* cat_out, int cat_col0, int cat_ld);
+                 int D, int heads, int mlp, int win_h, int win_w, __nv_bfloat16* cat_out, int cat_col0, int cat_ld,
+                 bool precise = false);
+  const __nv_bfloat16* need_x3(const std::string& name, int64_t numel) const;  // "<name>.x3": [2][numel] bf16
+  void* alloc2(size_t bytes);
   void run_h_a(cudaStream_t st, const float* y);     // -> z_
   void run_h_s(cudaStream_t st, const float* z_hat); // -> params_ (sigma | mu)
   void* alloc(size_t bytes);
@@ -99,6 +116,11 @@ class Model {
 
   uint8_t* ws_ = nullptr;
   size_t ws_bytes_ = 0, ws_used_ = 0;
+  int precision_ = 0;
+  uint8_t* ws2_ = nullptr;          // split-precision workspace (set_precision)
+  size_t ws2_bytes_ = 0, ws2_used_ = 0;
+  __nv_bfloat16 *cat2_ = nullptr, *patches2_ = nullptr, *ytok2_ = nullptr, *ztok2_ = nullptr, *ah2_ = nullptr;
+  size_t cat_half_ = 0, patches_half_ = 0, ytok_half_ = 0, ztok_half_ = 0, ah_half_ = 0;
   TrunkBuffers main_, hyper_;
   float *x1_, *x2_;                 // outputs of the two parallel head blocks
   __nv_bfloat16* cat_;              // [T][2D] bf16 (mean || logvar tokens)

@@ -24,25 +24,6 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// ------------------------------------------------------------------ programmatic dependent launch
-// Compiled in only with -DCRA5_PDL=1 (the libcra5b200_pdl.so build variant, selected at load time by CRA5_PDL=1);
-// in the default build these are empty, so the default library's SASS does not change.
-// Contract: a kernel launched through launch_chained() (host_util.h) calls pdl_grid_sync() with EVERY thread after its
-// prologue (barrier init, TMEM allocation, descriptor prefetch -- nothing that touches memory another kernel writes)
-// and before its first global-memory access. `wait` returns once the preceding grid in the stream has completed and its
-// writes are visible; `launch_dependents` then lets the NEXT kernel's CTAs become resident and run their own prologue
-// while this grid computes (they block in their own `wait`). Triggering only after the wait bounds the look-ahead to
-// one kernel.
-#ifndef CRA5_PDL
-#define CRA5_PDL 0
-#endif
-__device__ __forceinline__ void pdl_grid_sync() {
-#if CRA5_PDL
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
-}
-
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -97,6 +78,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
       "[%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 
@@ -210,21 +199,14 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
-// Arrive on a barrier that may live in the peer CTA of the pair. The default build uses release semantics at cluster
-// scope, which ptxas implements with ERRBAR + a cluster-scope membar in front of the arrive: the arriving epilogue warp
-// first drains its own global stores. The only consumer of these arrivals is the MMA issuer, which needs the TMEM READS
-// to have retired (tcgen05.wait::ld + tcgen05.fence::before_thread_sync order those) and never looks at the stores, so
-// -DCRA5_ARRIVE_CTA_SCOPE=1 (the experimental "tune" build variant) uses the unqualified form -- release at CTA scope, the
-// form CUTLASS's ClusterBarrier::arrive(cta_id) emits -- which needs no membar.
-#ifndef CRA5_ARRIVE_CTA_SCOPE
-#define CRA5_ARRIVE_CTA_SCOPE 0
-#endif
+// Arrive on a barrier that may live in the peer CTA of the pair. Unqualified form = release at CTA scope, what CUTLASS's
+// ClusterBarrier::arrive(cta_id) emits. (The `.release.cluster` form makes ptxas put MEMBAR.ALL.GPU + ERRBAR in front of
+// the arrive, i.e. the epilogue warp first drains its own global stores -- 10 % of the pair kernel's stall samples. The
+// only consumer of these arrivals is the MMA issuer, which needs the TMEM READS to have retired -- tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync order those -- and never looks at the stores. Bit-identical results and 1.7 % of the
+// frame time on a B200, tools/check_overlap.py, round 2.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-#if CRA5_ARRIVE_CTA_SCOPE
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-#else
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-#endif
 }
 // TMA load whose completion bytes are credited to an mbarrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,

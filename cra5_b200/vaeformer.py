@@ -107,6 +107,7 @@ class VAEformer:
     `VAEformer(268)` reproduces the hard-coded shipped variant (vaeformer.py:93-142); other geometries pass a
     `VaeformerConfig` via `cfg=`.
     """
+    _warned_ref_stream = False
 
     def __init__(self, model_version: int = 268, cfg: Optional[C.VaeformerConfig] = None, device="cuda",
                  streams_per_channel=(16, 4), init_seed: Optional[int] = 0, **kwargs):
@@ -131,6 +132,7 @@ class VAEformer:
         self._cdf = {"entropy_bottleneck": None, "gaussian_conditional": None}
         self.scale_table = torch.empty(0)
         self.training = False
+        self._precision = 0
         if init_seed is not None:
             self.load_state_dict(init_state_dict(self.cfg, init_seed))
 
@@ -167,6 +169,7 @@ class VAEformer:
         r = object.__new__(type(self))
         r.cfg, r.device, r._spc, r.training = self.cfg, self.device, self._spc, self.training
         r._sd, r._cdf, r.scale_table = self._sd, dict(self._cdf), self.scale_table
+        r._precision = self._precision
         r._dev = {}
         r._handle = ctypes.c_void_p()
         with torch.cuda.device(self.device):
@@ -184,6 +187,7 @@ class VAEformer:
                     _lib.check(_lib.lib.cra5_model_set_tensor(r._handle, name.encode(), _lib.ptr(t), _DT[t.dtype],
                                                               ctypes.c_int64(t.numel())))
             _lib.check(_lib.lib.cra5_model_set_coder(r._handle, *self._spc))
+            _lib.check(_lib.lib.cra5_model_set_precision(r._handle, self._precision))
         return r
 
     # ------------------------------------------------------------------ parameters
@@ -230,6 +234,38 @@ class VAEformer:
                     self._install_tables(mod, tabs, st)
         return self
 
+    PRECISIONS = {"bf16": 0, "tail": 1, "encoder": 2, "all": 3}
+
+    def _split_site(self, name: str) -> bool:
+        """does the current precision level run the GEMM that consumes weight `name` in split-bf16 form?
+        (same site table as csrc/model.cu: Model::set_precision)"""
+        lvl = self._precision
+        if lvl <= 0:
+            return False
+        n = self.cfg.enc_blocks
+        if name.startswith(("h_a.", "h_s.", "quant_conv.")) or name.startswith((f"g_a.blocks.{n - 2}.", f"g_a.blocks.{n - 1}.")):
+            return True
+        if name.startswith("g_a."):
+            return lvl >= 2
+        return lvl >= 3     # post_quant_conv, g_s.*
+
+    def set_precision(self, level="bf16"):
+        """Arithmetic of the linear / conv layers (additive extension; include/cra5_b200.h: cra5_model_set_precision).
+        "bf16" (0, default): bf16 tensor-core operands, fp32 accumulation. "tail" (1): the last two g_a blocks, quant_conv
+        and the whole hyperprior run split-bf16 GEMMs (each fp32 operand as bf16 hi + bf16 lo, three products per
+        k-block: ~fp32 products on the tensor cores). "encoder" (2): every layer the bitstream depends on. "all" (3):
+        the decoder too. Higher levels make the quantised symbols agree with the fp32 reference (tests/
+        test_gpu_precision.py reports the flip rates) at 3x the tensor work of the covered layers."""
+        lvl = self.PRECISIONS.get(level, level)
+        if lvl not in (0, 1, 2, 3):
+            raise ValueError(f'Invalid precision "{level}" (choose one of {list(self.PRECISIONS)} or 0..3)')
+        self._precision = int(lvl)
+        with torch.cuda.device(self.device):
+            if self._sd is not None:
+                self._upload()          # (re)creates the "<name>.x3" split copies the level needs
+            _lib.check(_lib.lib.cra5_model_set_precision(self._handle, self._precision))
+        return self
+
     def _upload(self):
         cfg, sd = self.cfg, self._sd
         D, Cc = cfg.dim, cfg.in_chans
@@ -240,6 +276,17 @@ class VAEformer:
         def bf(t):
             return t.to(dev).to(torch.bfloat16).contiguous()
 
+        def set_weight(name, w32, site=None):
+            """GEMM weight [N][K]: bf16 copy always; the split copy [2][N][K] = (hi, lo = bf16(w - hi)) when the level
+            covers the site"""
+            w32 = w32.to(dev, torch.float32)
+            hi = w32.to(torch.bfloat16)
+            self._set(name, hi.contiguous())
+            if self._split_site(site or name):
+                lo = (w32 - hi.float()).to(torch.bfloat16)
+                self._set(name + ".x3", torch.stack([hi, lo]).contiguous())
+            # (a split copy uploaded for an earlier, higher level stays alive: the library keeps its pointer)
+
         for k, v in sd.items():
             if k.startswith("entropy_bottleneck."):
                 continue
@@ -247,7 +294,7 @@ class VAEformer:
                      "post_quant_conv.weight", "h_a.patch_embed.proj.weight"):
                 continue
             if v.dim() == 2:          # nn.Linear weights feed tensor-core GEMMs
-                self._set(k, bf(v))
+                set_weight(k, v)
             elif k.endswith("pos_embed"):
                 self._set(k, v.reshape(-1, v.shape[-1]).float())
             else:                     # biases, LayerNorm affine
@@ -258,23 +305,23 @@ class VAEformer:
         w = w.permute(0, 2, 1, 3).reshape(D, ph, Cc * pw)
         wp = torch.zeros(D, ph, kpr * 64, device=dev)
         wp[:, :, : Cc * pw] = w
-        self._set("g_a.patch_embed.proj.weight", bf(wp.reshape(D, ph * kpr * 64)))
+        set_weight("g_a.patch_embed.proj.weight", wp.reshape(D, ph * kpr * 64))
         # reconstruction head
         wf = sd["g_s.final.weight"].to(dev)
         if cfg.conv_head:
             P = wf.permute(2, 1, 3, 0).contiguous()          # [ph][C][pw][D]
             nB = ph - sh
             if sh - nB > 0:
-                self._set("g_s.final.A", bf(P[nB:sh].reshape(-1, D)))
+                set_weight("g_s.final.A", P[nB:sh].reshape(-1, D))
             if nB > 0:
-                self._set("g_s.final.B", bf(torch.cat([P[:nB], P[sh:sh + nB]], dim=-1).reshape(-1, 2 * D)))
+                set_weight("g_s.final.B", torch.cat([P[:nB], P[sh:sh + nB]], dim=-1).reshape(-1, 2 * D))
         else:
-            self._set("g_s.final.weight", bf(wf))
+            set_weight("g_s.final.weight", wf)
         lat = cfg.latent_chans
-        self._set("quant_conv.weight", bf(sd["quant_conv.weight"][:lat].reshape(lat, 2 * D)))
+        set_weight("quant_conv.weight", sd["quant_conv.weight"][:lat].reshape(lat, 2 * D))
         self._set("quant_conv.bias", sd["quant_conv.bias"][:lat].float())
-        self._set("post_quant_conv.weight", bf(sd["post_quant_conv.weight"].reshape(D, lat)))
-        self._set("h_a.patch_embed.proj.weight", bf(sd["h_a.patch_embed.proj.weight"].reshape(cfg.hyper_dim, -1)))
+        set_weight("post_quant_conv.weight", sd["post_quant_conv.weight"].reshape(D, lat))
+        set_weight("h_a.patch_embed.proj.weight", sd["h_a.patch_embed.proj.weight"].reshape(cfg.hyper_dim, -1))
         self._set("entropy_bottleneck.medians", sd["entropy_bottleneck.quantiles"][:, 0, 1].float())
         # factorised-density parameters for the likelihood kernel: softplus(matrix), bias, tanh(factor) per layer, packed
         # per channel as m0[3] b0[3] f0[3] | (m[9] b[3] f[3]) x3 | m4[3] b4[1]  (entropy_models.py:434-453)
@@ -329,8 +376,14 @@ class VAEformer:
     def set_coder(self, streams_per_channel_y: int = 16, streams_per_channel_z: int = 4, format: str = None):
         """entropy-coder layout. Default: CR5B chunk-parallel container (16 / 4 interleaved rANS sub-streams per y / z
         channel). `format="ref"` (or 0 streams) selects the reference's single sequential stream per tensor: strings are
-        then byte-identical to what compressai.ans would write for the same symbols, and reference-written strings can be
-        decoded (one GPU thread per tensor: interoperability, not throughput). Decoding auto-detects the format."""
+        then byte-identical to what compressai.ans would write for the SAME symbols and indexes (one GPU thread per
+        tensor: interoperability of the coder, not throughput). Decoding auto-detects the format.
+
+        What this does NOT give is decoding of archives written by the PyTorch reference: the y stream can only be
+        decoded with the scale indexes and means its encoder used, i.e. `h_s(z_hat)` has to agree bit for bit between
+        writer and reader. This library's h_s (bf16 or split-bf16 tensor-core GEMMs) and torch's fp32 h_s do not --
+        nor do two torch builds / devices in general -- so one differing scale index desynchronises
+        the rest of the tensor. `decompress` therefore warns when it is handed a reference-format stream."""
         if format is not None:
             if format not in ("ref", "cr5b"):
                 raise ValueError(f'Invalid coder format "{format}" (choose "cr5b" or "ref")')
@@ -422,6 +475,13 @@ class VAEformer:
             s = _lib.stream_ptr()
             for b in range(B):
                 ys, zs = bytes(strings[0][b]), bytes(strings[1][b])
+                if ys[:4] != b"CR5B" and not VAEformer._warned_ref_stream:
+                    VAEformer._warned_ref_stream = True
+                    import warnings
+                    warnings.warn("decompress: reference-format (single-stream) input. It decodes correctly only if it "
+                                  "was written by this library on the same build (set_coder(format='ref')): a stream "
+                                  "written by the PyTorch reference needs bit-identical h_s outputs, which two "
+                                  "implementations do not produce.", RuntimeWarning, stacklevel=2)
                 _lib.check(_lib.lib.cra5_bin_to_latent(self._handle, ys, ctypes.c_uint64(len(ys)), zs,
                                                        ctypes.c_uint64(len(zs)), int(shape[0]), int(shape[1]),
                                                        _lib.ptr(y_hat[b]), s))

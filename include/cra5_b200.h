@@ -123,6 +123,18 @@ CRA5_API int cra5_model_set_cdf(cra5_model* m, int which, const int32_t* cdf_dev
 /* Interleaved rANS sub-streams per latent channel for y and z (parallelism / rate knob of the CR5B container). */
 CRA5_API int cra5_model_set_coder(cra5_model* m, int streams_per_channel_y, int streams_per_channel_z);
 
+/* Arithmetic of the linear / conv layers. The reference computes them in fp32 (nn.Linear / Conv2d on torch CPU,
+ * vit_nlc.py:63-67, 96, 111, 302, 629; vaeformer.py:154-155); the default here (level 0) feeds bf16 operands to the
+ * tensor cores with fp32 accumulation. Levels > 0 switch groups of GEMM sites to the split-bf16 form (every fp32
+ * operand carried as bf16 hi + bf16 lo, three tcgen05 products per k-block into one fp32 accumulator: ~16 mantissa
+ * bits per operand), which is what makes the quantised SYMBOLS agree with the fp32 reference:
+ *   1  encoder tail (the last two g_a blocks, quant_conv) + the whole hyperprior (h_a, h_s)
+ *   2  1 + patch-embed conv and every g_a block: every layer the bitstream depends on
+ *   3  2 + the decoder (post_quant_conv, g_s, reconstruction head)
+ * A level needs the split copies "<name>.x3" (bf16 [2][N][K]: hi, lo) of the weights it covers, handed over with
+ * cra5_model_set_tensor beforehand; ERR_STATE otherwise. Attention keeps bf16 Q/K/V/P at every level. */
+CRA5_API int cra5_model_set_precision(cra5_model* m, int level);
+
 /* x (C,H,W) fp32 -> y (latent, Hg, Wg) fp32. mean/std: optional per-channel (C) device arrays; when given the input
  * is physical-unit data and (x-mean)/std (cra5_api.normalization, cra5_api.py:264-266) is fused into the first kernel.
  * Replaces VAEformer.encode_latent(type='float') (vaeformer.py:272-292) = cra5_api.encode_to_latent (:53-71). */

@@ -1,0 +1,148 @@
+#!/usr/bin/env python
+"""CPU experiment (no GPU): which GEMM sites have to leave plain bf16 for the latent SYMBOLS to match the fp32
+reference in a trained-like regime (|y| up to ~35, sigma-hat over all 64 rows of the scale table)?
+
+The fp32 oracle forward is compared with emulations of the tensor-core path in which the operands of every linear /
+conv are rounded to bf16 (fp32 accumulation) except at the sites listed as `split`, where the three-term bf16 split
+(a_hi b_hi + a_lo b_hi + a_hi b_lo, the arithmetic of the library's precision levels) is used. Attention (q, k, v and
+the softmax numerators in bf16) is emulated as the tcgen05 attention kernel computes it, at every level.
+
+    python tools/precision_study.py [--cfg tiny69|small] [--gain 1.0]
+"""
+import argparse
+import os
+import sys
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.nn.functional as F
+
+from cra5_b200 import config as C
+from oracle import vaeformer_oracle as VO, weights
+
+
+def r(t):
+    return t.bfloat16().float()
+
+
+def split(t):
+    hi = r(t)
+    return hi, r(t - hi)
+
+
+class Emu:
+    """functional namespace whose linear/conv know which site they are called for"""
+
+    def __init__(self, sd, split_if, attn_split_if=lambda key: False):
+        self.sd, self.split_if, self.attn_split_if = sd, split_if, attn_split_if
+        self.by_id = {id(v): k for k, v in sd.items()}
+        self.layer_norm, self.gelu, self.pad = F.layer_norm, F.gelu, F.pad
+        self.last_key = ""
+
+    def _op(self, fn, x, w, b, **kw):
+        key = self.by_id.get(id(w), "?")
+        self.last_key = key
+        if self.split_if(key):
+            xh, xl = split(x)
+            wh, wl = split(w)
+            return fn(xh, wh, b, **kw) + (fn(xl, wh, None, **kw) + fn(xh, wl, None, **kw))
+        return fn(r(x), r(w), b, **kw)
+
+    def linear(self, x, w, b=None):
+        return self._op(F.linear, x, w, b)
+
+    def conv2d(self, x, w, b=None, stride=1):
+        return self._op(F.conv2d, x, w, b, stride=stride)
+
+    def conv_transpose2d(self, x, w, b=None, stride=1):
+        return self._op(F.conv_transpose2d, x, w, b, stride=stride)
+
+
+def make_mhsa(emu):
+    def mhsa(qkv, heads):
+        B, N, D3 = qkv.shape
+        D = D3 // 3
+        hd = D // heads
+        qkv = qkv.reshape(B, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+        if emu.attn_split_if(emu.last_key):       # fp32 attention (what a split attention would approach)
+            q, k, v = qkv[0] * hd ** -0.5, qkv[1], qkv[2]
+            out = torch.softmax(q @ k.transpose(-2, -1), dim=-1) @ v
+            return out.transpose(1, 2).reshape(B, N, D)
+        q, k, v = r(qkv[0] * hd ** -0.5), r(qkv[1]), r(qkv[2])
+        s = q @ k.transpose(-2, -1)
+        p = torch.exp(s - s.amax(dim=-1, keepdim=True))
+        out = (r(p) @ v) / p.sum(dim=-1, keepdim=True)
+        return r(out.transpose(1, 2).reshape(B, N, D))
+    return mhsa
+
+
+def trained_like(sd, cfg, gain=1.0):
+    """widen quant_conv so |y| reaches ~35 and the sigma rows of h_s.final so sigma-hat covers the scale table"""
+    sd = {k: v.clone() for k, v in sd.items()}
+    lat = cfg.latent_chans
+    sd["quant_conv.weight"] = sd["quant_conv.weight"] * (5.0 * gain)
+    w = sd["h_s.final.weight"].reshape(-1, 2 * lat, cfg.hyper_dim).clone()
+    w[:, :lat] *= 12.0 * gain
+    w[:, lat:] *= 3.0 * gain
+    sd["h_s.final.weight"] = w.reshape(-1, cfg.hyper_dim)
+    return sd
+
+
+def levels(cfg):
+    n = cfg.enc_blocks
+    tail_blocks = (f"g_a.blocks.{n - 2}.", f"g_a.blocks.{n - 1}.")
+    hyper = ("h_a.", "h_s.")
+    tail = lambda k: k.startswith(tail_blocks) or k.startswith(hyper) or k.startswith(("quant_conv", "post_quant_conv"))
+    enc = lambda k: k.startswith(("g_a.", "quant_conv")) or k.startswith(hyper)
+    return [("bf16 everywhere", lambda k: False, lambda k: False),
+            ("hyperprior only", lambda k: k.startswith(hyper), lambda k: False),
+            ("tail: g_a last 2 blocks + quant_conv + hyperprior", tail, lambda k: False),
+            ("encoder linears + hyperprior (attention bf16)", enc, lambda k: False),
+            ("all linears (attention bf16)", lambda k: True, lambda k: False),
+            ("all linears + hyperprior attention fp32", lambda k: True, lambda k: k.startswith(hyper)),
+            ("all linears + all attention fp32", lambda k: True, lambda k: True)]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cfg", default="tiny69")
+    ap.add_argument("--gain", type=float, default=1.0)
+    a = ap.parse_args()
+    torch.set_num_threads(os.cpu_count())
+    cfg, wseed, fseed = (C.tiny_fullres(69), 7, 1) if a.cfg == "tiny69" else (C.small_lowres(5), 11, 3)
+    sd = trained_like(weights.seeded_state_dict(C.param_shapes(cfg), wseed), cfg, a.gain)
+    x = weights.seeded_frame(cfg, fseed).unsqueeze(0)
+    codec = VO.OracleCodec(sd, cfg)
+    with torch.no_grad():
+        ref = codec.forward(x)
+    y, sc = ref["y"], ref["scales"]
+    print(f"regime: |y| max {y.abs().max():.1f} std {y.std():.2f}; sigma-hat raw min {sc.min():.2f} max {sc.max():.1f}; "
+          f"rows used {len(torch.unique(VO.EO.build_indexes(sc, codec.gc.scale_table)))} of 64")
+    sym_ref = torch.round(ref["y"] - ref["means"])
+    idx_ref = VO.EO.build_indexes(ref["scales"], codec.gc.scale_table)
+    rm_r = ((ref["x_hat"][0] - x[0]) ** 2).mean(dim=(1, 2)).sqrt()
+    keepF, keepM = VO.F, VO.mhsa
+    for name, sp, asp in levels(cfg):
+        emu = Emu(codec.sd, sp, asp)
+        VO.F, VO.mhsa = emu, make_mhsa(emu)
+        try:
+            with torch.no_grad():
+                out = codec.forward(x)
+        finally:
+            VO.F, VO.mhsa = keepF, keepM
+        rel = lambda k: ((out[k] - ref[k]).pow(2).mean().sqrt() / ref[k].pow(2).mean().sqrt()).item()
+        flips = (torch.round(out["y"] - out["means"]) != sym_ref).float().mean().item()
+        zflips = (out["z_hat"] != ref["z_hat"]).float().mean().item()
+        iflips = (VO.EO.build_indexes(out["scales"], codec.gc.scale_table) != idx_ref).float().mean().item()
+        rm_e = ((out["x_hat"][0] - x[0]) ** 2).mean(dim=(1, 2)).sqrt()
+        direct = ((out["x_hat"][0] - ref["x_hat"][0]) ** 2).mean(dim=(1, 2)).sqrt()
+        print(f"{name:52s} y {rel('y'):.1e} means {rel('means'):.1e} | y-symbol flips {100 * flips:6.3f} % "
+              f"z flips {100 * zflips:6.3f} % index flips {100 * iflips:6.3f} % | max|dRMSE| {(rm_e - rm_r).abs().max():.1e} "
+              f"direct rms(x_hat - ref) max {direct.max():.1e}")
+
+
+if __name__ == "__main__":
+    main()
