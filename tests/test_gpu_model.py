@@ -146,15 +146,22 @@ def test_g_s_reconstruction_close_to_oracle(ctx):
 
 
 def test_per_variable_rmse_within_tolerance_of_reference(ctx):
-    """north-star gate: |RMSE_new(c) - RMSE_ref(c)| <= 1e-4 (normalised units, RMSE against the input) at full
-    resolution; the low-resolution fixture has 20x fewer pixels per variable, so its sampling noise gets 3e-4."""
-    with torch.no_grad():
-        out = ctx.net.compress(ctx.x.cuda())
-        x_g = ctx.net.decompress(out["strings"], out["z_shape"])["x_hat"].cpu()
+    """north-star gate: |RMSE_new(c) - RMSE_ref(c)| <= 1e-4 (normalised units, RMSE against the input), no waiver.
+    The full-resolution fixture meets it with plain bf16 operands; the low-resolution one has 20x fewer pixels per
+    variable, so individual symbol flips show (1.1e-4 at bf16) -- it meets the same 1e-4 at precision level "encoder"
+    (split-bf16 GEMMs on every layer the symbols depend on), which is what the gate is asserted on there."""
+    level = 0 if ctx.name == "tiny69" else 2
+    ctx.net.set_precision(level)
+    try:
+        with torch.no_grad():
+            out = ctx.net.compress(ctx.x.cuda())
+            x_g = ctx.net.decompress(out["strings"], out["z_shape"])["x_hat"].cpu()
+    finally:
+        ctx.net.set_precision(0)
     rmse_g = ((x_g[0] - ctx.x[0]) ** 2).mean(dim=(1, 2)).sqrt().numpy()
     rmse_ref = ctx.gold["rmse_per_var"]  # produced by the real reference
-    tol = 1e-4 if ctx.name == "tiny69" else 3e-4
-    assert np.abs(rmse_g - rmse_ref).max() <= tol, np.abs(rmse_g - rmse_ref).max()
+    print(f"\n[{ctx.name}] precision level {level}: max |dRMSE| vs the reference {np.abs(rmse_g - rmse_ref).max():.2e}")
+    assert np.abs(rmse_g - rmse_ref).max() <= 1e-4, np.abs(rmse_g - rmse_ref).max()
     # and the reconstruction itself is close to the reference's (symbol flips near .5 allowed): rms diff <= 10 %
     assert np.abs(x_g[0].std(dim=(1, 2)).numpy() - ctx.gold["xhat_std_per_var"]).max() <= 5e-3
     # rate within 1 % + container overhead of the reference's single-stream coder
@@ -246,15 +253,46 @@ def test_forward_likelihoods_match_reference_arithmetic(ctx):
     assert torch.isfinite(out["x_hat"]).all() and out["posterior"] is None
 
 
-@pytest.mark.skipif(os.environ.get("CRA5_TEST_OVERLAP", "0") in ("", "0"),
-                    reason="experimental options: set CRA5_TEST_OVERLAP=1 to check the PDL build variant and CodecLanes")
-def test_overlap_options_are_bit_identical():
-    """the programmatic-dependent-launch build (CRA5_PDL=1) and two codec lanes per GPU must reproduce the default
-    single-stream result bit for bit (tools/check_overlap.py runs each configuration in its own process)"""
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_overlap.py")], capture_output=True, text=True,
-                       timeout=3600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert json.loads(r.stdout.strip().splitlines()[-1])["all_identical"]
+def test_codec_lanes_are_bit_identical(ctx):
+    """several codec lanes on one GPU (cra5_b200.stream.CodecLanes: own handle / stream / host thread, shared weights)
+    reproduce the single-lane bitstreams and reconstruction bit for bit. (The full-size model is checked the same way in
+    test_zz_fullsize_parity.py: that is where a timing-dependent race in the attention kernel showed in round 2.)"""
+    import hashlib
+    from cra5_b200.stream import CodecLanes
+
+    def roundtrip(codec, i):
+        with torch.no_grad():
+            o = codec.compress(ctx.x.cuda())
+            rec = codec.decompress(o["strings"], o["z_shape"])["x_hat"]
+        return hashlib.sha256(o["strings"][0][0] + o["strings"][1][0] + rec.cpu().numpy().tobytes()).hexdigest()
+
+    base = roundtrip(ctx.net, 0)
+    got = CodecLanes(ctx.net, lanes=3).run(roundtrip, 9)
+    assert got == [base] * 9
+
+
+def test_likelihoods_entry_accepts_null_outputs(ctx):
+    """include/cra5_b200.h: "Any output may be NULL" for cra5_latent_likelihoods. y_lik = NULL used to make the
+    quantise kernel read a null scale table; y_hat alone, z_lik alone and nothing at all must work."""
+    import ctypes
+    from cra5_b200 import _lib
+    net, cfg = ctx.net, ctx.cfg
+    y = ctx.y_g.contiguous()
+    y_hat = torch.empty_like(y)
+    z_lik = torch.empty((cfg.z_chans, *cfg.hyper_grid), device="cuda")
+    null = ctypes.c_void_p(0)
+    s = _lib.stream_ptr()
+    _lib.check(_lib.lib.cra5_latent_likelihoods(net._handle, _lib.ptr(y[0]), _lib.ptr(y_hat[0]), null, null, s))
+    torch.cuda.synchronize()
+    expect = ctx.ysym_g.reshape(ctx.mu_g.shape).float() + ctx.mu_g
+    assert torch.equal(y_hat.cpu(), expect)
+    _lib.check(_lib.lib.cra5_latent_likelihoods(net._handle, _lib.ptr(y[0]), null, null, _lib.ptr(z_lik), s))
+    _lib.check(_lib.lib.cra5_latent_likelihoods(net._handle, _lib.ptr(y[0]), null, null, null, s))
+    torch.cuda.synchronize()
+    assert torch.isfinite(z_lik).all() and (z_lik > 0).all()
+    # the operator entry refuses an index request without a scale table instead of faulting
+    idx = torch.empty(16, dtype=torch.uint8, device="cuda")
+    v = torch.zeros(16, device="cuda")
+    with pytest.raises(ValueError):
+        _lib.check(_lib.lib.cra5_op_gc_quantize(null, _lib.ptr(v), null, null, 64, ctypes.c_float(0.11), null,
+                                                _lib.ptr(idx), null, ctypes.c_uint64(16), s))

@@ -287,3 +287,72 @@ def test_numa_local_pinned_allocation_helper(tmp_path):
         assert not bound and os.sched_getaffinity(0) == prev
     with stream.near_gpu(pci_bus_id="0000:ff:00.0", sysfs=str(tmp_path)) as bound:
         assert not bound
+
+
+def test_reference_arm_times_whole_frames(monkeypatch, capsys):
+    """`bench.py --impl reference`: a step is one WHOLE frame through compress + decompress (nothing extrapolated), the
+    line reports the frames actually timed, and ms_per_step * steps is the wall time of the timed region."""
+    import json
+    import time
+    import types
+    import bench
+    import oracle.cpu_baseline as CB
+
+    calls = []
+
+    class FakeTimer:
+        kind = "port"
+
+        def __init__(self, cfg, threads=None, seed=1234):
+            self.cfg = cfg
+
+        def frame(self):
+            calls.append(time.perf_counter())
+            time.sleep(0.02)
+            return dict(encode_s=0.012, decode_s=0.008, total_s=0.02, bytes=1234)
+
+        def describe(self, n):
+            return f"{n} whole frames"
+
+    monkeypatch.setattr(CB, "FrameTimer", FakeTimer)
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    t0 = time.perf_counter()
+    bench.run_reference(types.SimpleNamespace(channels=268, steps=5, warmup=3, gpus=1))
+    wall = time.perf_counter() - t0
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["steps"] == 5 and line["warmup"] == 1
+    assert len(calls) == 6                                            # 1 warm-up + 5 timed whole frames
+    assert line["ms_per_step"] * line["steps"] / 1e3 <= wall          # fits the driver's clock
+    assert abs(line["value"] - 1e3 / line["ms_per_step"]) < 1e-6
+    assert line["e2e"]["value"] == line["value"] and line["cpu_baseline"]["kind"] == "port"
+    assert line["cpu_baseline"]["sample"] == "5 whole frames"
+    # the budget bounds the number of timed frames, never below 2
+    monkeypatch.setenv("CRA5_REF_BUDGET_S", "0.05")
+    bench.run_reference(types.SimpleNamespace(channels=268, steps=20, warmup=3, gpus=1))
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["steps"] == 2 and line["steps_requested"] == 20
+
+
+def test_whole_frame_timer_runs_the_real_codec():
+    """oracle/cpu_baseline.FrameTimer on the reduced-width full-resolution geometry: a real compress + decompress"""
+    from cra5_b200 import config as C
+    from oracle.cpu_baseline import FrameTimer
+    ft = FrameTimer(C.tiny_fullres(69), threads=4)
+    r = ft.frame()
+    assert r["total_s"] > 0 and abs(r["encode_s"] + r["decode_s"] - r["total_s"]) < 1e-3 and r["bytes"] > 1000
+    assert "nothing extrapolated" in ft.describe(1)
+
+
+def test_config_inferred_from_published_checkpoint_schema():
+    """from_state_dict reads the geometry off the checkpoint (vaeformer.py:172 reads in_chans off the patch-embed
+    weight); shapes only, so meta tensors stand in for the 1.6 GB of parameters"""
+    from cra5_b200 import config as C
+    for chans in (268, 159, 69):
+        want = C.variant(chans) if chans != 268 else C.cra5_268()
+        sd = {k: torch.empty(shape, device="meta") for k, shape in C.param_shapes(want).items()}
+        got = C.config_from_state_dict(sd)
+        assert got.to_dict() == want.to_dict()
+    tiny = {k: torch.empty(s, device="meta") for k, s in C.param_shapes(C.tiny_fullres(69)).items()}
+    with pytest.raises(ValueError, match="non-standard width"):
+        C.config_from_state_dict(tiny)
