@@ -58,8 +58,9 @@ struct A4Params {
   int n_seg;
   int heads;
   int n_qp;           // query-tile pairs per segment
-  int q_part_from;    // segments >= this index only need their first q_part_rows query rows (padded windows)
-  int q_part_rows;
+  int q_part_from;    // segments whose index within their frame (seg % seg_period) is >= this only need their first
+  int q_part_rows;    //   q_part_rows query rows (padded windows)
+  int seg_period;     // segments per frame of a batch
   __nv_bfloat16* out; // [rows_total, ldo]
   int ldo;
 };
@@ -155,7 +156,7 @@ __device__ __forceinline__ Item decode_item(const A4Params& p, int item) {
   it.seg = rest % p.n_seg;
   it.head = rest / p.n_seg;
   it.q0 = qp * (2 * A4_BM);
-  const int need = (it.seg >= p.q_part_from) ? p.q_part_rows : p.seg_len;  // query rows whose output is consumed
+  const int need = ((it.seg % p.seg_period) >= p.q_part_from) ? p.q_part_rows : p.seg_len;  // rows whose output is consumed
   it.act_a = it.q0 < need;
   it.act_b = it.q0 + A4_BM < need;
   return it;
@@ -490,11 +491,12 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }  // namespace
 
 // Q, K: [heads][rows_total][64] bf16; Vt: [heads][64][rows_total] bf16; out: [rows_total][ldo] bf16.
-// Segments with index >= q_part_from only need their first q_part_rows query rows (the rest are window-pad rows whose
-// output the caller drops); pass q_part_from >= n_seg for "all rows".
+// Segments with index (within their frame: seg % seg_period) >= q_part_from only need their first q_part_rows query rows
+// (the rest are window-pad rows whose output the caller drops); pass q_part_from >= seg_period for "all rows".
+// seg_period = segments per frame when rows_total holds a batch of frames (0: one frame).
 void attention_tc(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* Vt,
                   __nv_bfloat16* out, int ldo, int heads, int rows_total, int seg_len, int q_part_from,
-                  int q_part_rows) {
+                  int q_part_rows, int seg_period) {
   CRA5_CHECK(seg_len > 0 && rows_total % seg_len == 0, ERR_INVALID, "attention: rows must be whole segments");
   CRA5_CHECK((rows_total & 7) == 0, ERR_INVALID, "attention: rows_total must be a multiple of 8 (TMA stride)");
   static const int poly = [] { const char* e = getenv("CRA5_ATTN_POLY"); return e ? atoi(e) : 3; }();
@@ -510,7 +512,8 @@ void attention_tc(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* 
   p.n_seg = rows_total / seg_len;
   p.heads = heads;
   p.n_qp = (seg_len + 2 * A4_BM - 1) / (2 * A4_BM);
-  p.q_part_from = (q_part_rows > 0 && q_part_rows < seg_len) ? q_part_from : p.n_seg;
+  p.seg_period = (seg_period > 0 && seg_period <= p.n_seg) ? seg_period : p.n_seg;   // segments per frame
+  p.q_part_from = (q_part_rows > 0 && q_part_rows < seg_len) ? q_part_from : p.seg_period;
   p.q_part_rows = q_part_rows;
   p.out = out;
   p.ldo = ldo;

@@ -8,6 +8,7 @@
 #include "coder.h"
 
 #include <memory>
+#include <vector>
 #include <algorithm>
 #include <string.h>
 
@@ -144,12 +145,16 @@ int cra5_model_set_precision(cra5_model* m, int level) {
   });
 }
 
-int cra5_encode_to_latent(cra5_model* m, const float* x, float* y, const float* mean, const float* std_, void* stream) {
+int cra5_encode_to_latent_batch(cra5_model* m, const float* x, float* y, const float* mean, const float* std_, int batch,
+                                void* stream) {
   return guarded([&] {
     MODEL_GUARD(m);
     CRA5_CHECK(x && y, ERR_INVALID, "null tensor");
-    m->impl->encode_to_latent(x, y, mean, std_, static_cast<cudaStream_t>(stream));
+    m->impl->encode_to_latent(x, y, mean, std_, batch, static_cast<cudaStream_t>(stream));
   });
+}
+int cra5_encode_to_latent(cra5_model* m, const float* x, float* y, const float* mean, const float* std_, void* stream) {
+  return cra5_encode_to_latent_batch(m, x, y, mean, std_, 1, stream);
 }
 
 int cra5_latent_quantized(cra5_model* m, const float* y, float* y_hat, void* stream) {
@@ -168,33 +173,50 @@ int cra5_latent_likelihoods(cra5_model* m, const float* y, float* y_hat, float* 
   });
 }
 
-int cra5_latent_to_bin(cra5_model* m, const float* y, const uint8_t** y_bytes, uint64_t* y_len, const uint8_t** z_bytes,
-                       uint64_t* z_len, void* stream) {
+int cra5_latent_to_bin_batch(cra5_model* m, const float* y, int batch, const uint8_t** y_bytes, uint64_t* y_len,
+                             const uint8_t** z_bytes, uint64_t* z_len, void* stream) {
   return guarded([&] {
     MODEL_GUARD(m);
     CRA5_CHECK(y && y_bytes && y_len && z_bytes && z_len, ERR_INVALID, "null argument");
-    size_t yl = 0, zl = 0;
-    m->impl->latent_to_bin(y, y_bytes, &yl, z_bytes, &zl, static_cast<cudaStream_t>(stream));
-    *y_len = yl;
-    *z_len = zl;
+    CRA5_CHECK(batch >= 1 && batch <= m->impl->max_batch(), ERR_INVALID, "batch larger than the model's max_batch");
+    std::vector<size_t> yl(batch), zl(batch);
+    m->impl->latent_to_bin(y, batch, y_bytes, yl.data(), z_bytes, zl.data(), static_cast<cudaStream_t>(stream));
+    for (int b = 0; b < batch; ++b) {
+      y_len[b] = yl[b];
+      z_len[b] = zl[b];
+    }
   });
 }
+int cra5_latent_to_bin(cra5_model* m, const float* y, const uint8_t** y_bytes, uint64_t* y_len, const uint8_t** z_bytes,
+                       uint64_t* z_len, void* stream) {
+  return cra5_latent_to_bin_batch(m, y, 1, y_bytes, y_len, z_bytes, z_len, stream);
+}
 
-int cra5_bin_to_latent(cra5_model* m, const uint8_t* y_bytes, uint64_t y_len, const uint8_t* z_bytes, uint64_t z_len,
-                       int z_h, int z_w, float* y_hat, void* stream) {
+int cra5_bin_to_latent_batch(cra5_model* m, const uint8_t* const* y_bytes, const uint64_t* y_len,
+                             const uint8_t* const* z_bytes, const uint64_t* z_len, int batch, int z_h, int z_w, float* y_hat,
+                             void* stream) {
   return guarded([&] {
     MODEL_GUARD(m);
-    CRA5_CHECK(y_hat != nullptr, ERR_INVALID, "null tensor");
-    m->impl->bin_to_latent(y_bytes, y_len, z_bytes, z_len, z_h, z_w, y_hat, static_cast<cudaStream_t>(stream));
+    CRA5_CHECK(y_hat && y_bytes && y_len && z_bytes && z_len, ERR_INVALID, "null argument");
+    CRA5_CHECK(batch >= 1 && batch <= m->impl->max_batch(), ERR_INVALID, "batch larger than the model's max_batch");
+    std::vector<size_t> yl(y_len, y_len + batch), zl(z_len, z_len + batch);
+    m->impl->bin_to_latent(y_bytes, yl.data(), z_bytes, zl.data(), batch, z_h, z_w, y_hat, static_cast<cudaStream_t>(stream));
   });
 }
+int cra5_bin_to_latent(cra5_model* m, const uint8_t* y_bytes, uint64_t y_len, const uint8_t* z_bytes, uint64_t z_len,
+                       int z_h, int z_w, float* y_hat, void* stream) {
+  return cra5_bin_to_latent_batch(m, &y_bytes, &y_len, &z_bytes, &z_len, 1, z_h, z_w, y_hat, stream);
+}
 
-int cra5_latent_to_reconstruction(cra5_model* m, const float* y_hat, float* x_hat, void* stream) {
+int cra5_latent_to_reconstruction_batch(cra5_model* m, const float* y_hat, float* x_hat, int batch, void* stream) {
   return guarded([&] {
     MODEL_GUARD(m);
     CRA5_CHECK(y_hat && x_hat, ERR_INVALID, "null tensor");
-    m->impl->latent_to_reconstruction(y_hat, x_hat, static_cast<cudaStream_t>(stream));
+    m->impl->latent_to_reconstruction(y_hat, x_hat, batch, static_cast<cudaStream_t>(stream));
   });
+}
+int cra5_latent_to_reconstruction(cra5_model* m, const float* y_hat, float* x_hat, void* stream) {
+  return cra5_latent_to_reconstruction_batch(m, y_hat, x_hat, 1, stream);
 }
 
 int cra5_normalize(const float* in, float* out, const float* mean, const float* std_, int channels, uint64_t hw,

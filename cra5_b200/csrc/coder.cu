@@ -15,20 +15,25 @@ namespace cra5 {
 namespace {
 constexpr int XFER_BLOCKS = 64, XFER_THREADS = 256;
 
-// lengths[n_streams], total, err -> meta_host; payload[0, total) -> payload_host   (total = offsets[n_streams])
+// `frames` containers of ns sub-streams each, frame_words 32-bit words apart in host memory. Per frame f: the stream
+// lengths go to its length table (word 6 = byte 24 of the container), its payload bytes behind that table; the payload
+// size of frame f lands in meta_host[f], the coder's error word in meta_host[frames]. (The 24-byte headers are written
+// by the host in encode_end.)
 __global__ void container_to_host_kernel(const uint32_t* __restrict__ lengths, const uint32_t* __restrict__ offsets,
-                                         const int* __restrict__ err, int n_streams,
+                                         const int* __restrict__ err, int ns, int frames, size_t frame_words,
                                          const uint32_t* __restrict__ payload, uint32_t* meta_host,
-                                         uint32_t* payload_host) {
-  const uint32_t total = offsets[n_streams];
+                                         uint32_t* containers_host) {
   const int gt = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;
-  for (int i = gt; i < n_streams; i += gs) meta_host[i] = lengths[i];
-  if (gt == 0) {
-    meta_host[n_streams] = total;
-    meta_host[n_streams + 1] = (uint32_t)*err;
+  for (int f = 0; f < frames; ++f) {
+    uint32_t* c = containers_host + (size_t)f * frame_words;
+    const uint32_t base = offsets[(size_t)f * ns], end = offsets[(size_t)(f + 1) * ns];
+    for (int i = gt; i < ns; i += gs) c[6 + i] = lengths[(size_t)f * ns + i];
+    uint32_t* dst = c + 6 + ns;
+    const uint32_t* src = payload + base / 4;
+    for (uint32_t i = gt; i < (end - base) / 4; i += gs) dst[i] = src[i];
+    if (gt == 0) meta_host[f] = end - base;
   }
-  if (payload_host != nullptr)
-    for (uint32_t i = gt; i < total / 4; i += gs) payload_host[i] = payload[i];
+  if (gt == 0) meta_host[frames] = (uint32_t)*err;
 }
 // stage_host = [lengths: ns words][payload: words] -> lengths, payload on the device
 __global__ void container_from_host_kernel(const uint32_t* stage_host, int ns, uint32_t n_words, uint32_t* lengths,
@@ -131,8 +136,8 @@ size_t RansCoder::encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx
     CRA5_CHECK(n <= max_symbols_ && n < (size_t)1 << 30, ERR_INVALID, "rans_encode: tensor larger than the coder was sized for");
     const int cap_words = (int)(2 * n + 6);
     CRA5_CHECK((size_t)cap_words <= scratch_words_, ERR_INTERNAL, "rans_encode: scratch sizing");
-    rans_encode(st, sym, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, 1, (int)n, 1, L > 0 ? L : 1,
-                scratch_, cap_words, lengths_, offsets_, payload_, err_);
+    rans_encode(st, sym, idx, idx == nullptr ? (n_channels > 0 ? n_channels : 1) : 0, tab.cdf, tab.cols, tab.length, tab.offset, 1,
+                (int)n, 1, L > 0 ? L : 1, scratch_, cap_words, lengths_, offsets_, payload_, err_);
     CRA5_CUDA(cudaMemcpyAsync(host_meta_, lengths_, 4, cudaMemcpyDeviceToHost, st));
     CRA5_CUDA(cudaMemcpyAsync(host_meta_ + 1, err_, 4, cudaMemcpyDeviceToHost, st));
     CRA5_CUDA(cudaStreamSynchronize(st));
@@ -152,69 +157,79 @@ size_t RansCoder::encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx
   CRA5_CHECK(host_cap >= head, ERR_INVALID, "rans_encode: output buffer too small");
   encode_begin(st, 0, sym, idx, tab, n_channels, L, spc, host_stage_, host_stage_cap_);
   CRA5_CUDA(cudaStreamSynchronize(st));
-  const size_t total = encode_end(st, 0, n_channels, L, spc, host_stage_, host_stage_cap_);
+  size_t total = 0;
+  encode_end(st, 0, n_channels, L, spc, host_stage_, host_stage_cap_, 1, 0, &total);
   CRA5_CHECK(host_cap >= total, ERR_INVALID, "rans_encode: output buffer too small");
   memcpy(host_out, host_stage_, total);
   return total;
 }
 
-// Enqueue the encode of one tensor; its container lands in `host_mapped` (pinned + mapped, at least
-// max_container_bytes() large) once the stream has been synchronised and encode_end() has written the header.
+// Enqueue the encode of `frames` tensors of n_channels x L symbols each (contiguous: [frames][n_channels][L]); their
+// containers land in `host_mapped` (pinned + mapped), frame f at byte f * frame_stride (each slot at least
+// max_container_bytes() large), once the stream has been synchronised and encode_end() has written the headers. The
+// batch is ONE launch of every kernel: frames * n_channels * spc sub-streams.
 void RansCoder::encode_begin(cudaStream_t st, int slot, const int32_t* sym, const uint8_t* idx, const CdfTable& tab,
-                             int n_channels, int L, int spc, uint8_t* host_mapped, size_t host_cap) {
+                             int n_channels, int L, int spc, uint8_t* host_mapped, size_t host_cap, int frames,
+                             size_t frame_stride) {
   CRA5_CHECK(tab.ready(), ERR_STATE, "Uninitialized CDFs. Run update() first");
   CRA5_CHECK(spc >= 1 && spc <= CR5B_MAX_SPC, ERR_INVALID, "streams per channel must be in [1, 64]");
-  CRA5_CHECK(n_channels >= 0 && L >= 0 && (slot == 0 || slot == 1), ERR_INVALID, "rans_encode: bad argument");
-  const int n_streams = n_channels * spc;
-  CRA5_CHECK((size_t)n_channels * L <= max_symbols_ && n_streams <= max_streams_, ERR_INVALID,
+  CRA5_CHECK(n_channels >= 0 && L >= 0 && (slot == 0 || slot == 1) && frames >= 1, ERR_INVALID, "rans_encode: bad argument");
+  const int ns = n_channels * spc;                 // sub-streams per frame
+  const size_t per_frame = max_container_bytes((size_t)n_channels * L, ns);
+  if (frames == 1) frame_stride = host_cap;
+  CRA5_CHECK((size_t)frames * n_channels * L <= max_symbols_ && (size_t)frames * ns <= (size_t)max_streams_, ERR_INVALID,
              "rans_encode: tensor larger than the coder was sized for");
-  CRA5_CHECK(host_cap >= max_container_bytes((size_t)n_channels * L, n_streams), ERR_INVALID,
-             "rans_encode: output buffer too small");
-  const size_t head = CR5B_HEADER + 4 * (size_t)n_streams;
+  CRA5_CHECK((frame_stride & 3) == 0 && frame_stride >= per_frame && host_cap >= (frames - 1) * frame_stride + per_frame,
+             ERR_INVALID, "rans_encode: output buffer too small");
   const int count_max = (L + spc - 1) / spc;
   const int cap_words = 2 * count_max + 6;
-  CRA5_CHECK((size_t)n_streams * cap_words <= scratch_words_, ERR_INTERNAL, "rans_encode: scratch sizing");
-  if (n_streams == 0 || L == 0) return;
+  CRA5_CHECK((size_t)frames * ns * cap_words <= scratch_words_, ERR_INTERNAL, "rans_encode: scratch sizing");
+  if (ns == 0 || L == 0) return;
+  const int chan_mod = (idx == nullptr) ? n_channels : 0;   // EntropyBottleneck: CDF row = channel within the frame
   if (const Packed* pk = packed_for(st, tab))
-    rans_encode_smem(st, sym, idx, idx == nullptr, pk->data, pk->row_off, tab.length, tab.offset, pk->rows, pk->total,
-                     n_channels, L, spc, L, scratch_, cap_words, lengths_, offsets_, payload_, err_);
+    rans_encode_smem(st, sym, idx, chan_mod, pk->data, pk->row_off, tab.length, tab.offset, pk->rows, pk->total,
+                     frames * n_channels, L, spc, L, scratch_, cap_words, lengths_, offsets_, payload_, err_);
   else
-    rans_encode(st, sym, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, n_channels, L, spc, L > 0 ? L : 1,
+    rans_encode(st, sym, idx, chan_mod, tab.cdf, tab.cols, tab.length, tab.offset, frames * n_channels, L, spc, L > 0 ? L : 1,
                 scratch_, cap_words, lengths_, offsets_, payload_, err_);
-  uint8_t* out_dev = static_cast<uint8_t*>(device_alias(host_mapped)) + head;   // 4-byte aligned: head is
   count_launch();
   container_to_host_kernel<<<XFER_BLOCKS, XFER_THREADS, 0, st>>>(
-      lengths_, offsets_, err_, n_streams, reinterpret_cast<const uint32_t*>(payload_),
-      host_meta_dev_ + slot * meta_slot_words_, reinterpret_cast<uint32_t*>(out_dev));
+      lengths_, offsets_, err_, ns, frames, frame_stride / 4, reinterpret_cast<const uint32_t*>(payload_),
+      host_meta_dev_ + slot * meta_slot_words_, static_cast<uint32_t*>(device_alias(host_mapped)));
   CRA5_CUDA(cudaGetLastError());
 }
 
+// after the stream synchronisation: checks the error word, writes the 24-byte header of every frame's container and
+// stores the container sizes in sizes[frames]; returns the size of the first
 size_t RansCoder::encode_end(cudaStream_t st, int slot, int n_channels, int L, int spc, uint8_t* host_mapped,
-                             size_t host_cap) {
-  const int n_streams = n_channels * spc;
-  const size_t head = CR5B_HEADER + 4 * (size_t)n_streams;
+                             size_t host_cap, int frames, size_t frame_stride, size_t* sizes) {
+  const int ns = n_channels * spc;
+  const size_t head = CR5B_HEADER + 4 * (size_t)ns;
   uint32_t* meta = host_meta_ + slot * meta_slot_words_;
-  uint32_t total = 0;
-  if (n_streams > 0 && L > 0) {
-    if (meta[n_streams + 1] != 0) {
-      CRA5_CUDA(cudaMemsetAsync(err_, 0, sizeof(int), st));
-      throw Error(ERR_INTERNAL, "rans_encode: per-stream scratch overflow");
-    }
-    total = meta[n_streams];
-  } else {
-    for (int s = 0; s < n_streams; ++s) meta[s] = 0;
+  if (frames == 1) frame_stride = host_cap;
+  const bool coded = ns > 0 && L > 0;
+  if (coded && meta[frames] != 0) {
+    CRA5_CUDA(cudaMemsetAsync(err_, 0, sizeof(int), st));
+    throw Error(ERR_INTERNAL, "rans_encode: per-stream scratch overflow");
   }
-  CRA5_CHECK(host_cap >= head + total, ERR_INVALID, "rans_encode: output buffer too small");
-  memcpy(host_mapped, "CR5B", 4);
-  host_mapped[4] = 1;
-  host_mapped[5] = 0;
-  host_mapped[6] = host_mapped[7] = 0;
-  put_u32(host_mapped + 8, (uint32_t)n_channels);
-  put_u32(host_mapped + 12, (uint32_t)L);
-  put_u32(host_mapped + 16, (uint32_t)spc);
-  put_u32(host_mapped + 20, (uint32_t)n_streams);
-  memcpy(host_mapped + CR5B_HEADER, meta, (size_t)n_streams * 4);
-  return head + total;
+  size_t first = 0;
+  for (int f = 0; f < frames; ++f) {
+    uint8_t* c = host_mapped + (size_t)f * frame_stride;
+    const uint32_t total = coded ? meta[f] : 0;
+    CRA5_CHECK(frame_stride >= head + total, ERR_INVALID, "rans_encode: output buffer too small");
+    memcpy(c, "CR5B", 4);
+    c[4] = 1;
+    c[5] = 0;
+    c[6] = c[7] = 0;
+    put_u32(c + 8, (uint32_t)n_channels);
+    put_u32(c + 12, (uint32_t)L);
+    put_u32(c + 16, (uint32_t)spc);
+    put_u32(c + 20, (uint32_t)ns);
+    if (!coded) memset(c + CR5B_HEADER, 0, (size_t)ns * 4);
+    if (sizes != nullptr) sizes[f] = head + total;
+    if (f == 0) first = head + total;
+  }
+  return first;
 }
 
 void RansCoder::decode(cudaStream_t st, const uint8_t* bytes, size_t len, const uint8_t* idx, const CdfTable& tab,
@@ -235,8 +250,8 @@ void RansCoder::decode(cudaStream_t st, const uint8_t* bytes, size_t len, const 
     offs[1] = (uint32_t)len;
     CRA5_CUDA(cudaMemcpyAsync(payload_, host_stage_, len, cudaMemcpyHostToDevice, st));
     CRA5_CUDA(cudaMemcpyAsync(offsets_, offs, 8, cudaMemcpyHostToDevice, st));
-    rans_decode(st, payload_, offsets_, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, nullptr, 0, 1,
-                (int)n, 1, L > 0 ? L : 1, sym_out, mu, median, val_out, err_);
+    rans_decode(st, payload_, offsets_, idx, idx == nullptr ? (n_channels > 0 ? n_channels : 1) : 0, tab.cdf, tab.cols,
+                tab.length, tab.offset, nullptr, 0, 1, (int)n, 1, L > 0 ? L : 1, sym_out, mu, median, val_out, err_);
     CRA5_CUDA(cudaMemcpyAsync(host_meta_, err_, 4, cudaMemcpyDeviceToHost, st));
     CRA5_CUDA(cudaStreamSynchronize(st));
     if (host_meta_[0] != 0) {
@@ -245,51 +260,75 @@ void RansCoder::decode(cudaStream_t st, const uint8_t* bytes, size_t len, const 
     }
     return;
   }
-  if (decode_cr5b(st, bytes, len, idx, tab, n_channels, L, sym_out, mu, median, val_out, 0, true)) decode_finish(st);
+  if (decode_cr5b(st, &bytes, &len, 1, idx, tab, n_channels, L, sym_out, mu, median, val_out, 0, true, 0)) decode_finish(st);
 }
 
-// CR5B container -> device: validates the header, stages lengths + payload in the pinned buffer at `stage_off` (a
-// multiple of 16) and enqueues the upload, the length scan and the decode kernel. Returns false when there is nothing
-// to decode (no GPU work enqueued). With sync_before the stream is drained first, because the staging buffer may still
-// be in flight from a previous call; a caller that stages two containers at disjoint offsets inside one call passes
-// false for the second (Model::bin_to_latent). Errors found by the kernels are collected by decode_finish().
-bool RansCoder::decode_cr5b(cudaStream_t st, const uint8_t* bytes, size_t len, const uint8_t* idx, const CdfTable& tab,
-                            int n_channels, int L, int32_t* sym_out, const float* mu, const float* median,
-                            float* val_out, size_t stage_off, bool sync_before) {
+// CR5B containers of `frames` tensors (n_channels x L symbols each, all with the same sub-stream count) -> device:
+// validates every header, stages the length tables of all frames followed by their payloads in the pinned buffer at
+// `stage_off` (a multiple of 16) and enqueues ONE upload, ONE length scan and ONE decode launch for the whole batch.
+// Outputs are [frames][n_channels][L]; with per-symbol means, frame f reads mu[pos + f * mu_frame_extra]. Returns false
+// when there is nothing to decode (no GPU work enqueued). With sync_before the stream is drained first, because the
+// staging buffer may still be in flight from a previous call; a caller that stages two batches at disjoint offsets
+// inside one call passes false for the second (Model::bin_to_latent). Errors found by the kernels are collected by
+// decode_finish().
+bool RansCoder::decode_cr5b(cudaStream_t st, const uint8_t* const* bytes, const size_t* lens, int frames,
+                            const uint8_t* idx, const CdfTable& tab, int n_channels, int L, int32_t* sym_out,
+                            const float* mu, const float* median, float* val_out, size_t stage_off, bool sync_before,
+                            size_t mu_frame_extra) {
   CRA5_CHECK(tab.ready(), ERR_STATE, "Uninitialized CDFs. Run update() first");
-  CRA5_CHECK(bytes != nullptr && len >= 8 && memcmp(bytes, "CR5B", 4) == 0, ERR_BITSTREAM, "bitstream: not a CR5B container");
-  CRA5_CHECK((stage_off & 15) == 0, ERR_INTERNAL, "decode: staging offset");
-  CRA5_CHECK(len >= CR5B_HEADER, ERR_BITSTREAM, "bitstream: truncated header");
-  CRA5_CHECK(bytes[4] == 1, ERR_BITSTREAM, "bitstream: unsupported version");
-  const uint32_t nc = get_u32(bytes + 8), l = get_u32(bytes + 12), spc = get_u32(bytes + 16),
-                 ns = get_u32(bytes + 20);
-  CRA5_CHECK(nc == (uint32_t)n_channels && l == (uint32_t)L, ERR_BITSTREAM,
-             "bitstream: tensor shape does not match the model");
-  CRA5_CHECK(spc >= 1 && spc <= (uint32_t)CR5B_MAX_SPC && ns == nc * spc, ERR_BITSTREAM, "bitstream: bad stream count");
-  CRA5_CHECK((size_t)nc * l <= max_symbols_ && (int)ns <= max_streams_, ERR_BITSTREAM, "bitstream: too large");
-  const size_t head = CR5B_HEADER + 4 * (size_t)ns;
-  CRA5_CHECK(len >= head, ERR_BITSTREAM, "bitstream: truncated length table");
-  uint64_t total = 0;
-  for (uint32_t s = 0; s < ns; ++s) {
-    const uint32_t ls = get_u32(bytes + CR5B_HEADER + 4 * (size_t)s);
-    CRA5_CHECK((ls & 3) == 0 && (l == 0 || ls >= 8), ERR_BITSTREAM, "bitstream: bad sub-stream length");
-    total += ls;
+  CRA5_CHECK((stage_off & 15) == 0 && frames >= 1, ERR_INTERNAL, "decode: staging offset / frames");
+  uint32_t spc = 0, ns = 0;
+  uint64_t total_all = 0;
+  for (int f = 0; f < frames; ++f) {
+    const uint8_t* b = bytes[f];
+    const size_t len = lens[f];
+    CRA5_CHECK(b != nullptr && len >= 8 && memcmp(b, "CR5B", 4) == 0, ERR_BITSTREAM, "bitstream: not a CR5B container");
+    CRA5_CHECK(len >= CR5B_HEADER, ERR_BITSTREAM, "bitstream: truncated header");
+    CRA5_CHECK(b[4] == 1, ERR_BITSTREAM, "bitstream: unsupported version");
+    const uint32_t nc = get_u32(b + 8), l = get_u32(b + 12), spc_f = get_u32(b + 16), ns_f = get_u32(b + 20);
+    CRA5_CHECK(nc == (uint32_t)n_channels && l == (uint32_t)L, ERR_BITSTREAM,
+               "bitstream: tensor shape does not match the model");
+    CRA5_CHECK(spc_f >= 1 && spc_f <= (uint32_t)CR5B_MAX_SPC && ns_f == nc * spc_f, ERR_BITSTREAM, "bitstream: bad stream count");
+    if (f == 0) { spc = spc_f; ns = ns_f; }
+    CRA5_CHECK(spc_f == spc, ERR_BITSTREAM, "bitstream: the containers of one batch must share their sub-stream count");
+    const size_t head = CR5B_HEADER + 4 * (size_t)ns;
+    CRA5_CHECK(len >= head, ERR_BITSTREAM, "bitstream: truncated length table");
+    uint64_t total = 0;
+    for (uint32_t s = 0; s < ns; ++s) {
+      const uint32_t ls = get_u32(b + CR5B_HEADER + 4 * (size_t)s);
+      CRA5_CHECK((ls & 3) == 0 && (l == 0 || ls >= 8), ERR_BITSTREAM, "bitstream: bad sub-stream length");
+      total += ls;
+    }
+    CRA5_CHECK(head + total == len, ERR_BITSTREAM, "bitstream: payload size mismatch");
+    total_all += total;
   }
-  CRA5_CHECK(head + total == len, ERR_BITSTREAM, "bitstream: payload size mismatch");
-  if (ns == 0 || l == 0) return false;
-  CRA5_CHECK(total <= payload_cap_ && stage_off + len <= host_stage_cap_, ERR_BITSTREAM, "bitstream: too large");
+  CRA5_CHECK((size_t)frames * n_channels * L <= max_symbols_ && (size_t)frames * ns <= (size_t)max_streams_, ERR_BITSTREAM,
+             "bitstream: too large");
+  if (ns == 0 || L == 0) return false;
+  const size_t table_bytes = (size_t)frames * ns * 4;
+  CRA5_CHECK(total_all <= payload_cap_ && stage_off + table_bytes + total_all <= host_stage_cap_, ERR_BITSTREAM,
+             "bitstream: too large");
   if (sync_before) CRA5_CUDA(cudaStreamSynchronize(st));  // the staging buffer may still be in flight from a previous call
-  memcpy(host_stage_ + stage_off, bytes + CR5B_HEADER, len - CR5B_HEADER);
+  uint8_t* stage = host_stage_ + stage_off;
+  size_t pay = table_bytes;
+  for (int f = 0; f < frames; ++f) {
+    const size_t head = CR5B_HEADER + 4 * (size_t)ns;
+    memcpy(stage + (size_t)f * ns * 4, bytes[f] + CR5B_HEADER, (size_t)ns * 4);
+    memcpy(stage + pay, bytes[f] + head, lens[f] - head);
+    pay += lens[f] - head;
+  }
+  const int ns_all = frames * (int)ns, nc_all = frames * n_channels;
   count_launch();
   container_from_host_kernel<<<XFER_BLOCKS, XFER_THREADS, 0, st>>>(
-      reinterpret_cast<const uint32_t*>(host_stage_dev_ + stage_off), (int)ns, (uint32_t)(ns + total / 4), lengths_,
+      reinterpret_cast<const uint32_t*>(host_stage_dev_ + stage_off), ns_all, (uint32_t)(ns_all + total_all / 4), lengths_,
       reinterpret_cast<uint32_t*>(payload_));
   CRA5_CUDA(cudaGetLastError());
-  scan_lengths(st, lengths_, (int)ns, offsets_);
+  scan_lengths(st, lengths_, ns_all, offsets_);
+  const int chan_mod = (idx == nullptr) ? n_channels : 0;
   if (const Packed* pk = packed_for(st, tab)) {
-    rans_decode_smem(st, payload_, offsets_, idx, idx == nullptr, pk->data, pk->row_off, tab.length, tab.offset,
-                     pk->has_lut ? pk->lut : nullptr, pk->rows, pk->total, n_channels, L, (int)spc, L, sym_out, mu, median,
-                     val_out, err_);
+    rans_decode_smem(st, payload_, offsets_, idx, chan_mod, pk->data, pk->row_off, tab.length, tab.offset,
+                     pk->has_lut ? pk->lut : nullptr, pk->rows, pk->total, nc_all, L, (int)spc, L, sym_out, mu, median,
+                     val_out, err_, n_channels, mu_frame_extra);
   } else {
     // wide tables (GaussianConditional: up to 3133 entries per row) get a coarse inverse table; the per-channel
     // EntropyBottleneck rows are a few dozen entries and are searched directly
@@ -304,8 +343,8 @@ bool RansCoder::decode_cr5b(cudaStream_t st, const uint8_t* bytes, size_t len, c
       lut = lut_;
       lut_rows = tab.rows;
     }
-    rans_decode(st, payload_, offsets_, idx, idx == nullptr, tab.cdf, tab.cols, tab.length, tab.offset, lut, lut_rows,
-                n_channels, L, (int)spc, L > 0 ? L : 1, sym_out, mu, median, val_out, err_);
+    rans_decode(st, payload_, offsets_, idx, chan_mod, tab.cdf, tab.cols, tab.length, tab.offset, lut, lut_rows, nc_all, L,
+                (int)spc, L > 0 ? L : 1, sym_out, mu, median, val_out, err_, n_channels, mu_frame_extra);
   }
   return true;
 }

@@ -36,18 +36,23 @@ class RansCoder {
   // max_container_bytes() large): encode_begin only enqueues work -- the kernels write lengths and payload straight
   // into host memory -- so several tensors share ONE stream synchronisation; after it, encode_end checks the error
   // word, writes the header and returns the container size. slot (0 or 1) selects the metadata slot.
+  // A batch of `frames` tensors ([frames][n_channels][L]) is ONE launch of every kernel; frame f's container lands at
+  // host_mapped + f * frame_stride and its size in sizes[f].
   void encode_begin(cudaStream_t st, int slot, const int32_t* sym, const uint8_t* idx, const CdfTable& tab,
-                    int n_channels, int L, int spc, uint8_t* host_mapped, size_t host_cap);
-  size_t encode_end(cudaStream_t st, int slot, int n_channels, int L, int spc, uint8_t* host_mapped, size_t host_cap);
+                    int n_channels, int L, int spc, uint8_t* host_mapped, size_t host_cap, int frames = 1,
+                    size_t frame_stride = 0);
+  size_t encode_end(cudaStream_t st, int slot, int n_channels, int L, int spc, uint8_t* host_mapped, size_t host_cap,
+                    int frames = 1, size_t frame_stride = 0, size_t* sizes = nullptr);
   // container in host memory -> symbols and/or dequantised values on the device
   void invalidate_lut() { lut_for_ = nullptr; lut_rows_ = 0; packed_[0].key = packed_[1].key = nullptr; }
   void decode(cudaStream_t st, const uint8_t* bytes, size_t len, const uint8_t* idx, const CdfTable& tab,
               int n_channels, int L, int32_t* sym_out, const float* mu, const float* median, float* val_out);
   // the two halves of decode() for CR5B containers: enqueue only (false: nothing to decode) / one synchronisation + the
   // kernels' error word. Several containers staged at disjoint, 16-byte aligned offsets can share one decode_finish().
-  bool decode_cr5b(cudaStream_t st, const uint8_t* bytes, size_t len, const uint8_t* idx, const CdfTable& tab,
-                   int n_channels, int L, int32_t* sym_out, const float* mu, const float* median, float* val_out,
-                   size_t stage_off, bool sync_before);
+  // `frames` containers (same sub-stream count) decode in one launch into [frames][n_channels][L] outputs.
+  bool decode_cr5b(cudaStream_t st, const uint8_t* const* bytes, const size_t* lens, int frames, const uint8_t* idx,
+                   const CdfTable& tab, int n_channels, int L, int32_t* sym_out, const float* mu, const float* median,
+                   float* val_out, size_t stage_off, bool sync_before, size_t mu_frame_extra);
   void decode_finish(cudaStream_t st);
   void reset_error(cudaStream_t st);
   size_t stage_capacity() const { return host_stage_cap_; }

@@ -33,18 +33,27 @@ __device__ __forceinline__ int scale_index(float sigma, const float* __restrict_
 __global__ void __launch_bounds__(256)
 gc_quantize_index_kernel(const float* __restrict__ y, const float* __restrict__ sigma, const float* __restrict__ mu,
                          const float* __restrict__ scale_table, int levels, float bound, int32_t* __restrict__ sym,
-                         uint8_t* __restrict__ idx, float* __restrict__ y_hat, size_t n) {
+                         uint8_t* __restrict__ idx, float* __restrict__ y_hat, size_t n, int frames,
+                         size_t param_stride) {
   __shared__ float tab[256];
   if (scale_table != nullptr)   // only needed for the index output; callers that want symbols / y_hat alone pass null
     for (int i = threadIdx.x; i < levels; i += blockDim.x) tab[i] = scale_table[i];
   __syncthreads();
   const size_t n4 = n >> 2;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (size_t)gridDim.x * blockDim.x) {
+  // frames > 1 (host guarantees n % 4 == 0 and param_stride % 4 == 0): element group g of the batch lives at e = g in
+  // the per-frame-contiguous tensors (y, sym, idx, y_hat) and at ep = frame * param_stride / 4 + g % n4 in sigma / mu
+  const size_t total4 = n4 * (size_t)frames;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total4; e += (size_t)gridDim.x * blockDim.x) {
+    size_t ep = e;
+    if (frames > 1) {
+      const size_t f = e / n4;
+      ep = f * (param_stride >> 2) + (e - f * n4);
+    }
     int4 s = make_int4(0, 0, 0, 0);
     float4 mv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (y != nullptr) {
       const float4 yv = reinterpret_cast<const float4*>(y)[e];
-      mv = reinterpret_cast<const float4*>(mu)[e];
+      mv = reinterpret_cast<const float4*>(mu)[ep];
       s.x = __float2int_rn(__fsub_rn(yv.x, mv.x));
       s.y = __float2int_rn(__fsub_rn(yv.y, mv.y));
       s.z = __float2int_rn(__fsub_rn(yv.z, mv.z));
@@ -52,7 +61,7 @@ gc_quantize_index_kernel(const float* __restrict__ y, const float* __restrict__ 
       if (sym != nullptr) reinterpret_cast<int4*>(sym)[e] = s;
     }
     if (idx != nullptr) {
-      const float4 sv = reinterpret_cast<const float4*>(sigma)[e];
+      const float4 sv = reinterpret_cast<const float4*>(sigma)[ep];
       uchar4 q;
       q.x = (unsigned char)scale_index(sv.x, tab, levels, bound);
       q.y = (unsigned char)scale_index(sv.y, tab, levels, bound);
@@ -64,8 +73,8 @@ gc_quantize_index_kernel(const float* __restrict__ y, const float* __restrict__ 
       reinterpret_cast<float4*>(y_hat)[e] = make_float4(__fadd_rn((float)s.x, mv.x), __fadd_rn((float)s.y, mv.y),
                                                        __fadd_rn((float)s.z, mv.z), __fadd_rn((float)s.w, mv.w));
   }
-  // tail
-  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+  // tail (single frame only)
+  if (frames == 1 && blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const size_t e = (n4 << 2) + threadIdx.x;
     if (y != nullptr) {
       const int s = __float2int_rn(__fsub_rn(y[e], mu[e]));
@@ -77,36 +86,44 @@ gc_quantize_index_kernel(const float* __restrict__ y, const float* __restrict__ 
 }
 
 void gc_quantize_index(cudaStream_t st, const float* y, const float* sigma, const float* mu, const float* scale_table,
-                       int levels, float bound, int32_t* sym, uint8_t* idx, float* y_hat, size_t n) {
+                       int levels, float bound, int32_t* sym, uint8_t* idx, float* y_hat, size_t n, int frames,
+                       size_t param_stride) {
   CRA5_CHECK(levels >= 1 && levels <= 256, ERR_INVALID, "scale table must have 1..256 levels");
   CRA5_CHECK(idx == nullptr || (scale_table != nullptr && sigma != nullptr), ERR_INVALID,
              "gc_quantize_index: the index output needs sigma and the scale table");
   CRA5_CHECK(y == nullptr || mu != nullptr, ERR_INVALID, "gc_quantize_index: y needs mu");
+  CRA5_CHECK(frames >= 1, ERR_INVALID, "gc_quantize_index: frames");
+  CRA5_CHECK(frames == 1 || ((n & 3) == 0 && (param_stride & 3) == 0), ERR_INVALID,
+             "gc_quantize_index: batched launches need element counts that are multiples of 4");
   if (n == 0) return;
-  const int blocks = (int)std::min<size_t>(((n >> 2) + 255) / 256 + 1, 148 * 8);
+  const size_t n_all = n * (size_t)frames;
+  const int blocks = (int)std::min<size_t>(((n_all >> 2) + 255) / 256 + 1, 148 * 8);
   // algorithmic bytes: read y, sigma, mu (12 B) + write int32 symbol and uint8 index (5 B) per element
   LaunchScope scope(st, "gc_quantize_index", 0.0,
-                    (double)n * ((y ? 8.0 : 0.0) + (idx ? 5.0 : 0.0) + (sym ? 4.0 : 0.0) + (y_hat ? 4.0 : 0.0)));
-  gc_quantize_index_kernel<<<blocks, 256, 0, st>>>(y, sigma, mu, scale_table, levels, bound, sym, idx, y_hat, n);
+                    (double)n_all * ((y ? 8.0 : 0.0) + (idx ? 5.0 : 0.0) + (sym ? 4.0 : 0.0) + (y_hat ? 4.0 : 0.0)));
+  gc_quantize_index_kernel<<<blocks, 256, 0, st>>>(y, sigma, mu, scale_table, levels, bound, sym, idx, y_hat, n, frames,
+                                                   param_stride);
   CRA5_CUDA(cudaGetLastError());
 }
 
 // EntropyBottleneck: per-channel median, index == channel (entropy_models.py:529-542, 513-523)
-__global__ void eb_quantize_kernel(const float* __restrict__ z, const float* __restrict__ median, int L,
+__global__ void eb_quantize_kernel(const float* __restrict__ z, const float* __restrict__ median, int L, int n_ch,
                                    int32_t* __restrict__ sym, float* __restrict__ z_hat, size_t n) {
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
-    const float m = median[e / L];
+    const float m = median[(e / L) % n_ch];
     const int s = __float2int_rn(__fsub_rn(z[e], m));
     if (sym != nullptr) sym[e] = s;
     if (z_hat != nullptr) z_hat[e] = __fadd_rn((float)s, m);
   }
 }
 
-void eb_quantize(cudaStream_t st, const float* z, const float* median, int L, int32_t* sym, float* z_hat, size_t n) {
+void eb_quantize(cudaStream_t st, const float* z, const float* median, int L, int n_ch, int32_t* sym, float* z_hat,
+                 size_t n) {
   if (n == 0) return;
+  CRA5_CHECK(L > 0 && n_ch > 0, ERR_INVALID, "eb_quantize: sizes");
   const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
   LaunchScope scope(st, "eb_quantize", 0.0, (double)n * 12.0);
-  eb_quantize_kernel<<<blocks, 256, 0, st>>>(z, median, L, sym, z_hat, n);
+  eb_quantize_kernel<<<blocks, 256, 0, st>>>(z, median, L, n_ch, sym, z_hat, n);
   CRA5_CUDA(cudaGetLastError());
 }
 
@@ -272,7 +289,7 @@ rans_encode_kernel(const int32_t* __restrict__ sym, const uint8_t* __restrict__ 
       const int i = max(i0 - 1 - b, 0);
       pos[b] = base + (size_t)i * spc;
       sy[b] = sym[pos[b]];
-      ci[b] = index_is_channel ? (int)(pos[b] / (size_t)chan_len) : (int)idx[pos[b]];
+      ci[b] = index_is_channel ? (int)((pos[b] / (size_t)chan_len) % (size_t)index_is_channel) : (int)idx[pos[b]];
     }
 #pragma unroll
     for (int b = 0; b < RANS_BATCH; ++b) {
@@ -374,14 +391,14 @@ __global__ void __launch_bounds__(256) compact_streams_kernel(const uint32_t* __
   for (uint32_t w = lane; w < words; w += 32) dst[w] = src[w];
 }
 
-void rans_encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx, bool index_is_channel, const int32_t* cdf,
+void rans_encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx, int chan_mod, const int32_t* cdf,
                  int cdf_stride, const int32_t* cdf_len, const int32_t* offset, int n_channels, int L, int spc, int chan_len,
                  uint32_t* scratch, int cap_words, uint32_t* lengths, uint32_t* offsets, uint8_t* payload, int* err) {
   const int n_streams = n_channels * spc;
   if (n_streams == 0) return;
   {
-    LaunchScope scope(st, "rans_encode", 0.0, (double)n_channels * L * (index_is_channel ? 4.0 : 5.0));
-    rans_encode_kernel<<<(n_streams + RANS_THREADS - 1) / RANS_THREADS, RANS_THREADS, 0, st>>>(sym, idx, index_is_channel ? 1 : 0, cdf, cdf_stride,
+    LaunchScope scope(st, "rans_encode", 0.0, (double)n_channels * L * (chan_mod ? 4.0 : 5.0));
+    rans_encode_kernel<<<(n_streams + RANS_THREADS - 1) / RANS_THREADS, RANS_THREADS, 0, st>>>(sym, idx, chan_mod, cdf, cdf_stride,
                                                                 cdf_len, offset, n_channels, L, spc, chan_len,
                                                                 scratch, cap_words, lengths, err);
   }
@@ -454,7 +471,8 @@ rans_decode_kernel(const uint8_t* __restrict__ payload, const uint32_t* __restri
                    int cdf_stride, const int32_t* __restrict__ cdf_len, const int32_t* __restrict__ offset,
                    const uint16_t* __restrict__ lut_g, int lut_rows, int n_channels, int L, int spc, int chan_len,
                    int32_t* __restrict__ sym_out, const float* __restrict__ mu, const float* __restrict__ median,
-                   float* __restrict__ val_out, int* __restrict__ err) {
+                   float* __restrict__ val_out, int* __restrict__ err, int ch_per_frame,
+                   size_t mu_frame_extra) {
   extern __shared__ uint16_t lut_s[];
   const uint16_t* lut = lut_g;
   if (lut_g != nullptr && lut_rows > 0) {  // lut_rows > 0: stage the table in shared memory
@@ -474,6 +492,7 @@ rans_decode_kernel(const uint8_t* __restrict__ payload, const uint32_t* __restri
     const uint32_t lo = d.next(), hi = d.next();
     d.x = (uint64_t)lo | ((uint64_t)hi << 32);
   }
+  const size_t mu_extra = (size_t)(c / ch_per_frame) * mu_frame_extra;   // batch: per-frame mu blocks are further apart
   const size_t base = (size_t)c * L + k;
   for (int i0 = 0; i0 < count; i0 += RANS_BATCH) {
     int ci[RANS_BATCH];
@@ -483,8 +502,8 @@ rans_decode_kernel(const uint8_t* __restrict__ payload, const uint32_t* __restri
     for (int b = 0; b < RANS_BATCH; ++b) {  // independent loads first
       const int i = min(i0 + b, count - 1);
       const size_t pos = base + (size_t)i * spc;
-      ci[b] = index_is_channel ? (int)(pos / (size_t)chan_len) : (int)idx[pos];
-      mean[b] = (val_out == nullptr) ? 0.f : ((mu != nullptr) ? mu[pos] : median[ci[b]]);
+      ci[b] = index_is_channel ? (int)((pos / (size_t)chan_len) % (size_t)index_is_channel) : (int)idx[pos];
+      mean[b] = (val_out == nullptr) ? 0.f : ((mu != nullptr) ? mu[pos + mu_extra] : median[ci[b]]);
     }
 #pragma unroll
     for (int b = 0; b < RANS_BATCH; ++b) {
@@ -545,9 +564,10 @@ rans_decode_kernel(const uint8_t* __restrict__ payload, const uint32_t* __restri
 }
 
 void rans_decode(cudaStream_t st, const uint8_t* payload, const uint32_t* offsets, const uint8_t* idx,
-                 bool index_is_channel, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len,
+                 int chan_mod, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len,
                  const int32_t* offset, const uint16_t* lut, int lut_rows, int n_channels, int L, int spc,
-                 int chan_len, int32_t* sym_out, const float* mu, const float* median, float* val_out, int* err) {
+                 int chan_len, int32_t* sym_out, const float* mu, const float* median, float* val_out, int* err, int ch_per_frame,
+                 size_t mu_frame_extra) {
   const int n_streams = n_channels * spc;
   if (n_streams == 0) return;
   size_t smem = 0;
@@ -556,10 +576,10 @@ void rans_decode(cudaStream_t st, const uint8_t* payload, const uint32_t* offset
     stage_rows = lut_rows;
     smem = (size_t)lut_rows * RANS_LUT * 2;
   }
-  LaunchScope scope(st, "rans_decode", 0.0, (double)n_channels * L * (index_is_channel ? 4.0 : 9.0));
+  LaunchScope scope(st, "rans_decode", 0.0, (double)n_channels * L * (chan_mod ? 4.0 : 9.0));
   rans_decode_kernel<<<(n_streams + RANS_THREADS - 1) / RANS_THREADS, RANS_THREADS, smem, st>>>(
-      payload, offsets, idx, index_is_channel ? 1 : 0, cdf, cdf_stride, cdf_len, offset, lut, stage_rows, n_channels, L,
-      spc, chan_len, sym_out, mu, median, val_out, err);
+      payload, offsets, idx, chan_mod, cdf, cdf_stride, cdf_len, offset, lut, stage_rows, n_channels, L,
+      spc, chan_len, sym_out, mu, median, val_out, err, ch_per_frame > 0 ? ch_per_frame : (1 << 30), mu_frame_extra);
   CRA5_CUDA(cudaGetLastError());
 }
 
@@ -665,7 +685,7 @@ rans_encode_smem_kernel(const int32_t* __restrict__ sym, const uint8_t* __restri
       const int i = max(i0 - 1 - b, 0);
       const size_t pos = base + (size_t)i * spc;
       sy[b] = sym[pos];
-      ci[b] = index_is_channel ? c : (int)idx[pos];
+      ci[b] = index_is_channel ? (c % index_is_channel) : (int)idx[pos];
     }
   };
   gather(count);
@@ -751,7 +771,7 @@ rans_decode_smem_kernel(const uint8_t* __restrict__ payload, const uint32_t* __r
                         const int32_t* __restrict__ offset, const uint16_t* __restrict__ lut_g, int rows, int total,
                         int n_channels, int L, int spc, int chan_len, int32_t* __restrict__ sym_out,
                         const float* __restrict__ mu, const float* __restrict__ median, float* __restrict__ val_out,
-                        int* __restrict__ err) {
+                        int* __restrict__ err, int ch_per_frame, size_t mu_frame_extra) {
   extern __shared__ __align__(16) uint8_t tab_smem[];
   const SmemTables T = stage_tables(tab_smem, packed, row_off, cdf_len, offset, lut_g, rows, total);
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -765,7 +785,8 @@ rans_decode_smem_kernel(const uint8_t* __restrict__ payload, const uint32_t* __r
     d.x = (uint64_t)lo | ((uint64_t)hi << 32);
   }
   const size_t base = (size_t)c * L + k;
-  const float med = (val_out != nullptr && mu == nullptr) ? median[c] : 0.f;
+  const float med = (val_out != nullptr && mu == nullptr) ? median[index_is_channel ? c % index_is_channel : c] : 0.f;
+  const size_t mu_extra = (size_t)(c / ch_per_frame) * mu_frame_extra;   // batch: per-frame mu blocks are further apart
   int ci[RANS_BATCH], ci_n[RANS_BATCH];
   float mean[RANS_BATCH], mean_n[RANS_BATCH];
   auto gather = [&](int i0, int (&cc)[RANS_BATCH], float (&mm)[RANS_BATCH]) {
@@ -773,8 +794,8 @@ rans_decode_smem_kernel(const uint8_t* __restrict__ payload, const uint32_t* __r
     for (int b = 0; b < RANS_BATCH; ++b) {
       const int i = min(i0 + b, count - 1);
       const size_t pos = base + (size_t)i * spc;
-      cc[b] = index_is_channel ? c : (int)idx[pos];
-      mm[b] = (val_out == nullptr) ? 0.f : ((mu != nullptr) ? mu[pos] : med);
+      cc[b] = index_is_channel ? (c % index_is_channel) : (int)idx[pos];
+      mm[b] = (val_out == nullptr) ? 0.f : ((mu != nullptr) ? mu[pos + mu_extra] : med);
     }
   };
   gather(0, ci, mean);
@@ -860,7 +881,7 @@ bool rans_tables_fit(int rows, int total, bool with_lut) {
   return smem_tables_bytes(rows, total, with_lut) <= 200 * 1024;
 }
 
-void rans_encode_smem(cudaStream_t st, const int32_t* sym, const uint8_t* idx, bool index_is_channel,
+void rans_encode_smem(cudaStream_t st, const int32_t* sym, const uint8_t* idx, int chan_mod,
                       const uint16_t* packed, const int32_t* row_off, const int32_t* cdf_len, const int32_t* offset,
                       int rows, int total, int n_channels, int L, int spc, int chan_len, uint32_t* scratch, int cap_words,
                       uint32_t* lengths, uint32_t* offsets, uint8_t* payload, int* err) {
@@ -869,9 +890,9 @@ void rans_encode_smem(cudaStream_t st, const int32_t* sym, const uint8_t* idx, b
   const size_t smem = smem_tables_bytes(rows, total, false);
   if (smem > 48 * 1024) ensure_dynamic_smem(rans_encode_smem_kernel, 200 * 1024);
   {
-    LaunchScope scope(st, "rans_encode", 0.0, (double)n_channels * L * (index_is_channel ? 4.0 : 5.0));
+    LaunchScope scope(st, "rans_encode", 0.0, (double)n_channels * L * (chan_mod ? 4.0 : 5.0));
     rans_encode_smem_kernel<<<(n_streams + RANS_STHREADS - 1) / RANS_STHREADS, RANS_STHREADS, smem, st>>>(
-        sym, idx, index_is_channel ? 1 : 0, packed, row_off, cdf_len, offset, rows, total, n_channels, L, spc, chan_len,
+        sym, idx, chan_mod, packed, row_off, cdf_len, offset, rows, total, n_channels, L, spc, chan_len,
         scratch, cap_words, lengths, err);
   }
   CRA5_CUDA(cudaGetLastError());
@@ -887,17 +908,18 @@ void rans_encode_smem(cudaStream_t st, const int32_t* sym, const uint8_t* idx, b
 }
 
 void rans_decode_smem(cudaStream_t st, const uint8_t* payload, const uint32_t* offsets, const uint8_t* idx,
-                      bool index_is_channel, const uint16_t* packed, const int32_t* row_off, const int32_t* cdf_len,
+                      int chan_mod, const uint16_t* packed, const int32_t* row_off, const int32_t* cdf_len,
                       const int32_t* offset, const uint16_t* lut, int rows, int total, int n_channels, int L, int spc,
-                      int chan_len, int32_t* sym_out, const float* mu, const float* median, float* val_out, int* err) {
+                      int chan_len, int32_t* sym_out, const float* mu, const float* median, float* val_out, int* err, int ch_per_frame,
+                 size_t mu_frame_extra) {
   const int n_streams = n_channels * spc;
   if (n_streams == 0) return;
   const size_t smem = smem_tables_bytes(rows, total, lut != nullptr);
   if (smem > 48 * 1024) ensure_dynamic_smem(rans_decode_smem_kernel, 200 * 1024);
-  LaunchScope scope(st, "rans_decode", 0.0, (double)n_channels * L * (index_is_channel ? 4.0 : 9.0));
+  LaunchScope scope(st, "rans_decode", 0.0, (double)n_channels * L * (chan_mod ? 4.0 : 9.0));
   rans_decode_smem_kernel<<<(n_streams + RANS_STHREADS - 1) / RANS_STHREADS, RANS_STHREADS, smem, st>>>(
-      payload, offsets, idx, index_is_channel ? 1 : 0, packed, row_off, cdf_len, offset, lut, rows, total, n_channels, L,
-      spc, chan_len, sym_out, mu, median, val_out, err);
+      payload, offsets, idx, chan_mod, packed, row_off, cdf_len, offset, lut, rows, total, n_channels, L,
+      spc, chan_len, sym_out, mu, median, val_out, err, ch_per_frame > 0 ? ch_per_frame : (1 << 30), mu_frame_extra);
   CRA5_CUDA(cudaGetLastError());
 }
 

@@ -38,6 +38,8 @@ struct GemmShape {
   int pe_box_rows;  // tokens per TMA box (divides tokens-per-row and 128)
   int pe_Wp;        // tokens per patch row
   int pe_sh;        // vertical stride in pixels
+  int pe_Hg;        // patch rows per frame and pixel rows per frame: token row i of a batch maps to frame i / pe_Hg,
+  int pe_img_h;     //   pixel row pe_sh * (i % pe_Hg) + (i / pe_Hg) * pe_img_h   (pe_Hg <= 0: single frame)
   // A_CONCAT
   int cc_D;      // split point in K (multiple of 64)
   int cc_shift;  // row shift for the second half
@@ -132,6 +134,11 @@ struct EpiParams {
   const float* bias;      // [N] or null
   const float* add;       // EPI_F32: extra addend [M, lda] (pos-embed), or null
   int lda;
+  int add_period;         // > 0: the addend has add_period rows and repeats down the batch (row % add_period)
+  // batches of frames (rows = frame * rows_per_frame + r): EPI_T_F32 / EPI_PIXSHUF / EPI_CONVT write frame b of the
+  // output at out_f32 + b * fr_stride; fr_rows = rows per frame (<= 0: a single frame)
+  int fr_rows;
+  size_t fr_stride;
   float* out_f32;
   __nv_bfloat16* out_bf16;
   int ldo;                // row stride of out (elements)
@@ -187,7 +194,7 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
   if constexpr (KIND == EPI_F32) {
     float* o = p.out_f32 + (size_t)row * p.ldo + col0;
     if (p.add != nullptr) {
-      const float* a = p.add + (size_t)row * p.lda + col0;
+      const float* a = p.add + (size_t)(p.add_period > 0 ? row % p.add_period : row) * p.lda + col0;
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (col0 + i < N) v[i] += __ldg(a + i);
@@ -298,22 +305,41 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
         if (col0 + i < N) ob[i] = __float2bfloat16(v[i]);
     }
   } else if constexpr (KIND == EPI_T_F32) {
+    float* o = p.out_f32 + row;
+    if (p.fr_rows > 0) {   // batch: frame b's [N][ldo] matrix starts at b * fr_stride
+      const int b = row / p.fr_rows;
+      o = p.out_f32 + (size_t)b * p.fr_stride + (row - b * p.fr_rows);
+    }
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-      if (col0 + i < N) p.out_f32[(size_t)(col0 + i) * p.ldo + row] = v[i];
+      if (col0 + i < N) o[(size_t)(col0 + i) * p.ldo] = v[i];
   } else if constexpr (KIND == EPI_PIXSHUF) {
-    const int i_ = row / p.ps_Wh, j_ = row - i_ * p.ps_Wh;
+    int rf = row;
+    float* outb = p.out_f32;
+    if (p.fr_rows > 0) {
+      const int b = row / p.fr_rows;
+      rf = row - b * p.fr_rows;
+      outb += (size_t)b * p.fr_stride;
+    }
+    const int i_ = rf / p.ps_Wh, j_ = rf - i_ * p.ps_Wh;
     const int Wout = p.ps_P2 * p.ps_Wh;
     for (int i = 0; i < 32; ++i) {
       const int col = col0 + i;
       if (col >= N) break;
       const int pp = col / p.ps_C, c = col - pp * p.ps_C;
       const int p1 = pp / p.ps_P2, p2 = pp - p1 * p.ps_P2;
-      p.out_f32[(size_t)c * p.ldo + (size_t)(p.ps_P1 * i_ + p1) * Wout + p.ps_P2 * j_ + p2] = v[i];
+      outb[(size_t)c * p.ldo + (size_t)(p.ps_P1 * i_ + p1) * Wout + p.ps_P2 * j_ + p2] = v[i];
     }
   } else if constexpr (KIND == EPI_CONVT) {
     // row = (i, j) patch position; col = (r - r0, c, s); out[c][sh*i + r][pw*j + s]
-    const int i_ = row / p.ct_Wp, j_ = row - i_ * p.ct_Wp;
+    int rf = row;
+    float* outb = p.out_f32;
+    if (p.fr_rows > 0) {
+      const int b = row / p.fr_rows;
+      rf = row - b * p.fr_rows;
+      outb += (size_t)b * p.fr_stride;
+    }
+    const int i_ = rf / p.ct_Wp, j_ = rf - i_ * p.ct_Wp;
     for (int i = 0; i < 32; ++i) {
       const int col = col0 + i;
       if (col >= N) break;
@@ -321,7 +347,7 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
       const int c = cs / p.ct_pw, s = cs - c * p.ct_pw;
       const int h = p.ct_sh * i_ + p.ct_r0 + rr;
       if (h < p.ct_Himg)
-        p.out_f32[((size_t)c * p.ct_Himg + h) * p.ct_Wimg + p.ct_pw * j_ + s] = v[i];
+        outb[((size_t)c * p.ct_Himg + h) * p.ct_Wimg + p.ct_pw * j_ + s] = v[i];
     }
   }
 }
@@ -364,7 +390,8 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& p, const float* s
       float av[32];
 #pragma unroll
       for (int rr = 0; rr < 32; ++rr)
-        av[rr] = __ldg(p.add + (size_t)(row_base + min(rr, rows_valid - 1)) * p.lda + colc);
+        av[rr] = __ldg(p.add + (size_t)((p.add_period > 0) ? (row_base + min(rr, rows_valid - 1)) % p.add_period
+                                                            : (row_base + min(rr, rows_valid - 1))) * p.lda + colc);
 #pragma unroll
       for (int rr = 0; rr < 32; ++rr)
         if (ok && rr < rows_valid) p.out_f32[(size_t)(row_base + rr) * p.ldo + col] = stg[rr * STG_LD + lane] + b + av[rr];
@@ -443,12 +470,22 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& p, const float* s
     const int rk = col / p.ct_CS, cs = col - rk * p.ct_CS;
     const int c = cs / p.ct_pw, s_ = cs - c * p.ct_pw;
     float* plane = p.out_f32 + (size_t)c * p.ct_Himg * p.ct_Wimg + s_;
-    int i_ = row_base / p.ct_Wp, j_ = row_base - i_ * p.ct_Wp;   // one division per chunk; (i, j) advance with the row
+    int rf = row_base;
+    const int i_per = (p.fr_rows > 0) ? p.fr_rows / p.ct_Wp : (1 << 30);   // patch rows per frame (batch of frames)
+    if (p.fr_rows > 0) {
+      const int b = row_base / p.fr_rows;
+      rf = row_base - b * p.fr_rows;
+      plane += (size_t)b * p.fr_stride;
+    }
+    int i_ = rf / p.ct_Wp, j_ = rf - i_ * p.ct_Wp;   // one division per chunk; (i, j) advance with the row
 #pragma unroll 8
     for (int rr = 0; rr < rows_valid; ++rr) {
       const int h = p.ct_sh * i_ + p.ct_r0 + rk;
       if (h < p.ct_Himg) plane[(size_t)h * p.ct_Wimg + p.ct_pw * j_] = stg[rr * STG_LD + lane];
-      if (++j_ == p.ct_Wp) { j_ = 0; ++i_; }
+      if (++j_ == p.ct_Wp) {
+        j_ = 0;
+        if (++i_ == i_per) { i_ = 0; plane += p.fr_stride; }
+      }
     }
   }
 }
@@ -585,11 +622,16 @@ __device__ __forceinline__ void epilogue_f32_prefetch(const EpiParams& p, int ro
   const int piece = lane & 7;
   f.bias = (p.bias != nullptr) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + piece * 4))
                                : make_float4(0.f, 0.f, 0.f, 0.f);
+  // EPI_F32: a pos-embed addend repeats down a batch of frames (row % add_period); taken once per lane, not per piece
+  int src_t = max(f.my_t, 0);
+  if constexpr (KIND == EPI_F32) {
+    if (p.add_period > 0) src_t = src_t % p.add_period;
+  }
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
-    const int t = __shfl_sync(0xffffffffu, f.my_t, it * 4 + (lane >> 3));
+    const int t = __shfl_sync(0xffffffffu, src_t, it * 4 + (lane >> 3));
     f.add[it] = (src != nullptr)
-                    ? *reinterpret_cast<const float4*>(src + (size_t)max(t, 0) * ld_src + col0 + piece * 4)
+                    ? *reinterpret_cast<const float4*>(src + (size_t)t * ld_src + col0 + piece * 4)
                     : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
@@ -695,7 +737,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int t = m0 + g * shp.pe_box_rows;
             const int i = t / shp.pe_Wp;
             pe_j0[g] = t - i * shp.pe_Wp;
-            pe_h0[g] = shp.pe_sh * i;
+            const int fb = (shp.pe_Hg > 0) ? i / shp.pe_Hg : 0;     // frame of a batch
+            pe_h0[g] = shp.pe_sh * (i - fb * shp.pe_Hg) + fb * shp.pe_img_h;
           }
         }
         if (split_terms > 1) {
@@ -996,7 +1039,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int t = m0 + g * shp.pe_box_rows;
             const int i = t / shp.pe_Wp;
             pe_j0[g] = t - i * shp.pe_Wp;
-            pe_h0[g] = shp.pe_sh * i;
+            const int fb = (shp.pe_Hg > 0) ? i / shp.pe_Hg : 0;     // frame of a batch
+            pe_h0[g] = shp.pe_sh * (i - fb * shp.pe_Hg) + fb * shp.pe_img_h;
           }
         }
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {

@@ -27,7 +27,7 @@ void gemm_simt_check(cudaStream_t st, const __nv_bfloat16* A, int lda, const __n
 // index >= q_part_from only need their first q_part_rows query rows (window-pad rows).
 void attention_tc(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* Vt,
                   __nv_bfloat16* out, int ldo, int heads, int rows_total, int seg_len, int q_part_from = 1 << 30,
-                  int q_part_rows = 0);
+                  int q_part_rows = 0, int seg_period = 0);
 
 void attention_simt(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* Vt,
                     __nv_bfloat16* out, int ldo, int heads, int hd, int rows_total, int seg_len);
@@ -50,22 +50,31 @@ void affine_channels(cudaStream_t st, const float* in, float* out, const float* 
                      int forward);
 
 // entropy.cu
+// One launch covers `frames` frames of n elements each: y / sym / idx / y_hat advance by n per frame, sigma and mu by
+// param_stride (the hyperprior writes sigma | mu per frame, so consecutive frames' sigma are 2n apart).
 void gc_quantize_index(cudaStream_t st, const float* y, const float* sigma, const float* mu, const float* scale_table,
-                       int levels, float bound, int32_t* sym, uint8_t* idx, float* y_hat, size_t n);
-void eb_quantize(cudaStream_t st, const float* z, const float* median, int L, int32_t* sym, float* z_hat, size_t n);
+                       int levels, float bound, int32_t* sym, uint8_t* idx, float* y_hat, size_t n, int frames = 1,
+                       size_t param_stride = 0);
+// (n_ch = channels per frame: the median index is (e / L) % n_ch, so a batch of frames is one launch)
+void eb_quantize(cudaStream_t st, const float* z, const float* median, int L, int n_ch, int32_t* sym, float* z_hat,
+                 size_t n);
 void dequantize(cudaStream_t st, const int32_t* sym, const float* mu, const float* median, int L, float* out,
                 size_t n);
 void gc_likelihood(cudaStream_t st, const float* y, const float* sigma, const float* mu, float scale_bound,
                    float lik_bound, float* y_hat, float* lik, size_t n);
 void eb_likelihood(cudaStream_t st, const float* z_hat, const float* packed, int L, float lik_bound, float* lik,
                    size_t n);
-void rans_encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx, bool index_is_channel, const int32_t* cdf,
+// chan_mod: 0 = the CDF row of a symbol is idx[pos]; > 0 = it is (channel % chan_mod) -- EntropyBottleneck, where a
+// batch of frames is coded as frames * chan_mod channels. Decoders: ch_per_frame / mu_frame_extra place the per-symbol
+// means of frame f at mu[pos + f * mu_frame_extra] (the hyperprior writes sigma | mu per frame).
+void rans_encode(cudaStream_t st, const int32_t* sym, const uint8_t* idx, int chan_mod, const int32_t* cdf,
                  int cdf_stride, const int32_t* cdf_len, const int32_t* offset, int n_channels, int L, int spc,
                  int chan_len, uint32_t* scratch, int cap_words, uint32_t* lengths, uint32_t* offsets, uint8_t* payload, int* err);
 void rans_decode(cudaStream_t st, const uint8_t* payload, const uint32_t* offsets, const uint8_t* idx,
-                 bool index_is_channel, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len,
+                 int chan_mod, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len,
                  const int32_t* offset, const uint16_t* lut, int lut_rows, int n_channels, int L, int spc,
-                 int chan_len, int32_t* sym_out, const float* mu, const float* median, float* val_out, int* err);
+                 int chan_len, int32_t* sym_out, const float* mu, const float* median, float* val_out, int* err,
+                 int ch_per_frame = 0, size_t mu_frame_extra = 0);
 void build_decode_lut(cudaStream_t st, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len, int rows,
                       uint16_t* lut);
 void scan_lengths(cudaStream_t st, const uint32_t* lengths, int n, uint32_t* offsets);
@@ -73,13 +82,14 @@ void scan_lengths(cudaStream_t st, const uint32_t* lengths, int n, uint32_t* off
 void pack_cdf(cudaStream_t st, const int32_t* cdf, int cdf_stride, const int32_t* cdf_len, int rows, int32_t* row_off,
               uint16_t* packed, int cap, int* total_dev);
 bool rans_tables_fit(int rows, int total, bool with_lut);
-void rans_encode_smem(cudaStream_t st, const int32_t* sym, const uint8_t* idx, bool index_is_channel,
+void rans_encode_smem(cudaStream_t st, const int32_t* sym, const uint8_t* idx, int chan_mod,
                       const uint16_t* packed, const int32_t* row_off, const int32_t* cdf_len, const int32_t* offset,
                       int rows, int total, int n_channels, int L, int spc, int chan_len, uint32_t* scratch, int cap_words,
                       uint32_t* lengths, uint32_t* offsets, uint8_t* payload, int* err);
 void rans_decode_smem(cudaStream_t st, const uint8_t* payload, const uint32_t* offsets, const uint8_t* idx,
-                      bool index_is_channel, const uint16_t* packed, const int32_t* row_off, const int32_t* cdf_len,
+                      int chan_mod, const uint16_t* packed, const int32_t* row_off, const int32_t* cdf_len,
                       const int32_t* offset, const uint16_t* lut, int rows, int total, int n_channels, int L, int spc,
-                      int chan_len, int32_t* sym_out, const float* mu, const float* median, float* val_out, int* err);
+                      int chan_len, int32_t* sym_out, const float* mu, const float* median, float* val_out, int* err,
+                      int ch_per_frame = 0, size_t mu_frame_extra = 0);
 
 }  // namespace cra5

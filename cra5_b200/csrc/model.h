@@ -69,17 +69,19 @@ class Model {
   void set_precision(int level);
   int precision() const { return precision_; }
 
-  // hot path (all pointers device, fp32)
-  void encode_to_latent(const float* x, float* y, const float* mean, const float* std_, cudaStream_t st);
-  void latent_to_reconstruction(const float* y_hat, float* x_hat, cudaStream_t st);
+  // hot path (all pointers device, fp32). B frames (<= max_batch, contiguous in every tensor) run as ONE launch per
+  // kernel: B * tokens rows through every GEMM / LayerNorm / attention, B * channels through the entropy kernels.
+  void encode_to_latent(const float* x, float* y, const float* mean, const float* std_, int B, cudaStream_t st);
+  void latent_to_reconstruction(const float* y_hat, float* x_hat, int B, cudaStream_t st);
   void latent_quantized(const float* y, float* y_hat, cudaStream_t st);  // encode_latent(type='quantized') tail
   // same, plus the likelihood tensors of the eval-mode forward (rate estimation); any output may be null
   void latent_likelihoods(const float* y, float* y_hat, float* y_lik, float* z_lik, cudaStream_t st);
-  // entropy stage; returns pinned host buffers owned by the model, valid until the next call
-  void latent_to_bin(const float* y, const uint8_t** y_bytes, size_t* y_len, const uint8_t** z_bytes, size_t* z_len,
-                     cudaStream_t st);
-  void bin_to_latent(const uint8_t* y_bytes, size_t y_len, const uint8_t* z_bytes, size_t z_len, int z_h, int z_w,
-                     float* y_hat, cudaStream_t st);
+  // entropy stage; returns (per frame) pinned host buffers owned by the model, valid until the next call
+  void latent_to_bin(const float* y, int B, const uint8_t** y_bytes, size_t* y_len, const uint8_t** z_bytes,
+                     size_t* z_len, cudaStream_t st);
+  void bin_to_latent(const uint8_t* const* y_bytes, const size_t* y_len, const uint8_t* const* z_bytes,
+                     const size_t* z_len, int B, int z_h, int z_w, float* y_hat, cudaStream_t st);
+  int max_batch() const { return Bm; }
   // debug taps for the parity tests (device pointers into the workspace, valid until the next call)
   const void* tap(const std::string& name, int64_t* numel, int* dtype) const;
 
@@ -92,6 +94,8 @@ class Model {
   int hd, hdh;          // head dims
   int kpr, cs_pad, box_rows;  // patch-embed implicit-GEMM geometry
   int nA, nB;           // ConvTranspose kernel-row classes (non-overlapping rows, overlapping rows)
+  int Bm = 1;           // frames per call the workspace is sized for
+  int M2 = 0;           // rows per frame of the reconstruction head's operand buffer
 
  private:
   void finalize();  // resolve tensor pointers (first use)
@@ -100,11 +104,11 @@ class Model {
   WinMap make_winmap(int block_window_h, int block_window_w) const;
   void run_block(cudaStream_t st, const BlockWeights& w, const TrunkBuffers& tb, const float* x_in, float* x_out, int T_,
                  int D, int heads, int mlp, int win_h, int win_w, __nv_bfloat16* cat_out, int cat_col0, int cat_ld,
-                 bool precise = false);
+                 bool precise, int frames, bool main);
   const __nv_bfloat16* need_x3(const std::string& name, int64_t numel) const;  // "<name>.x3": [2][numel] bf16
   void* alloc2(size_t bytes);
-  void run_h_a(cudaStream_t st, const float* y);     // -> z_
-  void run_h_s(cudaStream_t st, const float* z_hat); // -> params_ (sigma | mu)
+  void run_h_a(cudaStream_t st, const float* y, int B);     // -> z_ [B][zc][Th]
+  void run_h_s(cudaStream_t st, const float* z_hat, int B); // -> params_ [B][sigma | mu][T]
   void* alloc(size_t bytes);
 
   cra5_config cfg_;
@@ -119,8 +123,9 @@ class Model {
   int precision_ = 0;
   uint8_t* ws2_ = nullptr;          // split-precision workspace (set_precision)
   size_t ws2_bytes_ = 0, ws2_used_ = 0;
-  __nv_bfloat16 *cat2_ = nullptr, *patches2_ = nullptr, *ytok2_ = nullptr, *ztok2_ = nullptr, *ah2_ = nullptr;
-  size_t cat_half_ = 0, patches_half_ = 0, ytok_half_ = 0, ztok_half_ = 0, ah_half_ = 0;
+  __nv_bfloat16 *cat2_ = nullptr, *patches2_ = nullptr, *ytok2_ = nullptr, *ztok2_ = nullptr, *ah2_ = nullptr,
+                *fin2_ = nullptr;
+  size_t cat_half_ = 0, patches_half_ = 0, ytok_half_ = 0, ztok_half_ = 0, ah_half_ = 0, fin_half_ = 0;
   TrunkBuffers main_, hyper_;
   float *x1_, *x2_;                 // outputs of the two parallel head blocks
   __nv_bfloat16* cat_;              // [T][2D] bf16 (mean || logvar tokens)
@@ -130,11 +135,12 @@ class Model {
   float *z_, *zhat_;                // [zc][Th]
   __nv_bfloat16* ztok_;             // [Th][zc]
   __nv_bfloat16* ah_;               // hyper im2col / generic A operand [Th][max K]
+  __nv_bfloat16* fin_;              // final LayerNorm of g_s, [frame][M2][D] with zero rows T..M2-1 per frame
   int32_t *ysym_, *zsym_;
   uint8_t* yidx_;
   RansCoder* coder_ = nullptr;
   uint8_t *host_y_ = nullptr, *host_z_ = nullptr;  // pinned output containers
-  size_t host_y_cap_ = 0, host_z_cap_ = 0;
+  size_t host_y_cap_ = 0, host_z_cap_ = 0, frame_cap_y_ = 0, frame_cap_z_ = 0;   // one container slot per frame
   std::map<std::string, TensorRef> taps_;
 };
 

@@ -34,10 +34,11 @@ class _CConfig(ctypes.Structure):
                 ("latent_chans", ctypes.c_int32), ("z_chans", ctypes.c_int32), ("hyper_dim", ctypes.c_int32),
                 ("hyper_depth", ctypes.c_int32), ("hyper_heads", ctypes.c_int32), ("hyper_patch_h", ctypes.c_int32),
                 ("hyper_patch_w", ctypes.c_int32), ("ln_eps", ctypes.c_float),
-                ("streams_per_channel_y", ctypes.c_int32), ("streams_per_channel_z", ctypes.c_int32)]
+                ("streams_per_channel_y", ctypes.c_int32), ("streams_per_channel_z", ctypes.c_int32),
+                ("max_batch", ctypes.c_int32)]
 
 
-def _c_config(cfg: C.VaeformerConfig, spc_y: int, spc_z: int) -> _CConfig:
+def _c_config(cfg: C.VaeformerConfig, spc_y: int, spc_z: int, max_batch: int = 1) -> _CConfig:
     if len(cfg.window_sizes) > 4:
         raise ValueError("at most 4 window sizes are supported")
     c = _CConfig()
@@ -55,6 +56,7 @@ def _c_config(cfg: C.VaeformerConfig, spc_y: int, spc_z: int) -> _CConfig:
     c.hyper_patch_h, c.hyper_patch_w = cfg.hyper_patch
     c.ln_eps = cfg.ln_eps
     c.streams_per_channel_y, c.streams_per_channel_z = spc_y, spc_z
+    c.max_batch = max_batch
     return c
 
 
@@ -110,7 +112,7 @@ class VAEformer:
     _warned_ref_stream = False
 
     def __init__(self, model_version: int = 268, cfg: Optional[C.VaeformerConfig] = None, device="cuda",
-                 streams_per_channel=(16, 4), init_seed: Optional[int] = 0, **kwargs):
+                 streams_per_channel=(16, 4), init_seed: Optional[int] = 0, max_batch: int = 1, **kwargs):
         if cfg is None:
             if model_version != 268:
                 # the reference dies on `Encoder(**None)` here (vaeformer.py:150); say why instead
@@ -123,9 +125,15 @@ class VAEformer:
         if self.device.type != "cuda":
             raise RuntimeError("cra5_b200 models live on a CUDA device")
         self._spc = tuple(streams_per_channel)
+        if not (1 <= int(max_batch) <= 64):
+            raise ValueError("max_batch must be in [1, 64]")
+        # frames per library call: the workspace is sized for it (about 2 GB per frame at quality 268) and a (B, C, H, W)
+        # input runs as ceil(B / max_batch) calls, each ONE launch per kernel for its whole chunk (additive extension;
+        # results are bit-identical to frame-by-frame calls)
+        self.max_batch = int(max_batch)
         self._handle = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            cc = _c_config(self.cfg, *self._spc)
+            cc = _c_config(self.cfg, *self._spc, self.max_batch)
             _lib.check(_lib.lib.cra5_model_create(ctypes.byref(cc), ctypes.byref(self._handle)))
         self._dev = {}      # name -> device tensor handed to the library (kept alive here)
         self._sd = None     # fp32 CPU copy in reference layout (for state_dict())
@@ -168,12 +176,13 @@ class VAEformer:
         latent_to_bin)."""
         r = object.__new__(type(self))
         r.cfg, r.device, r._spc, r.training = self.cfg, self.device, self._spc, self.training
+        r.max_batch = self.max_batch
         r._sd, r._cdf, r.scale_table = self._sd, dict(self._cdf), self.scale_table
         r._precision = self._precision
         r._dev = {}
         r._handle = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            cc = _c_config(self.cfg, *self._spc)
+            cc = _c_config(self.cfg, *self._spc, self.max_batch)
             _lib.check(_lib.lib.cra5_model_create(ctypes.byref(cc), ctypes.byref(r._handle)))
             for name, t in self._dev.items():
                 if isinstance(t, dict):   # "<module>.tables": the three int32 CDF tensors of an entropy model
@@ -400,6 +409,10 @@ class VAEformer:
                              f"got {tuple(x.shape)}")
         return x.to(self.device, torch.float32).contiguous()
 
+    def _chunks(self, B):
+        """(first frame, frames) of the library calls a batch of B frames is split into"""
+        return [(b0, min(self.max_batch, B - b0)) for b0 in range(0, B, self.max_batch)]
+
     def _latent_shape(self, B=1):
         return (B, self.cfg.latent_chans, *self.cfg.grid)
 
@@ -420,9 +433,9 @@ class VAEformer:
         y = torch.empty(self._latent_shape(x.shape[0]), device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
             s = _lib.stream_ptr()
-            for b in range(x.shape[0]):
-                _lib.check(_lib.lib.cra5_encode_to_latent(self._handle, _lib.ptr(x[b]), _lib.ptr(y[b]), _lib.ptr(mean),
-                                                          _lib.ptr(std), s))
+            for b0, nb in self._chunks(x.shape[0]):
+                _lib.check(_lib.lib.cra5_encode_to_latent_batch(self._handle, _lib.ptr(x[b0]), _lib.ptr(y[b0]),
+                                                                _lib.ptr(mean), _lib.ptr(std), nb, s))
             if type != "quantized":
                 return y, None, None
             y_hat = torch.empty_like(y)
@@ -439,23 +452,24 @@ class VAEformer:
         x_hat = torch.empty((y.shape[0], cfg.in_chans, *cfg.img_size), device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
             s = _lib.stream_ptr()
-            for b in range(y.shape[0]):
-                _lib.check(_lib.lib.cra5_latent_to_reconstruction(self._handle, _lib.ptr(y[b]), _lib.ptr(x_hat[b]), s))
+            for b0, nb in self._chunks(y.shape[0]):
+                _lib.check(_lib.lib.cra5_latent_to_reconstruction_batch(self._handle, _lib.ptr(y[b0]), _lib.ptr(x_hat[b0]),
+                                                                        nb, s))
         return x_hat
 
     def compress_from_latent(self, y):
         self._require_cdfs()
         y = self._check_y(y)
         y_strings, z_strings = [], []
-        yb, zb = ctypes.c_void_p(), ctypes.c_void_p()
-        yl, zl = ctypes.c_uint64(), ctypes.c_uint64()
         with torch.cuda.device(self.device):
             s = _lib.stream_ptr()
-            for b in range(y.shape[0]):
-                _lib.check(_lib.lib.cra5_latent_to_bin(self._handle, _lib.ptr(y[b]), ctypes.byref(yb), ctypes.byref(yl),
-                                                       ctypes.byref(zb), ctypes.byref(zl), s))
-                y_strings.append(ctypes.string_at(yb.value, yl.value))
-                z_strings.append(ctypes.string_at(zb.value, zl.value))
+            for b0, nb in self._chunks(y.shape[0]):
+                yb, zb = (ctypes.c_void_p * nb)(), (ctypes.c_void_p * nb)()
+                yl, zl = (ctypes.c_uint64 * nb)(), (ctypes.c_uint64 * nb)()
+                _lib.check(_lib.lib.cra5_latent_to_bin_batch(self._handle, _lib.ptr(y[b0]), nb, yb, yl, zb, zl, s))
+                for b in range(nb):
+                    y_strings.append(ctypes.string_at(yb[b], yl[b]))
+                    z_strings.append(ctypes.string_at(zb[b], zl[b]))
         return {"strings": [y_strings, z_strings], "z_shape": torch.Size(self.cfg.hyper_grid)}
 
     def compress(self, x):
@@ -473,18 +487,24 @@ class VAEformer:
         y_hat = torch.empty(self._latent_shape(B), device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
             s = _lib.stream_ptr()
-            for b in range(B):
-                ys, zs = bytes(strings[0][b]), bytes(strings[1][b])
-                if ys[:4] != b"CR5B" and not VAEformer._warned_ref_stream:
-                    VAEformer._warned_ref_stream = True
-                    import warnings
-                    warnings.warn("decompress: reference-format (single-stream) input. It decodes correctly only if it "
-                                  "was written by this library on the same build (set_coder(format='ref')): a stream "
-                                  "written by the PyTorch reference needs bit-identical h_s outputs, which two "
-                                  "implementations do not produce.", RuntimeWarning, stacklevel=2)
-                _lib.check(_lib.lib.cra5_bin_to_latent(self._handle, ys, ctypes.c_uint64(len(ys)), zs,
-                                                       ctypes.c_uint64(len(zs)), int(shape[0]), int(shape[1]),
-                                                       _lib.ptr(y_hat[b]), s))
+            ys = [bytes(v) for v in strings[0]]
+            zs = [bytes(v) for v in strings[1]]
+            chunked = all(v[:4] == b"CR5B" for v in ys + zs)
+            if not chunked and not VAEformer._warned_ref_stream:
+                VAEformer._warned_ref_stream = True
+                import warnings
+                warnings.warn("decompress: reference-format (single-stream) input. It decodes correctly only if it "
+                              "was written by this library on the same build (set_coder(format='ref')): a stream "
+                              "written by the PyTorch reference needs bit-identical h_s outputs, which two "
+                              "implementations do not produce.", RuntimeWarning, stacklevel=2)
+            # reference-format streams decode one frame per call; CR5B containers a whole chunk per call
+            for b0, nb in (self._chunks(B) if chunked else [(b, 1) for b in range(B)]):
+                yb = (ctypes.c_char_p * nb)(*ys[b0:b0 + nb])
+                zb = (ctypes.c_char_p * nb)(*zs[b0:b0 + nb])
+                yl = (ctypes.c_uint64 * nb)(*[len(v) for v in ys[b0:b0 + nb]])
+                zl = (ctypes.c_uint64 * nb)(*[len(v) for v in zs[b0:b0 + nb]])
+                _lib.check(_lib.lib.cra5_bin_to_latent_batch(self._handle, yb, yl, zb, zl, nb, int(shape[0]),
+                                                             int(shape[1]), _lib.ptr(y_hat[b0]), s))
         if return_format == "latent":
             return y_hat
         return {"x_hat": self.decode_latent(y_hat)}

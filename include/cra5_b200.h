@@ -95,6 +95,8 @@ typedef struct cra5_config {
   float ln_eps;              /* vit_nlc.py:381 */
   int32_t streams_per_channel_y; /* chunk-parallel coder: interleaved rANS sub-streams per latent channel */
   int32_t streams_per_channel_z;
+  int32_t max_batch;         /* frames per call the workspace is sized for (0 or 1: one frame). The reference API is
+                              * batched throughout (vaeformer.py:350-376; entropy_models.py:263-272 loops batch items). */
 } cra5_config;
 
 typedef struct cra5_model cra5_model;
@@ -168,6 +170,23 @@ CRA5_API int cra5_bin_to_latent(cra5_model* m, const uint8_t* y_bytes, uint64_t 
 /* y_hat -> x_hat (C,H,W) fp32, normalised units. Replaces VAEformer.decode_latent (vaeformer.py:294-300) =
  * cra5_api.latent_to_reconstruction (:146-151). */
 CRA5_API int cra5_latent_to_reconstruction(cra5_model* m, const float* y_hat_dev, float* x_hat_dev, void* stream);
+
+/* The same four calls on a batch of `batch` <= cfg.max_batch frames, contiguous in every tensor: x (B,C,H,W),
+ * y / y_hat (B,latent,Hg,Wg), x_hat (B,C,H,W). The batch runs as ONE launch of every kernel -- B x tokens rows through
+ * each GEMM / LayerNorm / attention, B x channels sub-streams through the entropy kernels -- and the results are
+ * bit-identical to B single-frame calls (fixed tile order, no split-K). The reference is batched the same way:
+ * VAEformer.compress / decompress take (B, C, H, W) tensors (vaeformer.py:350-400) and EntropyModel.compress loops the
+ * batch items (entropy_models.py:263-272). y_bytes[b] / z_bytes[b] are per-frame containers (one pinned slot per frame,
+ * valid until the next call on the handle); all four arrays hold `batch` entries. */
+CRA5_API int cra5_encode_to_latent_batch(cra5_model* m, const float* x_dev, float* y_dev, const float* mean_dev,
+                                         const float* std_dev, int batch, void* stream);
+CRA5_API int cra5_latent_to_bin_batch(cra5_model* m, const float* y_dev, int batch, const uint8_t** y_bytes,
+                                      uint64_t* y_len, const uint8_t** z_bytes, uint64_t* z_len, void* stream);
+CRA5_API int cra5_bin_to_latent_batch(cra5_model* m, const uint8_t* const* y_bytes, const uint64_t* y_len,
+                                      const uint8_t* const* z_bytes, const uint64_t* z_len, int batch, int z_h, int z_w,
+                                      float* y_hat_dev, void* stream);
+CRA5_API int cra5_latent_to_reconstruction_batch(cra5_model* m, const float* y_hat_dev, float* x_hat_dev, int batch,
+                                                 void* stream);
 
 /* per-channel (x - mean)/std (forward != 0) or x*std + mean (forward == 0); in == out allowed.
  * Replaces cra5_api.normalization / de_normalization (cra5_api.py:264-271). */

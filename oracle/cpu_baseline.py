@@ -28,14 +28,19 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _ref_coder():
-    """the reference's own compiled coder (oracle/_ref), if it travelled with the repo"""
+    """the reference's own compiled coder (oracle/_ref), if it travelled with the repo. A pybind11 module can be
+    initialised once per process, so it is shared with oracle/ref_import.py under its real name."""
+    import sys
+    if "compressai.ans" in sys.modules:
+        return sys.modules["compressai.ans"]
     so = glob.glob(os.path.join(_HERE, "_ref", "compressai", "ans*.so"))
     if not so:
         return None
     try:
-        spec = importlib.util.spec_from_file_location("ans", so[0])
+        spec = importlib.util.spec_from_file_location("compressai.ans", so[0])
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
+        sys.modules["compressai.ans"] = mod
         return mod
     except Exception:
         return None

@@ -55,10 +55,11 @@ def test_from_state_dict_strips_prefix_and_honours_shipped_tables(ckpt):
     # ...and they are what the coder uses, with no update() call: indexes follow the 40-level table, every stream decodes
     x = weights.seeded_frame(cfg, 1).unsqueeze(0)
     with torch.no_grad():
-        o = net.compress(x.cuda())
+        y_dev, _, _ = net.encode_latent(x.cuda(), type="float")      # (held: the "y" tap points at this tensor)
+        o = net.compress_from_latent(y_dev)
         sc = net.tap("scales").reshape(1, cfg.latent_chans, *cfg.grid).cpu()
         mu = net.tap("means").reshape(sc.shape).cpu()
-        y = net.tap("y").reshape(sc.shape).cpu()
+        y = y_dev.cpu()
         idx, sym = net.tap("y_indexes").cpu(), net.tap("y_symbols").cpu()
         assert int(idx.max()) <= 39
         assert torch.equal(EO.build_indexes(sc, scale_table).reshape(-1).to(torch.uint8), idx)

@@ -36,8 +36,8 @@ def split(t):
 class Emu:
     """functional namespace whose linear/conv know which site they are called for"""
 
-    def __init__(self, sd, split_if, attn_split_if=lambda key: False):
-        self.sd, self.split_if, self.attn_split_if = sd, split_if, attn_split_if
+    def __init__(self, sd, split_if, attn_split_if=lambda key: False, attn_mode="bf16"):
+        self.sd, self.split_if, self.attn_split_if, self.attn_mode = sd, split_if, attn_split_if, attn_mode
         self.by_id = {id(v): k for k, v in sd.items()}
         self.layer_norm, self.gelu, self.pad = F.layer_norm, F.gelu, F.pad
         self.last_key = ""
@@ -71,6 +71,13 @@ def make_mhsa(emu):
             q, k, v = qkv[0] * hd ** -0.5, qkv[1], qkv[2]
             out = torch.softmax(q @ k.transpose(-2, -1), dim=-1) @ v
             return out.transpose(1, 2).reshape(B, N, D)
+        if emu.attn_mode == "fp16":                # fp16 Q/K/V/P (what the reference's own flash path uses), O kept fp32
+            h = lambda t: t.half().float()
+            q, k, v = h(qkv[0] * hd ** -0.5), h(qkv[1]), h(qkv[2])
+            s = q @ k.transpose(-2, -1)
+            p = torch.exp(s - s.amax(dim=-1, keepdim=True))
+            out = (h(p) @ v) / p.sum(dim=-1, keepdim=True)
+            return out.transpose(1, 2).reshape(B, N, D)     # (the projection then splits it like any fp32 operand)
         q, k, v = r(qkv[0] * hd ** -0.5), r(qkv[1]), r(qkv[2])
         s = q @ k.transpose(-2, -1)
         p = torch.exp(s - s.amax(dim=-1, keepdim=True))
@@ -97,6 +104,11 @@ def levels(cfg):
     hyper = ("h_a.", "h_s.")
     tail = lambda k: k.startswith(tail_blocks) or k.startswith(hyper) or k.startswith(("quant_conv", "post_quant_conv"))
     enc = lambda k: k.startswith(("g_a.", "quant_conv")) or k.startswith(hyper)
+    if os.environ.get("STUDY_FULL"):
+        return [("bf16 everywhere", lambda k: False, lambda k: False, "bf16"),
+                ("encoder linears + hyperprior split (attention bf16)", enc, lambda k: False, "bf16"),
+                ("encoder linears + hyperprior split, attention fp16 + fp32 O", enc, lambda k: False, "fp16"),
+                ("encoder linears + hyperprior split, attention fp32", enc, lambda k: True, "bf16")]
     return [("bf16 everywhere", lambda k: False, lambda k: False),
             ("hyperprior only", lambda k: k.startswith(hyper), lambda k: False),
             ("tail: g_a last 2 blocks + quant_conv + hyperprior", tail, lambda k: False),
@@ -112,9 +124,17 @@ def main():
     ap.add_argument("--gain", type=float, default=1.0)
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    cfg, wseed, fseed = (C.tiny_fullres(69), 7, 1) if a.cfg == "tiny69" else (C.small_lowres(5), 11, 3)
-    sd = trained_like(weights.seeded_state_dict(C.param_shapes(cfg), wseed), cfg, a.gain)
-    x = weights.seeded_frame(cfg, fseed).unsqueeze(0)
+    if a.cfg == "full":
+        from cra5_b200.vaeformer import init_state_dict
+        cfg = C.cra5_268()
+        sd = init_state_dict(cfg, 3)
+        sd["quant_conv.weight"] = sd["quant_conv.weight"] * 6.0
+        sd["h_s.final.weight"] = sd["h_s.final.weight"] * 12.0
+        x = torch.randn(1, cfg.in_chans, *cfg.img_size, generator=torch.Generator().manual_seed(1000))
+    else:
+        cfg, wseed, fseed = (C.tiny_fullres(69), 7, 1) if a.cfg == "tiny69" else (C.small_lowres(5), 11, 3)
+        sd = trained_like(weights.seeded_state_dict(C.param_shapes(cfg), wseed), cfg, a.gain)
+        x = weights.seeded_frame(cfg, fseed).unsqueeze(0)
     codec = VO.OracleCodec(sd, cfg)
     with torch.no_grad():
         ref = codec.forward(x)
@@ -125,8 +145,9 @@ def main():
     idx_ref = VO.EO.build_indexes(ref["scales"], codec.gc.scale_table)
     rm_r = ((ref["x_hat"][0] - x[0]) ** 2).mean(dim=(1, 2)).sqrt()
     keepF, keepM = VO.F, VO.mhsa
-    for name, sp, asp in levels(cfg):
-        emu = Emu(codec.sd, sp, asp)
+    for lv in levels(cfg):
+        name, sp, asp = lv[:3]
+        emu = Emu(codec.sd, sp, asp, lv[3] if len(lv) > 3 else "bf16")
         VO.F, VO.mhsa = emu, make_mhsa(emu)
         try:
             with torch.no_grad():
