@@ -24,6 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FRAME_BYTES = 268 * 721 * 1440 * 4
+DEFAULT_BATCH = 8   # frames per step: hourly frames are independent (test.py:13), the stream is cut into batches
 
 
 def parse():
@@ -34,9 +35,15 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--channels", type=int, default=268, help="268 (headline), 159 or 69")
     ap.add_argument("--lanes", type=int, default=1,
-                    help="codec lanes per GPU (cra5_b200.stream.CodecLanes; experimental, default 1 = one stream)")
+                    help="codec lanes per GPU (cra5_b200.stream.CodecLanes: own handle / stream / host thread each)")
+    ap.add_argument("--batch", type=int, default=DEFAULT_BATCH,
+                    help="frames per step and per library call (one launch per kernel for the whole batch); "
+                         "BASELINE.json configs[4] is --channels 159 --batch 8")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tail", "encoder", "all"],
+                    help="arithmetic of the linear layers (include/cra5_b200.h: cra5_model_set_precision)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-profile", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs under ncu)")
     return ap.parse_args()
 
 
@@ -237,9 +244,11 @@ def measure_entropy_b8(dev, cfg):
             "algorithmic_bytes_per_element": 17}
 
 
-def workload(cfg):
-    return (f"full encode->rANS bin->decode round trip, {cfg.in_chans}x721x1440 frame, vaeformer quality={cfg.in_chans} "
-            f"(BASELINE.json configs[2]), one frame per step per GPU")
+def workload(cfg, batch=1):
+    which = "configs[4]" if (cfg.in_chans == 159 and batch == 8) else "configs[2] / [3]"
+    return (f"full encode->rANS bin->decode round trip, {cfg.in_chans}x721x1440 frames, vaeformer quality={cfg.in_chans} "
+            f"(BASELINE.json {which}), {batch} frame(s) per step per GPU" +
+            (" in one batched call (every kernel launched once per batch)" if batch > 1 else ""))
 
 
 def dist_env():
@@ -278,7 +287,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": steps, "warmup": 1, "steps_requested": args.steps, "warmup_requested": args.warmup,
         "ms_per_step": frame_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload(cfg), "l2": "n/a (CPU arm)",
+        "config": {"workload": workload(cfg, max(1, getattr(args, "batch", 1))), "batch": max(1, getattr(args, "batch", 1)), "l2": "n/a (CPU arm)",
                    "weights": "random init of the named architecture (seed 1234), same entropy regime as the GPU arm",
                    "coder": "reference single-stream rANS", "bytes_per_frame": frames[-1]["bytes"]},
         "gb_era5_per_s": fps * cfg.in_chans * 721 * 1440 * 4 / 1e9,
@@ -310,18 +319,19 @@ def run_b200(args):
 
     cfg = C.variant(args.channels) if args.channels != 268 else C.cra5_268()
     frame_bytes = cfg.in_chans * 721 * 1440 * 4
-    net = VAEformer(268, cfg=cfg, device=dev, init_seed=1234)   # random-init weights of the named architecture
-    # widen the two layers that set the latent / scale ranges so the coder sees realistic entropy (~1-2 MB/frame)
+    B = max(1, args.batch)
+    net = VAEformer(268, cfg=cfg, device=dev, init_seed=1234, max_batch=B)   # random-init weights of the named architecture
+    # trained-like entropy statistics (cra5_b200/synthetic.py): y std 8, positive log-uniform sigma-hat, ~2 MB per frame
+    from cra5_b200.synthetic import bench_regime
     sd = net.state_dict()
-    sd = {k: v for k, v in sd.items() if k in C.param_shapes(cfg)}
-    sd["quant_conv.weight"] = sd["quant_conv.weight"] * 6.0
-    sd["h_s.final.weight"] = sd["h_s.final.weight"] * 12.0
+    sd = bench_regime({k: v for k, v in sd.items() if k in C.param_shapes(cfg)}, cfg)
     net.load_state_dict(sd)
     net.update(force=True)
+    net.set_precision(args.precision)
 
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
-    n_frames = 2  # distinct frames, alternated: 1.1 GB each, far larger than the 126 MB L2
-    frames = [torch.randn(1, cfg.in_chans, 721, 1440, device=dev, generator=g) for _ in range(n_frames)]
+    n_frames = 2  # distinct batches, alternated: 1.1 GB per frame, far larger than the 126 MB L2
+    frames = [torch.randn(B, cfg.in_chans, 721, 1440, device=dev, generator=g) for _ in range(n_frames)]
 
     def barrier():
         if world > 1:
@@ -335,7 +345,7 @@ def run_b200(args):
 
     for i in range(max(args.warmup, 3)):
         out, rec = step(i)
-    nbytes = len(out["strings"][0][0]) + len(out["strings"][1][0])
+    nbytes = (sum(len(v) for v in out["strings"][0]) + sum(len(v) for v in out["strings"][1])) // B
     assert torch.isfinite(rec["x_hat"]).all()
 
     # ---- timed region: device-resident inputs
@@ -359,7 +369,7 @@ def run_b200(args):
         def lane_step(codec, i):
             o = codec.compress(frames[i % n_frames])
             codec.decompress(o["strings"], o["z_shape"])
-            return len(o["strings"][0][0]) + len(o["strings"][1][0])
+            return sum(len(v) for v in o["strings"][0]) + sum(len(v) for v in o["strings"][1])
 
         lanes.run(lane_step, 2 * args.lanes)     # every lane warms its own workspace / tables
         barrier()
@@ -381,7 +391,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    fps = world * args.steps / (ms_total / 1e3)
+    fps = world * args.steps * B / (ms_total / 1e3)
 
     # ---- end to end through the public API with HOST buffers (pinned): H2D of the frame and D2H of the result inside
     import contextlib
@@ -392,7 +402,7 @@ def run_b200(args):
     api.std.fill_(1.0)  # synthetic frames are already in normalised units
     from cra5_b200.stream import FramePipeline, near_gpu
     host_in, numa_bound = None, False
-    if cfg.in_chans == 268:
+    if cfg.in_chans == 268 and not args.no_e2e:
         src = [torch.randn(cfg.in_chans, 721, 1440, generator=torch.Generator().manual_seed(7 + rank)) for _ in range(2)]
         with near_gpu(dev) as numa_bound:   # pinned pages land on the NUMA node of the allocating thread
             host_in = [t.pin_memory() for t in src]
@@ -464,10 +474,11 @@ def run_b200(args):
                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
                         "peak_source": peaks["source"],
                         "share_of_step": tk["ms"] / tot}
-        sites = {n: {"ms_per_step": round(k["ms"] / 2, 4), "launches_per_step": k["launches"] / 2,
+        sites = {n: {"ms_per_step": round(k["ms"] / 2, 4), "ms_per_frame": round(k["ms"] / 2 / B, 4),
+                     "launches_per_step": k["launches"] / 2,
                      "tflops": round(k["flops"] / (k["ms"] / 1e3) / 1e12, 1) if k["flops"] and k["ms"] else None}
                  for n, k in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"]) if ":" in n}
-        kernels = {n: {"ms_per_step": k["ms"] / 2, "launches_per_step": k["launches"] / 2,
+        kernels = {n: {"ms_per_step": k["ms"] / 2, "ms_per_frame": k["ms"] / 2 / B, "launches_per_step": k["launches"] / 2,
                        "tflops": (k["flops"] / (k["ms"] / 1e3) / 1e12) if k["flops"] and k["ms"] else None,
                        "gbs": (k["bytes"] / (k["ms"] / 1e3) / 1e9) if k["bytes"] and k["ms"] else None}
                    for n, k in sorted(by_kernel.items(), key=lambda kv: -kv[1]["ms"])}
@@ -506,11 +517,12 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": workload(cfg),
+            "config": {"workload": workload(cfg, B), "batch": B, "precision_level": args.precision,
                        "precision": "bf16 tensor-core operands, fp32 accumulate / residual stream / softmax / LayerNorm; "
                                     "fp32 quantise + scale index; int32 / u8 / u64 entropy coder (bit-exact)",
-                       "l2": "inputs larger than L2: two alternating 1.1 GB frames, every kernel's working set is re-streamed",
-                       "weights": "random init of the named architecture (seed 1234), CDF tables from update(force=True)",
+                       "l2": "inputs larger than L2: two alternating batches of 1.1 GB frames, every kernel's working set is re-streamed",
+                       "weights": "random init of the named architecture (seed 1234) in the bench entropy regime "
+                                  "(cra5_b200/synthetic.py: y std 8, sigma-hat log-uniform in [2, 30]), CDF tables from update(force=True)",
                        "bytes_per_frame": nbytes, "coder": "CR5B chunk-parallel rANS, 16 sub-streams per y channel, 4 per z channel",
                        "lanes": args.lanes, "build": _lib.VARIANT or "default"},
             "gb_era5_per_s": fps * frame_bytes / 1e9,

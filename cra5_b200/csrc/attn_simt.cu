@@ -67,10 +67,23 @@ attn_simt_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __res
 constexpr int AS2_QPW = 4;             // queries per warp
 constexpr int AS2_QPB = AS_WARPS * AS2_QPW;
 
+// two 16-bit operand elements packed in a word -> fp32 (bf16: a shift; fp16 for the split-precision levels)
+template <bool F16>
+__device__ __forceinline__ void unpack16x2(uint32_t w, float& lo, float& hi) {
+  if constexpr (F16) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    lo = f.x; hi = f.y;
+  } else {
+    lo = __uint_as_float(w << 16); hi = __uint_as_float(w & 0xffff0000u);
+  }
+}
+
+template <bool F16>
 __global__ void __launch_bounds__(AS_WARPS * 32)
 attn_small_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ K,
-                  const __nv_bfloat16* __restrict__ Vt, __nv_bfloat16* __restrict__ out, int ldo, int hd,
-                  int rows_total, int S, int kw, int vw, int kv_words) {
+                  const __nv_bfloat16* __restrict__ Vt, __nv_bfloat16* __restrict__ out,
+                  __nv_bfloat16* __restrict__ out_lo, int ldo, int hd, int rows_total, int S, int kw, int vw,
+                  int kv_words) {
   extern __shared__ uint32_t sm32[];
   uint32_t* KV = sm32;                                          // K as [S][kw] words, later V^T as [hd][vw] words
   float* sc = reinterpret_cast<float*>(sm32 + kv_words);        // [AS_WARPS][AS2_QPW][S] scores / probabilities
@@ -90,7 +103,8 @@ attn_small_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __re
   for (int t = lane; t < AS2_QPW * hd; t += 32) {
     const int qq = t / hd, d = t - qq * hd;
     const int qi = q_base + qq;
-    myq[t] = (qi < S) ? __bfloat162float(Q[((size_t)head * rows_total + row0 + qi) * hd + d]) : 0.f;
+    const __nv_bfloat16 qe = Q[((size_t)head * rows_total + row0 + min(qi, S - 1)) * hd + d];
+    myq[t] = (qi < S) ? (F16 ? __half2float(*reinterpret_cast<const __half*>(&qe)) : __bfloat162float(qe)) : 0.f;
   }
   __syncthreads();
   const bool active = q_base < S;
@@ -106,8 +120,8 @@ attn_small_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __re
       for (int qq = 0; qq < AS2_QPW; ++qq) acc[qq] = 0.f;
       const uint32_t* kr = KV + (size_t)j * kw;
       for (int w = 0; w < hw; ++w) {
-        const uint32_t kk = kr[w];
-        const float k0 = __uint_as_float(kk << 16), k1 = __uint_as_float(kk & 0xffff0000u);
+        float k0, k1;
+        unpack16x2<F16>(kr[w], k0, k1);
 #pragma unroll
         for (int qq = 0; qq < AS2_QPW; ++qq) {
           const float2 qv = *reinterpret_cast<const float2*>(myq + qq * hd + 2 * w);
@@ -150,8 +164,8 @@ attn_small_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __re
 #pragma unroll
     for (int qq = 0; qq < AS2_QPW; ++qq) acc[qq] = 0.f;
     for (int w = 0; w < sw; ++w) {
-      const uint32_t vv = vr[w];
-      const float v0 = __uint_as_float(vv << 16), v1 = __uint_as_float(vv & 0xffff0000u);
+      float v0, v1;
+      unpack16x2<F16>(vr[w], v0, v1);
 #pragma unroll
       for (int qq = 0; qq < AS2_QPW; ++qq) {
         const float2 pv = *reinterpret_cast<const float2*>(mysc + qq * S + 2 * w);
@@ -162,7 +176,12 @@ attn_small_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __re
 #pragma unroll
     for (int qq = 0; qq < AS2_QPW; ++qq) {
       const int qi = q_base + qq;
-      if (qi < S) out[(row0 + qi) * ldo + (size_t)head * hd + d] = __float2bfloat16(acc[qq] * inv[qq]);
+      if (qi < S) {
+        const float o = acc[qq] * inv[qq];
+        const __nv_bfloat16 hi = __float2bfloat16(o);
+        out[(row0 + qi) * ldo + (size_t)head * hd + d] = hi;
+        if (out_lo != nullptr) out_lo[(row0 + qi) * ldo + (size_t)head * hd + d] = __float2bfloat16(o - __bfloat162float(hi));
+      }
     }
   }
 }
@@ -382,11 +401,12 @@ static bool launch_attn_mma(cudaStream_t st, const __nv_bfloat16* Q, const __nv_
 }
 
 void attention_simt(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* Vt,
-                    __nv_bfloat16* out, int ldo, int heads, int hd, int rows_total, int seg_len) {
+                    __nv_bfloat16* out, int ldo, int heads, int hd, int rows_total, int seg_len, bool f16,
+                    __nv_bfloat16* out_lo) {
   CRA5_CHECK(seg_len > 0 && rows_total % seg_len == 0, ERR_INVALID, "attention: rows must be whole segments");
   CRA5_CHECK((hd & 1) == 0, ERR_INVALID, "attention: head_dim must be even");
   static const bool no_mma = getenv("CRA5_ATTN_SMALL_SIMT") != nullptr;   // diagnostics: the fp32 SIMT kernels
-  if (!no_mma) {
+  if (!no_mma && !f16 && out_lo == nullptr) {
     if (hd == 72 && launch_attn_mma<72>(st, Q, K, Vt, out, ldo, heads, rows_total, seg_len)) return;
     if (hd == 24 && launch_attn_mma<24>(st, Q, K, Vt, out, ldo, heads, rows_total, seg_len)) return;
   }
@@ -396,16 +416,22 @@ void attention_simt(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16
     const int kv_words = (int)((std::max((size_t)seg_len * kw, (size_t)hd * vw) + 1) & ~size_t(1));  // keeps sc 8-byte aligned
     const size_t smem2 = (size_t)kv_words * 4 + ((size_t)AS_WARPS * AS2_QPW * seg_len + (size_t)AS_WARPS * AS2_QPW * hd) * 4;
     if (smem2 <= 227 * 1024) {
-      ensure_dynamic_smem(attn_small_kernel, smem2);
+      ensure_dynamic_smem(attn_small_kernel<false>, smem2);
+      ensure_dynamic_smem(attn_small_kernel<true>, smem2);
       dim3 grid((seg_len + AS2_QPB - 1) / AS2_QPB, rows_total / seg_len, heads);
       LaunchScope scope(st, "attn_small", 4.0 * heads * (double)rows_total * seg_len * hd,
                         4.0 * 2.0 * heads * (double)rows_total * hd);
-      attn_small_kernel<<<grid, AS_WARPS * 32, smem2, st>>>(Q, K, Vt, out, ldo, hd, rows_total, seg_len, kw, vw,
-                                                           kv_words);
+      if (f16)
+        attn_small_kernel<true><<<grid, AS_WARPS * 32, smem2, st>>>(Q, K, Vt, out, out_lo, ldo, hd, rows_total, seg_len, kw,
+                                                                   vw, kv_words);
+      else
+        attn_small_kernel<false><<<grid, AS_WARPS * 32, smem2, st>>>(Q, K, Vt, out, out_lo, ldo, hd, rows_total, seg_len, kw,
+                                                                    vw, kv_words);
       CRA5_CUDA(cudaGetLastError());
       return;
     }
   }
+  CRA5_CHECK(!f16 && out_lo == nullptr, ERR_INVALID, "attention_simt: the fp16 / split-output form needs the shared-memory kernel");
   const size_t smem = ((size_t)AS_WARPS * seg_len + (size_t)AS_WARPS * hd) * sizeof(float);
   CRA5_CHECK(smem <= 200 * 1024, ERR_INVALID, "attention_simt: segment too long for the generic kernel");
   ensure_dynamic_smem(attn_simt_kernel, smem);

@@ -62,6 +62,7 @@ struct A4Params {
   int q_part_rows;    //   q_part_rows query rows (padded windows)
   int seg_period;     // segments per frame of a batch
   __nv_bfloat16* out; // [rows_total, ldo]
+  __nv_bfloat16* out_lo;  // optional: bf16(O - bf16(O)), so that the projection can run in split-bf16 form
   int ldo;
 };
 
@@ -162,8 +163,10 @@ __device__ __forceinline__ Item decode_item(const A4Params& p, int item) {
   return it;
 }
 
-// POLY: of every 8 column pairs, this many take the polynomial exp2
-template <int POLY>
+// POLY: of every 8 column pairs, this many take the polynomial exp2. F16: Q, K, V arrive as fp16 (EPI_QKV_F16) and P is
+// written as fp16 -- 11 instead of 8 significand bits on every attention operand, the format the reference's own GPU
+// path uses (flash-attn on .half() tensors, vit_nlc.py:105-110); same tcgen05 kind::f16 pipeline, same speed.
+template <int POLY, bool F16>
 __global__ void __launch_bounds__(A4_THREADS, 1)
 attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmVt, const A4Params p) {
@@ -245,8 +248,8 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // (two independent in-order instruction streams: neither tile's PV product ever queues behind a wait that
       // belongs to the other tile)
       const int x = warp >> 1;
-      constexpr uint32_t idesc_s = umma_idesc_bf16(A4_BM, A4_BN);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(A4_BM, A4_HD);
+      constexpr uint32_t idesc_s = umma_idesc_f16kind(A4_BM, A4_BN, F16 ? 0u : 1u);
+      constexpr uint32_t idesc_pv = umma_idesc_f16kind(A4_BM, A4_HD, F16 ? 0u : 1u);
       const uint64_t q_desc0 = umma_smem_desc_sw128(smem_u32(smem + L::OFF_Q));
       const uint64_t kv_desc0 = umma_smem_desc_sw128(smem_u32(smem + L::OFF_KV));
       const uint32_t d_s = tmem_base + TM_S + x * A4_BN;
@@ -433,7 +436,12 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             e1 = ex2_mufu(x1);
           }
           if (q & 1) sum_b = add2(sum_b, pack2(e0, e1)); else sum_a = add2(sum_a, pack2(e0, e1));
-          pk[q] = pack_bf16x2(e0, e1);
+          if constexpr (F16) {
+            const __half2 hp = __floats2half2_rn(e0, e1);
+            pk[q] = *reinterpret_cast<const uint32_t*>(&hp);
+          } else {
+            pk[q] = pack_bf16x2(e0, e1);
+          }
         }
         {
           float a0, a1, b0, b1;
@@ -459,7 +467,8 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float inv = 1.0f / l;
       const int qrow = it.q0 + x * A4_BM + r;     // row inside the segment
       const bool store = qrow < p.seg_len;
-      __nv_bfloat16* dst = p.out + (size_t)(it.seg * p.seg_len + qrow) * p.ldo + it.head * A4_HD;
+      const size_t out_off = (size_t)(it.seg * p.seg_len + qrow) * p.ldo + it.head * A4_HD;
+      __nv_bfloat16* dst = p.out + out_off;
 #pragma unroll
       for (int h = 0; h < ND; h += 32) {
         uint32_t o[32];
@@ -474,6 +483,15 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
             u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
             *reinterpret_cast<uint4*>(dst + h + i) = u;
+          }
+          if (p.out_lo != nullptr) {   // split-precision projection: the rounding error of the bf16 store, as bf16
+            auto lo2 = [&](int i) {
+              const float a = __uint_as_float(o[i]) * inv, b = __uint_as_float(o[i + 1]) * inv;
+              return pack_bf16x2(a - __bfloat162float(__float2bfloat16(a)), b - __bfloat162float(__float2bfloat16(b)));
+            };
+#pragma unroll
+            for (int i = 0; i < 32; i += 8)
+              *reinterpret_cast<uint4*>(p.out_lo + out_off + h + i) = make_uint4(lo2(i), lo2(i + 2), lo2(i + 4), lo2(i + 6));
           }
         }
       }
@@ -496,11 +514,15 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // seg_period = segments per frame when rows_total holds a batch of frames (0: one frame).
 void attention_tc(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* Vt,
                   __nv_bfloat16* out, int ldo, int heads, int rows_total, int seg_len, int q_part_from,
-                  int q_part_rows, int seg_period) {
+                  int q_part_rows, int seg_period, bool f16, __nv_bfloat16* out_lo) {
   CRA5_CHECK(seg_len > 0 && rows_total % seg_len == 0, ERR_INVALID, "attention: rows must be whole segments");
   CRA5_CHECK((rows_total & 7) == 0, ERR_INVALID, "attention: rows_total must be a multiple of 8 (TMA stride)");
   static const int poly = [] { const char* e = getenv("CRA5_ATTN_POLY"); return e ? atoi(e) : 3; }();
-  auto kern = poly == 0 ? attn_tc4_kernel<0> : poly == 2 ? attn_tc4_kernel<2> : poly == 4 ? attn_tc4_kernel<4> : attn_tc4_kernel<3>;
+  auto kern = f16 ? attn_tc4_kernel<3, true>
+                  : poly == 0 ? attn_tc4_kernel<0, false>
+                  : poly == 2 ? attn_tc4_kernel<2, false>
+                  : poly == 4 ? attn_tc4_kernel<4, false>
+                              : attn_tc4_kernel<3, false>;
   ensure_dynamic_smem(kern, A4Smem::TOTAL);
   CUtensorMap tmQ = make_tmap_bf16_2d(Q, A4_HD, (uint64_t)heads * rows_total, A4_HD * 2, A4_HD, A4_BM);
   CUtensorMap tmK = make_tmap_bf16_2d(K, A4_HD, (uint64_t)heads * rows_total, A4_HD * 2, A4_HD, A4_BN);
@@ -516,6 +538,7 @@ void attention_tc(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* 
   p.q_part_from = (q_part_rows > 0 && q_part_rows < seg_len) ? q_part_from : p.seg_period;
   p.q_part_rows = q_part_rows;
   p.out = out;
+  p.out_lo = out_lo;
   p.ldo = ldo;
   const int n_items = heads * p.n_seg * p.n_qp;
   const int grid = n_items < device_sm_count() ? n_items : device_sm_count();

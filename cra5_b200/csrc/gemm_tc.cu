@@ -20,7 +20,7 @@ static void launch_one(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMa
   // (split-bf16 launches execute 2-3x the tensor work of their algorithmic flops; the profiler counts the algorithmic ones)
   LaunchScope scope(st, (shp.a_split || shp.b_split) ? "gemm_tc_split" : "gemm_tc", 2.0 * shp.M * shp.N * shp.K,
                     2.0 * ((double)shp.M * shp.K + (double)shp.N * shp.K) +
-                        (double)shp.M * shp.N * ((KIND == EPI_BF16 || KIND == EPI_GELU_BF16 || KIND == EPI_QKV) ? 2.0 : 4.0));
+                        (double)shp.M * shp.N * ((KIND == EPI_BF16 || KIND == EPI_GELU_BF16 || KIND == EPI_QKV || KIND == EPI_QKV_F16) ? 2.0 : 4.0));
   launch_chained(kern, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN>::TOTAL, st, tmA, tmB, shp, epi);
 }
 
@@ -55,15 +55,16 @@ void launch_gemm_pair(cudaStream_t st, int kind, const CUtensorMap& tmA, const C
   }
 }
 
-// CTA-pair tiles pay off for large problems (>= one 256 x 256 tile per SM pair); small / skinny ones keep the 1-CTA kernel
+// CTA-pair tiles (256 x 256, each SM stages half of B) where the shape is large enough for them. The choice depends on
+// N, K and the epilogue only, never on M beyond a floor: a batch of frames must take the same kernel as one frame so
+// that results stay bit-identical across batch sizes.
 bool gemm_use_pair(int M, int N, int K, int kind) {
   static const char* env = getenv("CRA5_GEMM_PAIR");  // diagnostics: 0 = never, 1 = whenever legal
   if (env != nullptr) return atoi(env) != 0 && N >= 256;
-  // measured on B200 (tools/perf_kernels.py): the pair kernel wins where the main loop is long and the tile count small
-  // (fc2: K = 4096, N = 1024 -> 849 vs 944 TFLOP/s); elsewhere the two are within 3 % and the 1-CTA kernel stays
-  // ... and, with the light bf16 epilogues, for the widest plain shape (qkv: N = 3072 -> 1137 vs 1224 TFLOP/s)
+  // measured on B200 (bench.py kernel_sites, 8 frames per call): qkv 1381 TFLOP/s, fc2 1368, proj 822 with the pair
+  // kernel against 1343 / 1281 / 711-773 with 1-CTA tiles; fc1 and the conv layers are within noise and stay 1-CTA
   if (kind == EPI_QKV && N >= 3072 && M >= 4096) return true;
-  return kind == EPI_RESID && K >= 2048 && N >= 512 && N <= 1024 && M >= 4096;
+  return kind == EPI_RESID && N >= 512 && N <= 1024 && K >= 1024 && M >= 4096;
 }
 
 template <int BN>
@@ -74,6 +75,7 @@ static void launch_kind(cudaStream_t st, int kind, const CUtensorMap& tmA, const
     case EPI_BF16: launch_one<BN, EPI_BF16>(st, tmA, tmB, shp, epi); break;
     case EPI_GELU_BF16: launch_one<BN, EPI_GELU_BF16>(st, tmA, tmB, shp, epi); break;
     case EPI_QKV: launch_one<BN, EPI_QKV>(st, tmA, tmB, shp, epi); break;
+    case EPI_QKV_F16: launch_one<BN, EPI_QKV_F16>(st, tmA, tmB, shp, epi); break;
     case EPI_RESID: launch_one<BN, EPI_RESID>(st, tmA, tmB, shp, epi); break;
     case EPI_T_F32: launch_one<BN, EPI_T_F32>(st, tmA, tmB, shp, epi); break;
     case EPI_PIXSHUF: launch_one<BN, EPI_PIXSHUF>(st, tmA, tmB, shp, epi); break;
@@ -120,11 +122,6 @@ void gemm_plain(cudaStream_t st, int kind, const __nv_bfloat16* A, int lda, cons
     return;
   }
   int bn = gemm_pick_bn(N);
-  // short main loop + residual epilogue + few tiles (attention projection: K = N = 1024 -> 2.2 waves of 128 x 256 tiles):
-  // 128 x 128 tiles give every CTA 4-5 tiles to pipeline and halve the exposed last epilogue (379 -> 442 TFLOP/s)
-  if (getenv("CRA5_GEMM_BN") == nullptr && bn == 256 && kind == EPI_RESID && K <= 1024 && N <= 1024 && M >= 4096 &&
-      !split.any())
-    bn = 128;
   CUtensorMap tmA = operand_map(A, K, M, lda, GEMM_BM, split.a_half);
   CUtensorMap tmB = operand_map(B, K, N, ldb, bn, split.b_half);
   GemmShape shp{};

@@ -128,7 +128,11 @@ enum EpiKind : int {
   EPI_T_F32 = 5,      // out_f32[col * ldo + row] = acc + bias  (channel-major / NCHW result)
   EPI_PIXSHUF = 6,    // hyperprior head: (p1 p2 c) pixel shuffle into NCHW
   EPI_CONVT = 7,      // un-patchify scatter into NCHW
+  EPI_QKV_F16 = 8,    // EPI_QKV with Q, K, V written as fp16 (the attention of the split-precision levels; the
+                      // reference's own GPU path runs attention on fp16 operands, vit_nlc.py:105-110). 1-CTA kernel only.
 };
+template <int KIND>
+__device__ __forceinline__ constexpr bool is_qkv() { return KIND == EPI_QKV || KIND == EPI_QKV_F16; }
 
 struct EpiParams {
   const float* bias;      // [N] or null
@@ -180,6 +184,26 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x + 0.5f * fabsf(x) * erf_abs;          // 0.5 x (1 + sign(x) erf(|x|/sqrt2))
 }
 
+// 16-bit output element of an epilogue kind: bf16, or fp16 bits travelling in bf16-typed buffers for EPI_QKV_F16
+template <int KIND>
+__device__ __forceinline__ uint32_t pack_pair(float lo, float hi) {
+  if constexpr (KIND == EPI_QKV_F16) {
+    const __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+  } else {
+    return pack_bf16x2(lo, hi);
+  }
+}
+template <int KIND>
+__device__ __forceinline__ __nv_bfloat16 cvt_elem(float v) {
+  if constexpr (KIND == EPI_QKV_F16) {
+    const __half h = __float2half_rn(v);
+    return *reinterpret_cast<const __nv_bfloat16*>(&h);
+  } else {
+    return __float2bfloat16(v);
+  }
+}
+
 template <int KIND>
 __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int col0, const uint32_t (&acc)[32],
                                                int M, int N) {
@@ -226,7 +250,7 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
       for (int i = 0; i < 32; ++i)
         if (col0 + i < N) o[i] = __float2bfloat16(v[i]);
     }
-  } else if constexpr (KIND == EPI_QKV) {
+  } else if constexpr (is_qkv<KIND>()) {
     // columns ordered [q|k|v][head][dim] (vit_nlc.py:99,242)
 #pragma unroll
     for (int i0 = 0; i0 < 32; i0 += 8) {
@@ -250,7 +274,7 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
             const int dcol = d + i + (odd ? 1 : 0);
             const float lo = odd ? other1 : mine0, hi = odd ? mine1 : other0;
             const int r0_ = odd ? row - 1 : row;
-            *reinterpret_cast<uint32_t*>(p.vt + ((size_t)head * p.hd + dcol) * p.rows_total + r0_) = pack_bf16x2(lo, hi);
+            *reinterpret_cast<uint32_t*>(p.vt + ((size_t)head * p.hd + dcol) * p.rows_total + r0_) = pack_pair<KIND>(lo, hi);
           }
         } else {
 #pragma unroll
@@ -258,7 +282,7 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
             if (col + i < N) {
               int c2 = col + i - 2 * p.D;
               int h2 = c2 / p.hd, d2 = c2 - h2 * p.hd;
-              p.vt[((size_t)h2 * p.hd + d2) * p.rows_total + row] = __float2bfloat16(v[i0 + i]);
+              p.vt[((size_t)h2 * p.hd + d2) * p.rows_total + row] = cvt_elem<KIND>(v[i0 + i]);
             }
         }
       } else {
@@ -266,10 +290,10 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
         const float s = (which == 0) ? p.qscale : 1.0f;
         if (vec) {
           uint4 u;
-          u.x = pack_bf16x2(v[i0] * s, v[i0 + 1] * s);
-          u.y = pack_bf16x2(v[i0 + 2] * s, v[i0 + 3] * s);
-          u.z = pack_bf16x2(v[i0 + 4] * s, v[i0 + 5] * s);
-          u.w = pack_bf16x2(v[i0 + 6] * s, v[i0 + 7] * s);
+          u.x = pack_pair<KIND>(v[i0] * s, v[i0 + 1] * s);
+          u.y = pack_pair<KIND>(v[i0 + 2] * s, v[i0 + 3] * s);
+          u.z = pack_pair<KIND>(v[i0 + 4] * s, v[i0 + 5] * s);
+          u.w = pack_pair<KIND>(v[i0 + 6] * s, v[i0 + 7] * s);
           *reinterpret_cast<uint4*>(dst) = u;
         } else {
 #pragma unroll
@@ -278,7 +302,7 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
               int c2 = col + i - which * p.D;
               int h2 = c2 / p.hd, d2 = c2 - h2 * p.hd;
               ((which == 0 ? p.q : p.k))[((size_t)h2 * p.rows_total + row) * p.hd + d2] =
-                  __float2bfloat16(v[i0 + i] * s);
+                  cvt_elem<KIND>(v[i0 + i] * s);
             }
         }
       }
@@ -359,6 +383,7 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
 constexpr int STG_LD = 33;  // padded row stride (words): conflict-free both for the row writes and the column reads
 
 // bf16 row stores, two rows per step: lanes 0-15 take row rr, lanes 16-31 row rr+1, two adjacent columns each
+template <int KIND>
 __device__ __forceinline__ void store_rows_bf16x2(const float* stg, __nv_bfloat16* base, size_t ld, int rows_valid,
                                                   int lane, float b0, float b1, float scale) {
   const int half = lane >> 4, l2 = (lane & 15) * 2;
@@ -372,7 +397,7 @@ __device__ __forceinline__ void store_rows_bf16x2(const float* stg, __nv_bfloat1
   for (int k = 0; k < 16; ++k) {
     const int rr = 2 * k + half;
     if (rr < rows_valid)
-      *reinterpret_cast<uint32_t*>(base + (size_t)rr * ld + l2) = pack_bf16x2((a0[k] + b0) * scale, (a1[k] + b1) * scale);
+      *reinterpret_cast<uint32_t*>(base + (size_t)rr * ld + l2) = pack_pair<KIND>((a0[k] + b0) * scale, (a1[k] + b1) * scale);
   }
 }
 
@@ -428,7 +453,7 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& p, const float* s
         }
       }
     }
-  } else if constexpr (KIND == EPI_QKV) {
+  } else if constexpr (is_qkv<KIND>()) {
     // columns ordered [q|k|v][head][dim] (vit_nlc.py:99,242)
     if (((p.D | p.hd) & 31) == 0 && col0 + 32 <= N) {
       // the whole 32-column chunk lies inside one head of Q or K (V chunks take the direct path): 4-byte stores
@@ -439,7 +464,7 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& p, const float* s
       const float b0 = (p.bias != nullptr) ? __ldg(p.bias + col0 + l2) : 0.f;
       const float b1 = (p.bias != nullptr) ? __ldg(p.bias + col0 + l2 + 1) : 0.f;
       __nv_bfloat16* base = (which == 0 ? p.q : p.k) + ((size_t)head * p.rows_total + row_base) * p.hd + d0;
-      store_rows_bf16x2(stg, base, (size_t)p.hd, rows_valid, lane, b0, b1, which == 0 ? p.qscale : 1.0f);
+      store_rows_bf16x2<KIND>(stg, base, (size_t)p.hd, rows_valid, lane, b0, b1, which == 0 ? p.qscale : 1.0f);
       return;
     }
     // generic: each lane owns one column for all rows of the chunk
@@ -453,13 +478,13 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& p, const float* s
       __nv_bfloat16* dst = p.vt + ((size_t)head * p.hd + d) * p.rows_total + row_base;
 #pragma unroll
       for (int rr = 0; rr < 32; ++rr)
-        if (rr < rows_valid) dst[rr] = __float2bfloat16(stg[rr * STG_LD + lane] + b);
+        if (rr < rows_valid) dst[rr] = cvt_elem<KIND>(stg[rr * STG_LD + lane] + b);
     } else {
       const float sc = (which == 0) ? p.qscale : 1.0f;
       __nv_bfloat16* dst = (which == 0 ? p.q : p.k) + ((size_t)head * p.rows_total + row_base) * p.hd + d;
 #pragma unroll
       for (int rr = 0; rr < 32; ++rr)
-        if (rr < rows_valid) dst[(size_t)rr * p.hd] = __float2bfloat16((stg[rr * STG_LD + lane] + b) * sc);
+        if (rr < rows_valid) dst[(size_t)rr * p.hd] = cvt_elem<KIND>((stg[rr * STG_LD + lane] + b) * sc);
     }
   } else if constexpr (KIND == EPI_RESID) {
     // handled by epilogue_resid_load / epilogue_resid_finish (the residual loads are issued before the TMEM read)
@@ -543,7 +568,7 @@ __device__ __forceinline__ void epilogue_bf16_fast(const uint32_t (&acc)[32], co
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
   }
-  if constexpr (KIND == EPI_QKV) {
+  if constexpr (is_qkv<KIND>()) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] *= scale;
   }
@@ -551,10 +576,10 @@ __device__ __forceinline__ void epilogue_bf16_fast(const uint32_t (&acc)[32], co
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint4 u;
-    u.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]);
-    u.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
-    u.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
-    u.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+    u.x = pack_pair<KIND>(v[8 * c + 0], v[8 * c + 1]);
+    u.y = pack_pair<KIND>(v[8 * c + 2], v[8 * c + 3]);
+    u.z = pack_pair<KIND>(v[8 * c + 4], v[8 * c + 5]);
+    u.w = pack_pair<KIND>(v[8 * c + 6], v[8 * c + 7]);
     *reinterpret_cast<uint4*>(stage + lane * 64 + ((c ^ sw) << 4)) = u;
   }
   __syncwarp();
@@ -571,6 +596,7 @@ __device__ __forceinline__ void epilogue_bf16_fast(const uint32_t (&acc)[32], co
 // V^T (EPI_QKV, chunk wholly inside one head of V): the same idea transposed -- the row owner drops its 32 values into
 // a [dim][row] bf16 staging tile (2-byte stores, one contiguous 64-byte line per dim), then the warp writes 16-byte
 // pieces = 8 consecutive rows of one dim of V^T[head][dim][rows_total].
+template <int KIND>
 __device__ __forceinline__ void epilogue_vt_fast(const uint32_t (&acc)[32], const float* __restrict__ bias, int col0,
                                                  uint8_t* stage, __nv_bfloat16* vt_d0_row0, size_t rows_total,
                                                  int rows_valid, int lane) {
@@ -579,10 +605,10 @@ __device__ __forceinline__ void epilogue_vt_fast(const uint32_t (&acc)[32], cons
   for (int i = 0; i < 32; i += 4) {
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
-    st16[(i + 0) * 32 + lane] = __float2bfloat16(__uint_as_float(acc[i]) + b.x);
-    st16[(i + 1) * 32 + lane] = __float2bfloat16(__uint_as_float(acc[i + 1]) + b.y);
-    st16[(i + 2) * 32 + lane] = __float2bfloat16(__uint_as_float(acc[i + 2]) + b.z);
-    st16[(i + 3) * 32 + lane] = __float2bfloat16(__uint_as_float(acc[i + 3]) + b.w);
+    st16[(i + 0) * 32 + lane] = cvt_elem<KIND>(__uint_as_float(acc[i]) + b.x);
+    st16[(i + 1) * 32 + lane] = cvt_elem<KIND>(__uint_as_float(acc[i + 1]) + b.y);
+    st16[(i + 2) * 32 + lane] = cvt_elem<KIND>(__uint_as_float(acc[i + 2]) + b.z);
+    st16[(i + 3) * 32 + lane] = cvt_elem<KIND>(__uint_as_float(acc[i + 3]) + b.w);
   }
   __syncwarp();
   const int c = lane & 3;
@@ -893,7 +919,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         bool direct = epi_is_direct<KIND>();
-        if constexpr (KIND == EPI_QKV)  // a chunk that lies wholly inside V is written transposed, thread = row
+        if constexpr (is_qkv<KIND>())  // a chunk that lies wholly inside V is written transposed, thread = row
           direct = (col0 >= 2 * epi.D) && (col0 + 32 <= shp.N);
         bool fast = false;
         if constexpr (KIND == EPI_BF16 || KIND == EPI_GELU_BF16) {
@@ -904,7 +930,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                      epi.out_bf16 + (size_t)row_base * epi.ldo + col0, (size_t)epi.ldo,
                                      min(32, shp.M - row_base), lane);
         }
-        if constexpr (KIND == EPI_QKV) {   // a chunk wholly inside one head of Q or K
+        if constexpr (is_qkv<KIND>()) {   // a chunk wholly inside one head of Q or K
           fast = !direct && (col0 + 32 <= shp.N) && (((epi.D | epi.hd) & 31) == 0) && (col0 < 2 * epi.D) &&
                  (((reinterpret_cast<uintptr_t>(epi.q) | reinterpret_cast<uintptr_t>(epi.k)) & 15) == 0) &&
                  (epi.bias == nullptr || (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0);
@@ -916,13 +942,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                      base, (size_t)epi.hd, min(32, shp.M - row_base), lane);
           }
         }
-        if constexpr (KIND == EPI_QKV) {   // a chunk wholly inside one head of V: transposed store
+        if constexpr (is_qkv<KIND>()) {   // a chunk wholly inside one head of V: transposed store
           if (!fast && direct && (((epi.D | epi.hd) & 31) == 0) && ((epi.rows_total & 7) == 0) && ((shp.M & 7) == 0) &&
               ((reinterpret_cast<uintptr_t>(epi.vt) & 15) == 0) &&
               (epi.bias == nullptr || (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0)) {
             const QkvSplit qs = qkv_split(col0, epi.D, epi.hd);
             const int head = qs.head, d0 = qs.d;
-            epilogue_vt_fast(acc, epi.bias, col0, reinterpret_cast<uint8_t*>(stg),
+            epilogue_vt_fast<KIND>(acc, epi.bias, col0, reinterpret_cast<uint8_t*>(stg),
                              epi.vt + ((size_t)head * epi.hd + d0) * epi.rows_total + row_base, (size_t)epi.rows_total,
                              min(32, shp.M - row_base), lane);
             fast = true;
@@ -1149,7 +1175,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
         bool direct = epi_is_direct<KIND>();
-        if constexpr (KIND == EPI_QKV) direct = (col0 >= 2 * epi.D) && (col0 + 32 <= shp.N);
+        if constexpr (is_qkv<KIND>()) direct = (col0 >= 2 * epi.D) && (col0 + 32 <= shp.N);
         bool fast = false;
         if constexpr (KIND == EPI_BF16 || KIND == EPI_GELU_BF16) {
           fast = (col0 + 32 <= shp.N) && ((epi.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(epi.out_bf16) & 15) == 0) &&
@@ -1159,7 +1185,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                      epi.out_bf16 + (size_t)row_base * epi.ldo + col0, (size_t)epi.ldo,
                                      min(32, shp.M - row_base), lane);
         }
-        if constexpr (KIND == EPI_QKV) {   // a chunk wholly inside one head of Q or K
+        if constexpr (is_qkv<KIND>()) {   // a chunk wholly inside one head of Q or K
           fast = !direct && (col0 + 32 <= shp.N) && (((epi.D | epi.hd) & 31) == 0) && (col0 < 2 * epi.D) &&
                  (((reinterpret_cast<uintptr_t>(epi.q) | reinterpret_cast<uintptr_t>(epi.k)) & 15) == 0) &&
                  (epi.bias == nullptr || (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0);
@@ -1171,13 +1197,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                      base, (size_t)epi.hd, min(32, shp.M - row_base), lane);
           }
         }
-        if constexpr (KIND == EPI_QKV) {   // a chunk wholly inside one head of V: transposed store
+        if constexpr (is_qkv<KIND>()) {   // a chunk wholly inside one head of V: transposed store
           if (!fast && direct && (((epi.D | epi.hd) & 31) == 0) && ((epi.rows_total & 7) == 0) && ((shp.M & 7) == 0) &&
               ((reinterpret_cast<uintptr_t>(epi.vt) & 15) == 0) &&
               (epi.bias == nullptr || (reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0)) {
             const QkvSplit qs = qkv_split(col0, epi.D, epi.hd);
             const int head = qs.head, d0 = qs.d;
-            epilogue_vt_fast(acc, epi.bias, col0, reinterpret_cast<uint8_t*>(stg),
+            epilogue_vt_fast<KIND>(acc, epi.bias, col0, reinterpret_cast<uint8_t*>(stg),
                              epi.vt + ((size_t)head * epi.hd + d0) * epi.rows_total + row_base, (size_t)epi.rows_total,
                              min(32, shp.M - row_base), lane);
             fast = true;

@@ -27,10 +27,13 @@ void gemm_simt_check(cudaStream_t st, const __nv_bfloat16* A, int lda, const __n
 // index >= q_part_from only need their first q_part_rows query rows (window-pad rows).
 void attention_tc(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* Vt,
                   __nv_bfloat16* out, int ldo, int heads, int rows_total, int seg_len, int q_part_from = 1 << 30,
-                  int q_part_rows = 0, int seg_period = 0);
+                  int q_part_rows = 0, int seg_period = 0, bool f16 = false, __nv_bfloat16* out_lo = nullptr);
 
+// f16: Q, K, V hold fp16 bits (EPI_QKV_F16) -- routed to the fp32-softmax shared-memory kernel; out_lo: optional
+// bf16(O - bf16(O)) for a split-precision projection
 void attention_simt(cudaStream_t st, const __nv_bfloat16* Q, const __nv_bfloat16* K, const __nv_bfloat16* Vt,
-                    __nv_bfloat16* out, int ldo, int heads, int hd, int rows_total, int seg_len);
+                    __nv_bfloat16* out, int ldo, int heads, int hd, int rows_total, int seg_len, bool f16 = false,
+                    __nv_bfloat16* out_lo = nullptr);
 
 // elementwise.cu
 struct WinMap;

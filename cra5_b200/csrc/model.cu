@@ -147,7 +147,9 @@ void* Model::alloc2(size_t bytes) {
 // Precision levels (see model.h). The split-bf16 mode carries every fp32 GEMM operand as hi = bf16(v), lo = bf16(v - hi)
 // and accumulates A_hi B_hi + A_lo B_hi + A_hi B_lo in the same fp32 TMEM accumulator (gemm_tc.cuh, GemmShape::a_split):
 // ~16 mantissa bits per operand instead of 8, on the same tcgen05 pipeline, at 3x the tensor work of the covered sites.
-// Attention keeps bf16 Q, K, V and P at every level (the reference's own GPU path runs it in fp16, vit_nlc.py:105-110).
+// Attention in a split-precision block runs on fp16 Q, K, V and P -- 11 significand bits instead of 8, the format the
+// reference's own GPU path uses (flash-attn on .half() tensors, vit_nlc.py:105-110) -- and hands its output to the
+// projection as a bf16 hi | lo pair; blocks outside the level keep bf16 operands.
 void Model::set_precision(int level) {
   CRA5_CHECK(level >= 0 && level <= 3, ERR_INVALID, "precision level must be 0 (bf16), 1 (tail), 2 (encoder) or 3 (all)");
   if (level > 0 && ws2_ == nullptr) {
@@ -160,8 +162,10 @@ void Model::set_precision(int level) {
     const size_t nb = (size_t)Bm;
     main_.a_half = nb * Tpad * D;
     main_.h_half = nb * T * mlp * D;
+    main_.o_half = nb * Tpad * D;
     hyper_.a_half = nb * Th * std::max<size_t>(Dh, kh_max);
     hyper_.h_half = nb * Th * hw;
+    hyper_.o_half = nb * Th * Dh;
     cat_half_ = nb * T * 2 * D;
     patches_half_ = nb * c.img_h * Wg * cs_pad;
     ytok_half_ = nb * T * lat;
@@ -169,8 +173,8 @@ void Model::set_precision(int level) {
     ah_half_ = nb * Th * kh_max;
     fin_half_ = nb * M2 * D;
     size_t total = 4096;
-    for (size_t half : {main_.a_half, main_.h_half, hyper_.a_half, hyper_.h_half, cat_half_, patches_half_, ytok_half_,
-                        ztok_half_, ah_half_, fin_half_})
+    for (size_t half : {main_.a_half, main_.h_half, main_.o_half, hyper_.a_half, hyper_.h_half, hyper_.o_half, cat_half_,
+                        patches_half_, ytok_half_, ztok_half_, ah_half_, fin_half_})
       total += align_up(2 * half * 2, 256);
     total += align_up(nb * T * mlp * D * 4, 256) + align_up(nb * Th * hw * 4, 256);
     CRA5_CUDA(cudaMalloc(&ws2_, total));
@@ -180,9 +184,11 @@ void Model::set_precision(int level) {
     main_.a2 = (__nv_bfloat16*)alloc2(2 * main_.a_half * 2);
     main_.h2 = (__nv_bfloat16*)alloc2(2 * main_.h_half * 2);
     main_.f32 = (float*)alloc2(nb * T * mlp * D * 4);
+    main_.o2 = (__nv_bfloat16*)alloc2(2 * main_.o_half * 2);
     hyper_.a2 = (__nv_bfloat16*)alloc2(2 * hyper_.a_half * 2);
     hyper_.h2 = (__nv_bfloat16*)alloc2(2 * hyper_.h_half * 2);
     hyper_.f32 = (float*)alloc2(nb * Th * hw * 4);
+    hyper_.o2 = (__nv_bfloat16*)alloc2(2 * hyper_.o_half * 2);
     cat2_ = (__nv_bfloat16*)alloc2(2 * cat_half_ * 2);
     patches2_ = (__nv_bfloat16*)alloc2(2 * patches_half_ * 2);
     ytok2_ = (__nv_bfloat16*)alloc2(2 * ytok_half_ * 2);
@@ -310,8 +316,8 @@ void Model::run_block(cudaStream_t st, const BlockWeights& w, const TrunkBuffers
     e.D = D; e.hd = hd_; e.rows_total = rows;
     e.qscale = 1.0f / sqrtf((float)hd_);
     TagScope tag_("qkv");
-    if (precise)
-      gemm_plain(st, EPI_QKV, ln_out, D, w.qkv_w3, D, rows, 3 * D, D, e, GemmSplit{tb.a_half, (size_t)3 * D * D});
+    if (precise)   // Q, K, V leave the epilogue as fp16
+      gemm_plain(st, EPI_QKV_F16, ln_out, D, w.qkv_w3, D, rows, 3 * D, D, e, GemmSplit{tb.a_half, (size_t)3 * D * D});
     else
       gemm_plain(st, EPI_QKV, tb.a, D, w.qkv_w, D, rows, 3 * D, D, e);
   }
@@ -323,18 +329,19 @@ void Model::run_block(cudaStream_t st, const BlockWeights& w, const TrunkBuffers
       part_from = (wm.nWr - 1) * wm.nWc;
       part_rows = (Hg - (wm.nWr - 1) * wm.wh) * wm.ww;
     }
-    attention_tc(st, tb.q, tb.k, tb.vt, tb.o, D, heads, rows, seg, part_from, part_rows,
-                 wm.enabled ? wm.nWr * wm.nWc : 1);
+    attention_tc(st, tb.q, tb.k, tb.vt, precise ? tb.o2 : tb.o, D, heads, rows, seg, part_from, part_rows,
+                 wm.enabled ? wm.nWr * wm.nWc : 1, precise, precise ? tb.o2 + tb.o_half : nullptr);
   }
   else
-    attention_simt(st, tb.q, tb.k, tb.vt, tb.o, D, heads, hd_, rows, seg);
+    attention_simt(st, tb.q, tb.k, tb.vt, precise ? tb.o2 : tb.o, D, heads, hd_, rows, seg, precise,
+                   precise ? tb.o2 + tb.o_half : nullptr);
   {
     EpiParams e{};
     e.bias = w.proj_b;
     e.resid = x_in; e.out_f32 = x_out; e.ldo = D; e.wm = wm;
     TagScope tag_("proj");
-    if (precise)   // the attention output is bf16 by construction: only the weight is split
-      gemm_plain(st, EPI_RESID, tb.o, D, w.proj_w3, D, rows, D, D, e, GemmSplit{0, (size_t)D * D});
+    if (precise)
+      gemm_plain(st, EPI_RESID, tb.o2, D, w.proj_w3, D, rows, D, D, e, GemmSplit{tb.o_half, (size_t)D * D});
     else
       gemm_plain(st, EPI_RESID, tb.o, D, w.proj_w, D, rows, D, D, e);
   }
@@ -379,7 +386,7 @@ void Model::run_block(cudaStream_t st, const BlockWeights& w, const TrunkBuffers
     taps_["blk.q"] = TensorRef{tb.q, CRA5_DT_BF16, (int64_t)rows * D};
     taps_["blk.k"] = TensorRef{tb.k, CRA5_DT_BF16, (int64_t)rows * D};
     taps_["blk.vt"] = TensorRef{tb.vt, CRA5_DT_BF16, (int64_t)rows * D};
-    taps_["blk.o"] = TensorRef{tb.o, CRA5_DT_BF16, (int64_t)rows * D};
+    taps_["blk.o"] = TensorRef{precise ? tb.o2 : tb.o, CRA5_DT_BF16, (int64_t)rows * D};
     taps_["blk.a"] = TensorRef{tb.a, CRA5_DT_BF16, (int64_t)T_ * D};
     taps_["blk.h"] = TensorRef{tb.h, CRA5_DT_BF16, (int64_t)T_ * mlp * D};
   }

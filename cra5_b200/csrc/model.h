@@ -52,6 +52,8 @@ struct TrunkBuffers {
   __nv_bfloat16* h2 = nullptr;   // [2][T][mlp*D]
   size_t h_half = 0;
   float* f32 = nullptr;          // [T][mlp*D] pre-activation of fc1 (GELU + split run as their own kernel)
+  __nv_bfloat16* o2 = nullptr;   // [2][Tpad][D] attention output hi | lo
+  size_t o_half = 0;
 };
 
 class Model {

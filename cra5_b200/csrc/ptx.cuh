@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace cra5 {
@@ -160,6 +161,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, shape M x N.
+// (operand format 1 = bf16, 0 = fp16)
+__host__ __device__ constexpr uint32_t umma_idesc_f16kind(uint32_t M, uint32_t N, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (0u << 15) | (0u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4)              // c_format = F32
          | (1u << 7)            // a_format = BF16

@@ -134,7 +134,9 @@ CRA5_API int cra5_model_set_coder(cra5_model* m, int streams_per_channel_y, int 
  *   2  1 + patch-embed conv and every g_a block: every layer the bitstream depends on
  *   3  2 + the decoder (post_quant_conv, g_s, reconstruction head)
  * A level needs the split copies "<name>.x3" (bf16 [2][N][K]: hi, lo) of the weights it covers, handed over with
- * cra5_model_set_tensor beforehand; ERR_STATE otherwise. Attention keeps bf16 Q/K/V/P at every level. */
+ * cra5_model_set_tensor beforehand; ERR_STATE otherwise. Attention inside a covered block runs on fp16 Q/K/V/P (the
+ * format of the reference's own GPU path, flash-attn on .half() tensors, vit_nlc.py:105-110) with an fp32 softmax and
+ * passes its output to the projection as a bf16 hi + lo pair. */
 CRA5_API int cra5_model_set_precision(cra5_model* m, int level);
 
 /* x (C,H,W) fp32 -> y (latent, Hg, Wg) fp32. mean/std: optional per-channel (C) device arrays; when given the input

@@ -73,10 +73,9 @@ class FrameTimer:
         self.cfg = cfg
         self.threads = threads or os.cpu_count()
         torch.set_num_threads(self.threads)
-        sd = init_state_dict(cfg, seed)
-        # the bench's entropy regime (bench.py: same two scalings as the GPU arm, so both arms code comparable symbols)
-        sd["quant_conv.weight"] = sd["quant_conv.weight"] * 6.0
-        sd["h_s.final.weight"] = sd["h_s.final.weight"] * 12.0
+        from cra5_b200.synthetic import bench_regime
+        # the bench's entropy regime: the same weights as the GPU arm, so both arms code comparable symbols
+        sd = bench_regime(init_state_dict(cfg, seed), cfg)
         self.codec = VO.OracleCodec(sd, cfg)
         ans = _ref_coder()
         self.coder_kind = "reference C++ coder (oracle/_ref), list-in/list-out as entropy_models.py calls it" \

@@ -95,3 +95,33 @@ def test_full_size_268_round_trip_against_fp32_oracle():
     base = roundtrip(net, 0)
     assert CodecLanes(net, lanes=2).run(roundtrip, 6) == [base] * 6
     assert 1e6 < len(out["strings"][0][0]) < 12e6
+
+
+def test_full_size_batch_of_4_equals_frame_by_frame():
+    """batch invariance at BASELINE.json's size: 4 x 268 x 721 x 1440 frames in one call (one launch per kernel; the GEMMs
+    see 41 472 rows) reproduce four single-frame calls bit for bit -- latents, every container, the decoded latents and
+    the reconstructions. (The reduced-width fixtures in test_gpu_batch.py never reach the tile counts of this size.)"""
+    from cra5_b200.synthetic import bench_regime
+    from cra5_b200.vaeformer import VAEformer, init_state_dict
+    cfg = C.cra5_268()
+    sd = bench_regime(init_state_dict(cfg, 5), cfg)
+    x = torch.randn(4, cfg.in_chans, *cfg.img_size, device="cuda", generator=torch.Generator(device="cuda").manual_seed(11))
+    outs = []
+    for mb in (1, 4):
+        net = VAEformer(268, cfg=cfg, init_seed=None, max_batch=mb)
+        net.load_state_dict(sd)
+        net.update(force=True)
+        with torch.no_grad():
+            y, _, _ = net.encode_latent(x, type="float")
+            o = net.compress_from_latent(y)
+            y_hat = net.decompress(o["strings"], o["z_shape"], return_format="latent")
+            x_hat = net.decode_latent(y_hat)
+        outs.append((y.cpu(), list(o["strings"][0]), list(o["strings"][1]), y_hat.cpu(), x_hat.cpu()))
+        del net
+        torch.cuda.empty_cache()
+    (y1, sy1, sz1, yh1, xh1), (y4, sy4, sz4, yh4, xh4) = outs
+    assert torch.equal(y4, y1) and sy4 == sy1 and sz4 == sz1 and torch.equal(yh4, yh1) and torch.equal(xh4, xh1)
+    # the bench's entropy regime (cra5_b200/synthetic.py): about 2 MB per frame, like real CRA5 frames
+    per_frame = [len(a) + len(b) for a, b in zip(sy1, sz1)]
+    print(f"\n[full size 268, bench regime] bytes per frame {per_frame}")
+    assert all(1.2e6 < n < 3.5e6 for n in per_frame)

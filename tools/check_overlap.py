@@ -68,9 +68,8 @@ def child(n_lanes, spc_y=16):
     cfg = C.cra5_268()
     net = VAEformer(268, cfg=cfg, init_seed=1234)
     sd = {k: v for k, v in net.state_dict().items() if k in C.param_shapes(cfg)}
-    sd["quant_conv.weight"] = sd["quant_conv.weight"] * 6.0      # bench.py's entropy regime
-    sd["h_s.final.weight"] = sd["h_s.final.weight"] * 12.0
-    net.load_state_dict(sd)
+    from cra5_b200.synthetic import bench_regime
+    net.load_state_dict(bench_regime(sd, cfg))                   # bench.py's entropy regime
     net.update(force=True)
     net.set_coder(spc_y, 4)
     g = torch.Generator(device="cuda").manual_seed(1000)
