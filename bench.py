@@ -193,20 +193,24 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def ncu_traffic(kernel):
+def ncu_traffic(kernel, batch):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
-    captures (profiles/r1_traffic.json; a number measured under the profiler, so it is read, never re-measured here)"""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if not os.path.exists(p):
+    captures (profiles/r2_traffic.json, taken at 8 frames per launch and scaled to this run's batch; a number measured
+    under the profiler, so it is read, never re-measured here)"""
+    for rnd in ("r2", "r1"):
+        p = os.path.join(ROOT, "profiles", f"{rnd}_traffic.json")
+        if os.path.exists(p):
+            break
+    else:
         return None, "no capture committed"
     t = json.load(open(p))
     sites = {"gemm_tc": ["qkv", "proj", "fc1", "fc2"], "attn_tc": ["attn_global"], "rans_decode": ["rans_dec"],
-             "rans_encode": ["rans_enc"], "gc_quantize_index": ["quantize"], "layernorm_bf16": ["layernorm"]}.get(kernel, [])
-    vals = [t[s]["dram_bytes_per_launch"] for s in sites if s in t]
+             "rans_encode": ["rans_enc"], "gc_quantize_index": ["quantize_encode", "quantize"], "layernorm_bf16": ["layernorm"]}.get(kernel, [])
+    vals = [t[s]["dram_bytes_per_launch"] * batch / t[s].get("frames_per_launch", 1) for s in sites if s in t]
     if not vals:
         return None, "no capture of this kernel"
-    return sum(vals) / len(vals), ("profiles/r1_traffic.json: mean over the captured launches " + "/".join(s for s in sites if s in t)
-                                   + " (one trunk block; cold-cache single launches under ncu)")
+    return sum(vals) / len(vals), (f"profiles/{rnd}_traffic.json: mean over the captured launches " + "/".join(s for s in sites if s in t)
+                                   + " (one trunk block; cold-cache single launches under ncu, scaled to this batch size)")
 
 
 def measure_entropy_b8(dev, cfg):
@@ -410,7 +414,7 @@ def run_b200(args):
         del src
     e2e = None
     if host_in is not None:
-        pipe = FramePipeline(api)
+        pipe = FramePipeline(api, bin_dir=api.local_root)   # strings travel through a real .bin file (tmpfs)
 
         def e2e_run(n):
             """public streaming API: pinned host frames in, bitstreams + pinned host reconstructions out; the H2D of
@@ -434,9 +438,10 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": world * n_e2e / float(t.item()), "unit": "frames/s", "h2d_bytes_per_step": frame_bytes + nbytes,
                "d2h_bytes_per_step": frame_bytes + nbytes, "steps": n_e2e, "pinned_on_gpu_numa_node": bool(numa_bound),
-               "path": "cra5_b200.stream.FramePipeline over cra5_api: pinned host frame -> H2D -> encode_to_latent "
-                       "(normalisation fused) -> latent_to_bin -> bin strings -> bin_to_latent -> "
-                       "latent_to_reconstruction -> D2H -> pinned host; copies on side streams overlap compute"}
+               "path": "cra5_b200.stream.FramePipeline over cra5_api, one frame per call: pinned host frame -> H2D -> "
+                       "encode_to_latent (normalisation fused) -> latent_to_bin -> write_bin(.bin on tmpfs) -> "
+                       "bin_to_latent(path) -> latent_to_reconstruction -> D2H -> pinned host; copies on side streams "
+                       "overlap compute"}
 
     # ---- per-kernel profile (CUDA events on the launch stream, separate pass so the events do not perturb `value`)
     roofline, kernels, sites = None, None, None
@@ -459,7 +464,7 @@ def run_b200(args):
                 a[f] += k[f]
         top = max(by_kernel.items(), key=lambda kv: kv[1]["ms"])
         tname, tk = top
-        traffic, traffic_src = ncu_traffic(tname)
+        traffic, traffic_src = ncu_traffic(tname, B)
         if tk["flops"] > 0:
             achieved = tk["flops"] / (tk["ms"] / 1e3) / 1e12
             roofline = {"kernel": tname, "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"],

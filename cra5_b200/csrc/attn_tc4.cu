@@ -146,6 +146,41 @@ __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.al
 template <int N>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
+// exponentials of one 128-score row against the reference maximum folded into nm = -m_ref * log2(e): P as packed
+// 16-bit pairs (bf16, or fp16 for the split-precision levels) and the fp32 row sum
+template <int POLY, bool F16>
+__device__ __forceinline__ float softmax_row(const uint32_t (&s)[A4_BN], float nm, uint32_t (&pk)[A4_BN / 2]) {
+  constexpr float LOG2E = 1.4426950408889634f;
+  const uint64_t l2e2 = pack2(LOG2E, LOG2E);
+  const uint64_t nm2 = pack2(nm, nm);
+  uint64_t sum_a = pack2(0.f, 0.f), sum_b = pack2(0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < A4_BN / 2; ++q) {
+    const int i = 2 * q;
+    const uint64_t xs = fma2(pack2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), l2e2, nm2);
+    float e0, e1;
+    if ((q & 7) < POLY) {
+      ex2_poly2(xs, e0, e1);
+    } else {
+      float x0, x1;
+      unpack2(xs, x0, x1);
+      e0 = ex2_mufu(x0);
+      e1 = ex2_mufu(x1);
+    }
+    if (q & 1) sum_b = add2(sum_b, pack2(e0, e1)); else sum_a = add2(sum_a, pack2(e0, e1));
+    if constexpr (F16) {
+      const __half2 hp = __floats2half2_rn(e0, e1);
+      pk[q] = *reinterpret_cast<const uint32_t*>(&hp);
+    } else {
+      pk[q] = pack_bf16x2(e0, e1);
+    }
+  }
+  float a0, a1, b0, b1;
+  unpack2(sum_a, a0, a1);
+  unpack2(sum_b, b0, b1);
+  return (a0 + a1) + (b0 + b1);
+}
+
 struct Item {
   int head, seg, q0;
   bool act_a, act_b;
@@ -166,6 +201,11 @@ __device__ __forceinline__ Item decode_item(const A4Params& p, int item) {
 // POLY: of every 8 column pairs, this many take the polynomial exp2. F16: Q, K, V arrive as fp16 (EPI_QKV_F16) and P is
 // written as fp16 -- 11 instead of 8 significand bits on every attention operand, the format the reference's own GPU
 // path uses (flash-attn on .half() tensors, vit_nlc.py:105-110); same tcgen05 kind::f16 pipeline, same speed.
+// (Tried and dropped in round 2, tools/perf_attn.py: four instead of two running maxima per row -- no change, the
+// FMNMX3 chain already hides behind the second TMEM load; computing the exponentials speculatively against the previous
+// reference maximum while the tile maximum is still being reduced -- the scores then have to stay live for a possible
+// redo and the kernel spills. POLY = 3 remains the best split: 907 / 881 / 726 TFLOP/s for POLY 3 / 2 / 4 on the global
+// shape at 8 frames per launch.)
 template <int POLY, bool F16>
 __global__ void __launch_bounds__(A4_THREADS, 1)
 attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -337,7 +377,6 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t t_o = tmem_base + lane_addr + TM_O + x * A4_HD;
     constexpr float LOG2E = 1.4426950408889634f;
     constexpr float RESCALE_TH = 8.0f / LOG2E;  // move the reference maximum only for growth beyond 2^8
-    const uint64_t l2e2 = pack2(LOG2E, LOG2E);
     uint32_t cnt = 0;                           // steps processed by this tile (phases of all four barriers)
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -390,6 +429,8 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
         const float mt = fmaxf(mt0, mt1);
+        uint32_t pk[NC / 2];                      // P as packed 16-bit pairs
+        float lsum = 0.f;
         if (j == 0) {
           m_ref = mt;
         } else if (__any_sync(0xffffffffu, mt > m_ref + RESCALE_TH)) {
@@ -418,37 +459,8 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           tmem_st_wait();
         }
-        const float nm = -m_ref * LOG2E;
-        const uint64_t nm2 = pack2(nm, nm);
-        uint64_t sum_a = pack2(0.f, 0.f), sum_b = pack2(0.f, 0.f);
-        uint32_t pk[NC / 2];                      // P as packed bf16 pairs
-#pragma unroll
-        for (int q = 0; q < NC / 2; ++q) {
-          const int i = 2 * q;
-          const uint64_t xs = fma2(pack2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), l2e2, nm2);
-          float e0, e1;
-          if ((q & 7) < POLY) {
-            ex2_poly2(xs, e0, e1);
-          } else {
-            float x0, x1;
-            unpack2(xs, x0, x1);
-            e0 = ex2_mufu(x0);
-            e1 = ex2_mufu(x1);
-          }
-          if (q & 1) sum_b = add2(sum_b, pack2(e0, e1)); else sum_a = add2(sum_a, pack2(e0, e1));
-          if constexpr (F16) {
-            const __half2 hp = __floats2half2_rn(e0, e1);
-            pk[q] = *reinterpret_cast<const uint32_t*>(&hp);
-          } else {
-            pk[q] = pack_bf16x2(e0, e1);
-          }
-        }
-        {
-          float a0, a1, b0, b1;
-          unpack2(sum_a, a0, a1);
-          unpack2(sum_b, b0, b1);
-          l += (a0 + a1) + (b0 + b1);
-        }
+        lsum = softmax_row<POLY, F16>(s, -m_ref * LOG2E, pk);
+        l += lsum;
         // the previous PV product of this tile reads P: it must have retired before P is overwritten (it was issued a
         // whole softmax step ago, so this wait does not stall in steady state)
         if (j > 0) {

@@ -215,6 +215,14 @@ int cra5_latent_to_reconstruction_batch(cra5_model* m, const float* y_hat, float
     m->impl->latent_to_reconstruction(y_hat, x_hat, batch, static_cast<cudaStream_t>(stream));
   });
 }
+int cra5_latent_to_reconstruction_denorm(cra5_model* m, const float* y_hat, float* x_hat, const float* mean,
+                                         const float* std_, int batch, void* stream) {
+  return guarded([&] {
+    MODEL_GUARD(m);
+    CRA5_CHECK(y_hat && x_hat && mean && std_, ERR_INVALID, "null tensor");
+    m->impl->latent_to_reconstruction(y_hat, x_hat, batch, static_cast<cudaStream_t>(stream), mean, std_);
+  });
+}
 int cra5_latent_to_reconstruction(cra5_model* m, const float* y_hat, float* x_hat, void* stream) {
   return cra5_latent_to_reconstruction_batch(m, y_hat, x_hat, 1, stream);
 }

@@ -164,6 +164,8 @@ struct EpiParams {
   int ct_sh;     // vertical stride
   int ct_Wp;     // tokens per row
   int ct_Himg, ct_Wimg;
+  const float *ct_mean, *ct_std;   // optional per-channel de-normalisation fused into the store: x * std[c] + mean[c]
+                                   // (cra5_api.de_normalization, cra5_api.py:268-271); null = normalised units
 };
 
 // exact (erf) GELU, nn.GELU default (vit_nlc.py:53). erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32
@@ -371,7 +373,8 @@ __device__ __forceinline__ void epilogue_store(const EpiParams& p, int row, int 
       const int c = cs / p.ct_pw, s = cs - c * p.ct_pw;
       const int h = p.ct_sh * i_ + p.ct_r0 + rr;
       if (h < p.ct_Himg)
-        outb[((size_t)c * p.ct_Himg + h) * p.ct_Wimg + p.ct_pw * j_ + s] = v[i];
+        outb[((size_t)c * p.ct_Himg + h) * p.ct_Wimg + p.ct_pw * j_ + s] =
+            (p.ct_std != nullptr) ? fmaf(v[i], __ldg(p.ct_std + c), __ldg(p.ct_mean + c)) : v[i];
     }
   }
 }
@@ -495,6 +498,8 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& p, const float* s
     const int rk = col / p.ct_CS, cs = col - rk * p.ct_CS;
     const int c = cs / p.ct_pw, s_ = cs - c * p.ct_pw;
     float* plane = p.out_f32 + (size_t)c * p.ct_Himg * p.ct_Wimg + s_;
+    const float dn_s = (p.ct_std != nullptr) ? __ldg(p.ct_std + c) : 1.0f;     // a lane's column fixes its channel
+    const float dn_m = (p.ct_std != nullptr) ? __ldg(p.ct_mean + c) : 0.0f;
     int rf = row_base;
     const int i_per = (p.fr_rows > 0) ? p.fr_rows / p.ct_Wp : (1 << 30);   // patch rows per frame (batch of frames)
     if (p.fr_rows > 0) {
@@ -506,7 +511,9 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& p, const float* s
 #pragma unroll 8
     for (int rr = 0; rr < rows_valid; ++rr) {
       const int h = p.ct_sh * i_ + p.ct_r0 + rk;
-      if (h < p.ct_Himg) plane[(size_t)h * p.ct_Wimg + p.ct_pw * j_] = stg[rr * STG_LD + lane];
+      if (h < p.ct_Himg)
+        plane[(size_t)h * p.ct_Wimg + p.ct_pw * j_] =
+            (p.ct_std != nullptr) ? fmaf(stg[rr * STG_LD + lane], dn_s, dn_m) : stg[rr * STG_LD + lane];
       if (++j_ == p.ct_Wp) {
         j_ = 0;
         if (++i_ == i_per) { i_ = 0; plane += p.fr_stride; }

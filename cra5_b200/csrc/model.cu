@@ -778,8 +778,10 @@ void Model::bin_to_latent(const uint8_t* const* y_bytes, const size_t* y_len, co
 }
 
 // VAEformer.decode_latent (vaeformer.py:294-300): post_quant_conv + ViT_Decoder.forward (vit_nlc.py:682-693)
-void Model::latent_to_reconstruction(const float* y_hat, float* x_hat, int B, cudaStream_t st) {
+void Model::latent_to_reconstruction(const float* y_hat, float* x_hat, int B, cudaStream_t st, const float* mean,
+                                      const float* std_) {
   finalize();
+  CRA5_CHECK((mean == nullptr) == (std_ == nullptr), ERR_INVALID, "mean and std must be given together");
   const cra5_config& c = cfg_;
   const int D = c.dim, lat = c.latent_chans, CS = c.in_chans * c.patch_w;
   CRA5_CHECK(B >= 1 && B <= Bm, ERR_INVALID, "batch larger than the model's max_batch");
@@ -827,6 +829,7 @@ void Model::latent_to_reconstruction(const float* y_hat, float* x_hat, int B, cu
     EpiParams e{};
     e.out_f32 = x_hat;
     e.ct_CS = CS; e.ct_pw = c.patch_w; e.ct_sh = c.stride_h; e.ct_Wp = Wg; e.ct_Himg = c.img_h; e.ct_Wimg = c.img_w;
+    e.ct_mean = mean; e.ct_std = std_;   // de-normalisation fused into the un-patchify store
     e.fr_rows = M2; e.fr_stride = frame_out;
     if (nA > 0) {
       e.ct_r0 = nB;
@@ -880,6 +883,9 @@ void Model::latent_to_reconstruction(const float* y_hat, float* x_hat, int B, cu
     else
       gemm_plain(st, EPI_PIXSHUF, main_.a, D, (const __nv_bfloat16*)need("g_s.final.weight", CRA5_DT_BF16, (int64_t)Nf * D), D, TB,
                  Nf, D, e);
+    if (mean != nullptr)   // the Linear head (non-ERA5 geometries) has no fused form: one extra pass per frame
+      for (int b = 0; b < B; ++b)
+        affine_channels(st, x_hat + b * frame_out, x_hat + b * frame_out, mean, std_, (size_t)c.img_h * c.img_w, c.in_chans, 0);
   }
 }
 

@@ -74,7 +74,9 @@ class Model {
   // hot path (all pointers device, fp32). B frames (<= max_batch, contiguous in every tensor) run as ONE launch per
   // kernel: B * tokens rows through every GEMM / LayerNorm / attention, B * channels through the entropy kernels.
   void encode_to_latent(const float* x, float* y, const float* mean, const float* std_, int B, cudaStream_t st);
-  void latent_to_reconstruction(const float* y_hat, float* x_hat, int B, cudaStream_t st);
+  // mean / std (per channel, device) optionally fuse x * std + mean into the un-patchify store
+  void latent_to_reconstruction(const float* y_hat, float* x_hat, int B, cudaStream_t st, const float* mean = nullptr,
+                                const float* std_ = nullptr);
   void latent_quantized(const float* y, float* y_hat, cudaStream_t st);  // encode_latent(type='quantized') tail
   // same, plus the likelihood tensors of the eval-mode forward (rate estimation); any output may be null
   void latent_likelihoods(const float* y, float* y_hat, float* y_lik, float* z_lik, cudaStream_t st);

@@ -250,10 +250,14 @@ class FramePipeline:
     tensors that receive the (normalised) reconstructions round-robin -- an entry is valid until it is reused.
     """
 
-    def __init__(self, api, roundtrip: bool = True):
+    def __init__(self, api, roundtrip: bool = True, bin_dir: str = None):
+        """bin_dir: when given, every frame's strings go through the reference's `.bin` container on disk -- written
+        with api/utils.write_bin (cra5_api.py:108-116) and read back by `api.bin_to_latent(path)` (:127-144) -- instead
+        of being handed to the decoder in memory; four files are reused round-robin."""
         import torch
         self.api = api
         self.roundtrip = roundtrip
+        self.bin_dir = bin_dir
         self.dev = torch.device(api.device)
         self.copy_in = torch.cuda.Stream(self.dev)
         self.copy_out = torch.cuda.Stream(self.dev)
@@ -292,7 +296,13 @@ class FramePipeline:
             if not self.roundtrip:
                 yield i, out["strings"], None
                 continue
-            y_hat = api.net.decompress(out["strings"], out["z_shape"], return_format="latent")
+            if self.bin_dir is not None:
+                from .api.utils import write_bin
+                path = f"{self.bin_dir}/frame_{i % 4}.bin"
+                write_bin(path, out["strings"], out["z_shape"])
+                y_hat = api.bin_to_latent(path)
+            else:
+                y_hat = api.net.decompress(out["strings"], out["z_shape"], return_format="latent")
             x_hat = api.latent_to_reconstruction(y_hat)       # post_quant_conv + g_s
             done = torch.cuda.Event()
             done.record(main)

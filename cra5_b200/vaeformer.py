@@ -446,15 +446,21 @@ class VAEformer:
                                                             _lib.ptr(y_lik[b]), _lib.ptr(self._z_likelihoods[b]), s))
         return y, y_hat, y_lik
 
-    def decode_latent(self, y, type="quantized"):
+    def decode_latent(self, y, type="quantized", mean=None, std=None):
+        """`mean` / `std` (C,) optionally fuse the de-normalisation x * std + mean into the last kernel (additive
+        extension; cra5_api.decode_from_bin uses it for return_format='de_normalized')"""
         y = self._check_y(y)
         cfg = self.cfg
         x_hat = torch.empty((y.shape[0], cfg.in_chans, *cfg.img_size), device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
             s = _lib.stream_ptr()
             for b0, nb in self._chunks(y.shape[0]):
-                _lib.check(_lib.lib.cra5_latent_to_reconstruction_batch(self._handle, _lib.ptr(y[b0]), _lib.ptr(x_hat[b0]),
-                                                                        nb, s))
+                if mean is not None:
+                    _lib.check(_lib.lib.cra5_latent_to_reconstruction_denorm(
+                        self._handle, _lib.ptr(y[b0]), _lib.ptr(x_hat[b0]), _lib.ptr(mean), _lib.ptr(std), nb, s))
+                else:
+                    _lib.check(_lib.lib.cra5_latent_to_reconstruction_batch(self._handle, _lib.ptr(y[b0]),
+                                                                            _lib.ptr(x_hat[b0]), nb, s))
         return x_hat
 
     def compress_from_latent(self, y):

@@ -190,6 +190,13 @@ CRA5_API int cra5_bin_to_latent_batch(cra5_model* m, const uint8_t* const* y_byt
 CRA5_API int cra5_latent_to_reconstruction_batch(cra5_model* m, const float* y_hat_dev, float* x_hat_dev, int batch,
                                                  void* stream);
 
+/* cra5_latent_to_reconstruction_batch with the de-normalisation of cra5_api.decode_from_bin(return_format=
+ * 'de_normalized') fused into the last kernel's stores: x_hat[c] = x_hat_normalised[c] * std[c] + mean[c]
+ * (cra5_api.de_normalization, cra5_api.py:268-271) -- no separate read-modify-write pass over the 1.1 GB frame.
+ * mean / std: per-channel (C) device arrays. */
+CRA5_API int cra5_latent_to_reconstruction_denorm(cra5_model* m, const float* y_hat_dev, float* x_hat_dev,
+                                                  const float* mean_dev, const float* std_dev, int batch, void* stream);
+
 /* per-channel (x - mean)/std (forward != 0) or x*std + mean (forward == 0); in == out allowed.
  * Replaces cra5_api.normalization / de_normalization (cra5_api.py:264-271). */
 CRA5_API int cra5_normalize(const float* in_dev, float* out_dev, const float* mean_dev, const float* std_dev,

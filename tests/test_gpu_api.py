@@ -78,3 +78,11 @@ def test_pipeline_matches_synchronous_calls(api):
     for (idx, strings, rec), (es, ex) in zip(got, expect):
         assert strings[0][0] == es[0][0] and strings[1][0] == es[1][0]
         assert torch.equal(rec, ex)
+    # the same stream with every frame's strings going through a real .bin file (write_bin -> bin_to_latent(path)):
+    # what bench.py's end-to-end leg times
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        got2 = [(i, st, r.clone()) for i, st, r in FramePipeline(api, bin_dir=d).run(frames, outs, n_frames=3)]
+        assert sorted(os.listdir(d)) == ["frame_0.bin", "frame_1.bin", "frame_2.bin"]
+    for (idx, strings, rec), (es, ex) in zip(got2, expect):
+        assert strings[0][0] == es[0][0] and torch.equal(rec, ex)

@@ -125,3 +125,43 @@ def test_full_size_batch_of_4_equals_frame_by_frame():
     per_frame = [len(a) + len(b) for a, b in zip(sy1, sz1)]
     print(f"\n[full size 268, bench regime] bytes per frame {per_frame}")
     assert all(1.2e6 < n < 3.5e6 for n in per_frame)
+
+
+@pytest.mark.parametrize("chans", [159, 69])
+def test_full_width_other_channel_counts_against_fp32_oracle(chans):
+    """SURVEY 8f-4 / BASELINE.json configs[1] and [4]: the same architecture at 159 variables
+    (config/vaeformer_era5_159v_1h.py:41-50) and at 69, full width and depth, one frame against the fp32 oracle: latent and
+    reconstruction within bf16 tolerance, integer stage bit-exact on the GPU's own floats, coder round trip bit-exact,
+    per-variable RMSE within 1e-4 of the reference path's."""
+    from cra5_b200.synthetic import bench_regime
+    from cra5_b200.vaeformer import init_state_dict
+    from cra5_b200.zoo import vaeformer_pretrained
+    cfg = C.variant(chans)
+    sd = bench_regime(init_state_dict(cfg, 4), cfg)
+    net = vaeformer_pretrained(quality=chans, pretrained=False, init_seed=None)     # the zoo entry itself
+    assert net.cfg.in_chans == chans
+    net.load_state_dict(sd)
+    net.update(force=True)
+    codec = VO.OracleCodec(sd, cfg)
+    x = torch.randn(1, chans, *cfg.img_size, generator=torch.Generator().manual_seed(2000 + chans))
+    shape = (1, cfg.latent_chans, *cfg.grid)
+    with torch.no_grad():
+        y_g, _, _ = net.encode_latent(x.cuda(), type="float")
+        out = net.compress_from_latent(y_g)
+        mu_g, sc_g = net.tap("means").reshape(shape).cpu(), net.tap("scales").reshape(shape).cpu()
+        ysym_g, yidx_g = net.tap("y_symbols").cpu(), net.tap("y_indexes").cpu()
+        y_hat_g = net.decompress(out["strings"], out["z_shape"], return_format="latent")
+        assert torch.equal(net.tap("y_symbols").cpu(), ysym_g)
+        x_g = net.decode_latent(y_hat_g).cpu()
+        y_o = VO.encode_y(codec.sd, cfg, x)
+        dbg = codec.compress_from_latent(y_o)["debug"]
+        x_o = VO.decode_y(codec.sd, cfg, dbg["y_symbols"].float() + dbg["means"])
+        x_o_given_g = VO.decode_y(codec.sd, cfg, y_hat_g.cpu())
+    assert rel_rms(y_g, y_o) <= 1.5e-2 and rel_rms(x_g, x_o_given_g) <= 1.5e-2
+    assert torch.equal(EO.quantize_symbols(y_g.cpu(), mu_g).reshape(-1), ysym_g)
+    assert torch.equal(EO.build_indexes(sc_g, codec.gc.scale_table).reshape(-1).to(torch.uint8), yidx_g)
+    rm_g = ((x_g[0] - x[0]) ** 2).mean(dim=(1, 2)).sqrt()
+    rm_o = ((x_o[0] - x[0]) ** 2).mean(dim=(1, 2)).sqrt()
+    print(f"\n[full width, {chans} variables] latent rel-rms {rel_rms(y_g, y_o):.2e}, max |dRMSE| {(rm_g - rm_o).abs().max():.2e}, "
+          f"{len(out['strings'][0][0]) + len(out['strings'][1][0])} bytes")
+    assert (rm_g - rm_o).abs().max().item() <= 1e-4
