@@ -444,7 +444,7 @@ def run_b200(args):
                        "overlap compute"}
 
     # ---- per-kernel profile (CUDA events on the launch stream, separate pass so the events do not perturb `value`)
-    roofline, kernels, sites = None, None, None
+    roofline, kernels, sites, entropy_product = None, None, None, None
     if not args.no_kernel_profile and rank == 0:
         peaks = measured_peaks()
         _lib.check(_lib.lib.cra5_profile_enable(1))
@@ -491,6 +491,17 @@ def run_b200(args):
         for n in ("gc_quantize_index", "rans_encode", "rans_decode"):
             if n in kernels and kernels[n]["gbs"]:
                 kernels[n]["hbm_frac"] = kernels[n]["gbs"] / peaks["hbm_gbs"]
+        # ... and the fused quantise + scale-index launch of the ENCODE side on its own (read y, sigma, mu; write int32
+        # symbol + uint8 index = 17 B per element), as the product path issues it: once per batch
+        entropy_product = None
+        raw = json.loads(buf.value.decode())
+        q = raw.get("gc_quantize_index:encode")
+        if q and q["ms"]:
+            gbs = q["bytes"] / (q["ms"] / 1e3) / 1e9
+            entropy_product = {"kernel": "gc_quantize_index", "site": "latent_to_bin (encode side)", "frames_per_launch": B,
+                               "ms_per_launch": q["ms"] / q["launches"], "achieved": gbs, "unit": "GB/s",
+                               "peak": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"], "bound": "hbm",
+                               "algorithmic_bytes_per_element": 17}
 
     # ---- the fused quantise + scale-index kernel at B = 8 (at B = 1 its 45 MB launch lasts 15 us and is
     #      launch-latency bound; BASELINE.json configs[4] batches 8 frames per GPU): 8 frames' latents in one launch,
@@ -533,7 +544,7 @@ def run_b200(args):
             "gb_era5_per_s": fps * frame_bytes / 1e9,
             "e2e": e2e, "gpu_launches": int(lane_launches if lane_launches is not None else lc1.value - lc0.value),
             "clocks": clock_info,
-            "roofline": roofline, "entropy_b8": entropy_b8, "kernels": kernels, "kernel_sites": sites if kernels else None, "cpu_baseline": cpu,
+            "roofline": roofline, "entropy_product": entropy_product, "entropy_b8": entropy_b8, "kernels": kernels, "kernel_sites": sites if kernels else None, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

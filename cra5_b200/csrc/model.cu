@@ -694,7 +694,10 @@ void Model::latent_to_bin(const float* y, int B, const uint8_t** y_bytes, size_t
   taps_["z_symbols"] = TensorRef{zsym_, CRA5_DT_I32, (int64_t)B * zc * Th};
   taps_["z_hat"] = TensorRef{zhat_, CRA5_DT_F32, (int64_t)B * zc * Th};
   run_h_s(st, zhat_, B);
-  gc_quantize_index(st, y, params_, params_ + n, table, gc_.rows, SCALE_BOUND, ysym_, yidx_, nullptr, n, B, 2 * n);
+  {
+    TagScope tag_("encode");   // symbols + indexes: the 17 B/element launch the HBM roofline target is stated for
+    gc_quantize_index(st, y, params_, params_ + n, table, gc_.rows, SCALE_BOUND, ysym_, yidx_, nullptr, n, B, 2 * n);
+  }
   taps_["y_symbols"] = TensorRef{ysym_, CRA5_DT_I32, (int64_t)(B * n)};
   taps_["y_indexes"] = TensorRef{yidx_, CRA5_DT_U8, (int64_t)(B * n)};
   if (spc_y_ > 0 && spc_z_ > 0) {
@@ -750,7 +753,10 @@ void Model::bin_to_latent(const uint8_t* const* y_bytes, const size_t* y_len, co
       taps_["z_symbols"] = TensorRef{zsym_, CRA5_DT_I32, (int64_t)B * zc * Th};
       taps_["z_hat"] = TensorRef{zhat_, CRA5_DT_F32, (int64_t)B * zc * Th};
       run_h_s(st, zhat_, B);
-      gc_quantize_index(st, nullptr, params_, nullptr, table, gc_.rows, SCALE_BOUND, nullptr, yidx_, nullptr, n, B, 2 * n);
+      {
+        TagScope tag_("decode_idx");   // decode side: indexes only (4 B in, 1 B out per element)
+        gc_quantize_index(st, nullptr, params_, nullptr, table, gc_.rows, SCALE_BOUND, nullptr, yidx_, nullptr, n, B, 2 * n);
+      }
       // frame f's means start at params_ + n + f * 2n while its symbols start at f * n: n extra elements per frame
       any = coder_->decode_cr5b(st, y_bytes, y_len, B, yidx_, gc_, lat, T, ysym_, params_ + n, nullptr, y_hat, y_off, false,
                                 n) || any;
