@@ -30,6 +30,21 @@ __device__ __forceinline__ int scale_index(float sigma, const float* __restrict_
   return lo;
 }
 
+// The same index for a (near) log-spaced table -- get_scale_table() is exp(linspace(ln 0.11, ln 256, 64)),
+// models/base.py:54-61 -- without the 6 dependent shared-memory probes: log2(s) * a + b lands within +-0.25 of the
+// fractional position (checked per launch against every table entry, see the kernel prologue), so ceil() is within one
+// step of the answer and two compares against the EXACT table entries finish it. Same integer as scale_index() for
+// every input; the kernel was issue-bound on the search (22 instructions per element, ALU pipe 58 %, ncu round 2).
+__device__ __forceinline__ int scale_index_log(float sigma, const float* __restrict__ tab, int levels, float bound,
+                                               float a, float b) {
+  const float s = fmaxf(sigma, bound);
+  int g = __float2int_ru(fmaf(__log2f(s), a, b));
+  g = min(max(g, 0), levels - 1);
+  g -= (g > 0 && s <= tab[g - 1]) ? 1 : 0;
+  g += (g < levels - 1 && s > tab[g]) ? 1 : 0;
+  return g;
+}
+
 __global__ void __launch_bounds__(256)
 gc_quantize_index_kernel(const float* __restrict__ y, const float* __restrict__ sigma, const float* __restrict__ mu,
                          const float* __restrict__ scale_table, int levels, float bound, int32_t* __restrict__ sym,
@@ -39,10 +54,25 @@ gc_quantize_index_kernel(const float* __restrict__ y, const float* __restrict__ 
   if (scale_table != nullptr)   // only needed for the index output; callers that want symbols / y_hat alone pass null
     for (int i = threadIdx.x; i < levels; i += blockDim.x) tab[i] = scale_table[i];
   __syncthreads();
+  // is the table log-spaced (every entry within a quarter step of its predicted position)? block-uniform answer
+  float la = 0.f, lb = 0.f;
+  int fast = 0;
+  if (idx != nullptr && levels >= 4 && tab[0] > 0.f && tab[levels - 1] > tab[0]) {
+    const float l0 = __log2f(tab[0]), l1 = __log2f(tab[levels - 1]);
+    la = (float)(levels - 1) / (l1 - l0);
+    lb = -l0 * la;
+    int ok = 1;
+    for (int i = threadIdx.x; i < levels; i += blockDim.x)
+      ok = ok && (fabsf(fmaf(__log2f(tab[i]), la, lb) - (float)i) < 0.25f) && (i == 0 || tab[i] > tab[i - 1]);
+    fast = __syncthreads_and(ok);
+  }
   const size_t n4 = n >> 2;
   // frames > 1 (host guarantees n % 4 == 0 and param_stride % 4 == 0): element group g of the batch lives at e = g in
   // the per-frame-contiguous tensors (y, sym, idx, y_hat) and at ep = frame * param_stride / 4 + g % n4 in sigma / mu
   const size_t total4 = n4 * (size_t)frames;
+  // (unrolled: the loads of two iterations are independent and issue back to back -- the kernel is bound by memory-level
+  // parallelism, not by the 6-step table search)
+#pragma unroll 2
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total4; e += (size_t)gridDim.x * blockDim.x) {
     size_t ep = e;
     if (frames > 1) {
@@ -63,10 +93,17 @@ gc_quantize_index_kernel(const float* __restrict__ y, const float* __restrict__ 
     if (idx != nullptr) {
       const float4 sv = reinterpret_cast<const float4*>(sigma)[ep];
       uchar4 q;
-      q.x = (unsigned char)scale_index(sv.x, tab, levels, bound);
-      q.y = (unsigned char)scale_index(sv.y, tab, levels, bound);
-      q.z = (unsigned char)scale_index(sv.z, tab, levels, bound);
-      q.w = (unsigned char)scale_index(sv.w, tab, levels, bound);
+      if (fast) {
+        q.x = (unsigned char)scale_index_log(sv.x, tab, levels, bound, la, lb);
+        q.y = (unsigned char)scale_index_log(sv.y, tab, levels, bound, la, lb);
+        q.z = (unsigned char)scale_index_log(sv.z, tab, levels, bound, la, lb);
+        q.w = (unsigned char)scale_index_log(sv.w, tab, levels, bound, la, lb);
+      } else {
+        q.x = (unsigned char)scale_index(sv.x, tab, levels, bound);
+        q.y = (unsigned char)scale_index(sv.y, tab, levels, bound);
+        q.z = (unsigned char)scale_index(sv.z, tab, levels, bound);
+        q.w = (unsigned char)scale_index(sv.w, tab, levels, bound);
+      }
       reinterpret_cast<uchar4*>(idx)[e] = q;
     }
     if (y_hat != nullptr && y != nullptr)  // "dequantize": round(y - mu) + mu, entropy_models.py:173-178

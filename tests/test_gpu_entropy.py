@@ -116,6 +116,41 @@ def test_round_half_even_and_scale_boundaries(tabs):
     assert torch.equal(idx.cpu().int(), EO.build_indexes(ss, st))
 
 
+@pytest.mark.parametrize("kind", ["default64", "log40", "irregular", "linear", "tiny"])
+def test_scale_index_paths_equal_reference_bucketisation(kind):
+    """GaussianConditional.build_indexes (entropy_models.py:679-685) for log-spaced tables (the kernel's log2 + two-compare
+    path) and for tables that are not log-spaced (binary-search fallback): a dense sweep plus every table entry and its
+    two float neighbours must give the reference's integer, whichever path the kernel picks."""
+    import math
+    lib = L()
+    g = torch.Generator().manual_seed(5)
+    if kind == "default64":
+        st = EO.get_scale_table()
+    elif kind == "log40":
+        st = torch.exp(torch.linspace(math.log(0.2), math.log(100.0), 40))
+    elif kind == "irregular":
+        st = torch.cumsum(torch.rand(50, generator=g) * 3 + 0.01, 0) + 0.11          # uneven steps
+    elif kind == "linear":
+        st = torch.linspace(0.11, 64.0, 64)
+    else:
+        st = torch.tensor([0.5, 2.0, 9.0])                                             # fewer than 4 levels
+    st = st.float()
+    dense = torch.exp(torch.empty(200000).uniform_(math.log(0.01), math.log(2000.0), generator=g))
+    below = torch.nextafter(st, torch.zeros_like(st))
+    above = torch.nextafter(st, torch.full_like(st, 1e9))
+    sig = torch.cat([dense, st, below, above, torch.tensor([-3.0, 0.0, 0.11, float("inf")])]).float()
+    pad = (-sig.numel()) % 4
+    sig = torch.cat([sig, torch.ones(pad)])
+    n = sig.numel()
+    idx = torch.empty(n, dtype=torch.uint8, device="cuda")
+    tab = st.cuda().contiguous()
+    lib.check(lib.lib.cra5_op_gc_quantize(ctypes.c_void_p(0), lib.ptr(sig.cuda()), ctypes.c_void_p(0), lib.ptr(tab),
+                                          int(st.numel()), ctypes.c_float(0.11), ctypes.c_void_p(0), lib.ptr(idx),
+                                          ctypes.c_void_p(0), ctypes.c_uint64(n), lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(idx.cpu().int(), EO.build_indexes(sig, st).int())
+
+
 @pytest.mark.parametrize("n_ch,Lc,spc", [(1, 1, 1), (3, 7, 8), (4, 1000, 8), (256, 648, 1), (16, 10368, 8), (5, 333, 64),
                                          (2, 0, 4), (0, 5, 2)])
 @pytest.mark.parametrize("table", [False, True], ids=["global-table", "smem-table"])
