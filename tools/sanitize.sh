@@ -6,9 +6,9 @@
 set -u
 mkdir -p gpurun_out
 SEL='tests/test_gpu_kernels.py tests/test_gpu_entropy.py'
-MODEL='tests/test_gpu_model.py -k small'
+MODEL='tests/test_gpu_model.py tests/test_gpu_batch.py tests/test_gpu_precision.py -k small'
 rc=0
-for tool in memcheck racecheck initcheck; do
+for tool in ${TOOLS:-memcheck racecheck initcheck}; do
   log=gpurun_out/sanitize_${tool}.log
   timeout 1200 compute-sanitizer --tool ${tool} --error-exitcode 7 --print-limit 20 \
       python -m pytest ${SEL} ${MODEL} -m gpu -x -q > ${log} 2>&1
