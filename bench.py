@@ -514,7 +514,7 @@ def run_b200(args):
             entropy_b8 = {"error": repr(e)}
 
     # ---- CPU baseline (oracle port on the host cores), rank 0, N == 1 only
-    cpu = None
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             from oracle.cpu_baseline import FrameTimer
@@ -523,6 +523,30 @@ def run_b200(args):
             cpu = {"value": 1.0 / r["total_s"], "unit": "frames/s", "cores": os.cpu_count(), "kind": ft.kind,
                    "sample": ft.describe(1) + "; single cold frame", "encode_s": r["encode_s"], "decode_s": r["decode_s"],
                    "bytes_per_frame": r["bytes"]}
+            # parity of this very run: the frame the CPU arm just coded (same weights) through the GPU path, compared
+            # with the fp32 reference path's own symbols / indexes / reconstruction (the oracle is the checker here)
+            with torch.no_grad():
+                xg = ft.x.to(dev)
+                yg, _, _ = net.encode_latent(xg, type="float")
+                og = net.compress_from_latent(yg)
+                sym_g = net.tap("y_symbols").cpu()[: yg[0].numel()]
+                idx_g = net.tap("y_indexes").cpu()[: yg[0].numel()]
+                rec_g = net.decompress(og["strings"], og["z_shape"])["x_hat"].cpu()
+            dbg, x_ref = ft.last["debug"], ft.last["x_hat"]
+            y_ref = dbg["y"]
+            rm_g = ((rec_g[0] - ft.x[0]) ** 2).mean(dim=(1, 2)).sqrt()
+            rm_r = ((x_ref[0] - ft.x[0]) ** 2).mean(dim=(1, 2)).sqrt()
+            parity = {
+                "against": "fp32 reference path (oracle port) on the same frame and weights",
+                "precision_level": args.precision,
+                "latent_rel_rms": float(((yg.cpu() - y_ref).pow(2).mean().sqrt() / y_ref.pow(2).mean().sqrt()).item()),
+                "symbol_flip_rate": float((sym_g != dbg["y_symbols"].reshape(-1).int()).float().mean().item()),
+                "index_flip_rate": float((idx_g.int() != dbg["indexes"].reshape(-1).int()).float().mean().item()),
+                "max_direct_rmse_per_variable": float(((rec_g[0] - x_ref[0]) ** 2).mean(dim=(1, 2)).sqrt().max().item()),
+                "max_abs_delta_rmse_per_variable": float((rm_g - rm_r).abs().max().item()),
+                "tolerance": "north star: max_abs_delta_rmse_per_variable <= 1e-4; integer stages bit-exact (tests/)",
+                "bytes_gpu": len(og["strings"][0][0]) + len(og["strings"][1][0]), "bytes_reference": r["bytes"],
+            }
         except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line
             cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
 
@@ -544,7 +568,7 @@ def run_b200(args):
             "gb_era5_per_s": fps * frame_bytes / 1e9,
             "e2e": e2e, "gpu_launches": int(lane_launches if lane_launches is not None else lc1.value - lc0.value),
             "clocks": clock_info,
-            "roofline": roofline, "entropy_product": entropy_product, "entropy_b8": entropy_b8, "kernels": kernels, "kernel_sites": sites if kernels else None, "cpu_baseline": cpu,
+            "roofline": roofline, "entropy_product": entropy_product, "entropy_b8": entropy_b8, "kernels": kernels, "kernel_sites": sites if kernels else None, "cpu_baseline": cpu, "parity": parity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,5 +1,8 @@
 #include "host_util.h"
 
+#include <nvtx3/nvToolsExt.h>
+#include <stdlib.h>
+
 #include <atomic>
 #include <mutex>
 #include <utility>
@@ -79,6 +82,13 @@ void ensure_dynamic_smem(const void* func, size_t bytes) {
   CRA5_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   have = bytes;
 }
+
+bool nvtx_enabled() {
+  static const bool on = [] { const char* e = getenv("CRA5_NVTX"); return e != nullptr && atoi(e) != 0; }();
+  return on;
+}
+void nvtx_push(const char* name) { nvtxRangePushA(name); }
+void nvtx_pop() { nvtxRangePop(); }
 
 void require_sm100() {
   int dev = 0, major = 0;

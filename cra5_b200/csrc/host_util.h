@@ -74,9 +74,21 @@ struct LaunchScope {
   cudaStream_t st_;
   int slot_;
 };
+// NVTX ranges (header-only nvtx3: a no-op unless a tool such as Nsight Systems / ncu --nvtx is attached), enabled with
+// CRA5_NVTX=1: one range per public entry point (encode_to_latent, latent_to_bin, ...) and one per tagged call site
+// (qkv, proj, fc1, ...), so a timeline reads like the reference's module tree.
+bool nvtx_enabled();
+void nvtx_push(const char* name);
+void nvtx_pop();
+struct NvtxRange {
+  explicit NvtxRange(const char* name) : on_(nvtx_enabled()) { if (on_) nvtx_push(name); }
+  ~NvtxRange() { if (on_) nvtx_pop(); }
+  bool on_;
+};
 struct TagScope {
-  explicit TagScope(const char* tag) { prof_set_tag(tag); }
+  explicit TagScope(const char* tag) : nv_(tag) { prof_set_tag(tag); }
   ~TagScope() { prof_set_tag(""); }
+  NvtxRange nv_;
 };
 void require_sm100();
 

@@ -403,6 +403,7 @@ static void window_of(const cra5_config& c, int abs_block, int* wh, int* ww) {
 // ViT_Encoder.forward + quant_conv + mode(): x -> y  (vit_nlc.py:458-486, vaeformer.py:272-283)
 void Model::encode_to_latent(const float* x, float* y, const float* mean, const float* std_, int B, cudaStream_t st) {
   finalize();
+  NvtxRange nvtx_("encode_to_latent");
   const cra5_config& c = cfg_;
   const int D = c.dim, CS = c.in_chans * c.patch_w;
   CRA5_CHECK((mean == nullptr) == (std_ == nullptr), ERR_INVALID, "mean and std must be given together");
@@ -487,6 +488,7 @@ void Model::encode_to_latent(const float* x, float* y, const float* mean, const 
 // HyperpriorEncoder: y (latent, Hg, Wg) -> z_ (zc, Hh, Wh)   (vit_nlc.py:488-551 via :477-486)
 void Model::run_h_a(cudaStream_t st, const float* y, int B) {
   finalize();
+  NvtxRange nvtx_("h_a");
   const cra5_config& c = cfg_;
   const int Dh = c.hyper_dim, lat = c.latent_chans, zc = c.z_chans;
   const int Kc = lat * c.hyper_patch_h * c.hyper_patch_w;
@@ -560,6 +562,7 @@ void Model::run_h_a(cudaStream_t st, const float* y, int B) {
 // HyperpriorDecoder: z_hat (zc, Hh, Wh) -> params_ = [sigma (latent) | mu (latent)] x (Hg, Wg)  (vit_nlc.py:696-748)
 void Model::run_h_s(cudaStream_t st, const float* z_hat, int B) {
   finalize();
+  NvtxRange nvtx_("h_s");
   const cra5_config& c = cfg_;
   const int Dh = c.hyper_dim, lat = c.latent_chans, zc = c.z_chans;
   const int hidden = std::max(1, (int)sqrt((double)(Dh / zc))) * zc;
@@ -681,6 +684,7 @@ void Model::latent_likelihoods(const float* y, float* y_hat, float* y_lik, float
 // reference loops over the batch items inside EntropyModel.compress (entropy_models.py:263-272).
 void Model::latent_to_bin(const float* y, int B, const uint8_t** y_bytes, size_t* y_len, const uint8_t** z_bytes,
                           size_t* z_len, cudaStream_t st) {
+  NvtxRange nvtx_("latent_to_bin");
   const cra5_config& c = cfg_;
   CRA5_CHECK(eb_.ready() && gc_.ready(), ERR_STATE, "Uninitialized CDFs. Run update() first");
   CRA5_CHECK(B >= 1 && B <= Bm, ERR_INVALID, "batch larger than the model's max_batch");
@@ -726,6 +730,7 @@ void Model::latent_to_bin(const float* y, int B, const uint8_t** y_bytes, size_t
 // VAEformer.decompress(return_format='latent') (vaeformer.py:378-391) for a batch of B frames
 void Model::bin_to_latent(const uint8_t* const* y_bytes, const size_t* y_len, const uint8_t* const* z_bytes,
                           const size_t* z_len, int B, int z_h, int z_w, float* y_hat, cudaStream_t st) {
+  NvtxRange nvtx_("bin_to_latent");
   const cra5_config& c = cfg_;
   CRA5_CHECK(eb_.ready() && gc_.ready(), ERR_STATE, "Uninitialized CDFs. Run update() first");
   CRA5_CHECK(z_h == Hh && z_w == Wh, ERR_INVALID, "z shape does not match the model geometry");
@@ -787,6 +792,7 @@ void Model::bin_to_latent(const uint8_t* const* y_bytes, const size_t* y_len, co
 void Model::latent_to_reconstruction(const float* y_hat, float* x_hat, int B, cudaStream_t st, const float* mean,
                                       const float* std_) {
   finalize();
+  NvtxRange nvtx_("latent_to_reconstruction");
   CRA5_CHECK((mean == nullptr) == (std_ == nullptr), ERR_INVALID, "mean and std must be given together");
   const cra5_config& c = cfg_;
   const int D = c.dim, lat = c.latent_chans, CS = c.in_chans * c.patch_w;

@@ -99,6 +99,7 @@ class FrameTimer:
         finally:
             EO.rans_encode, EO.rans_decode = keep
         assert rec["x_hat"].shape == self.x.shape
+        self.last = {"debug": out["debug"], "x_hat": rec["x_hat"]}   # for the bench's parity report (same frame, same weights)
         nbytes = len(out["strings"][0][0]) + len(out["strings"][1][0])
         return dict(encode_s=t1 - t0, decode_s=t2 - t1, total_s=t2 - t0, bytes=nbytes)
 

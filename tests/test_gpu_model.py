@@ -228,6 +228,32 @@ def test_reference_coder_format_end_to_end(ctx):
     assert torch.equal(y_hat2.cpu(), y_hat.cpu())
 
 
+def test_reference_written_archive_is_flagged_not_trusted(ctx):
+    """strings written by the fp32 reference path (here: the oracle codec, byte-identical to the real
+    reference, tools/make_golden.py). The z stream depends on integer tables and the channel index only, so it decodes
+    exactly. The y stream needs the writer's h_s floats bit for bit; this library's h_s is a different implementation,
+    so the y latent is NOT trusted: decompress warns, and either reports a corrupt stream or returns symbols that may
+    differ from the writer's -- never silently claims success."""
+    from cra5_b200.vaeformer import VAEformer
+    with torch.no_grad():
+        o = ctx.codec.compress(ctx.x)
+    VAEformer._warned_ref_stream = False
+    with pytest.warns(RuntimeWarning, match="reference-format"):
+        try:
+            ctx.net.decompress(o["strings"], o["z_shape"], return_format="latent")
+        except ValueError:
+            pass                                  # stream exhausted: reported as a corrupt bitstream
+    assert torch.equal(ctx.net.tap("z_symbols").cpu(), o["debug"]["z_symbols"].reshape(-1).int())
+    # a second call does not repeat the warning (once per process)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        try:
+            ctx.net.decompress(o["strings"], o["z_shape"], return_format="latent")
+        except ValueError:
+            pass
+
+
 def test_forward_likelihoods_match_reference_arithmetic(ctx):
     """rate-estimation path (VAEformer.forward, vaeformer.py:302-333): likelihood tensors against the oracle's fp32
     erfc / logistic arithmetic on the GPU's own (y, sigma, mu, z_hat); total bits against the reference's own forward()"""
