@@ -25,6 +25,25 @@
 #include "kernels.h"
 #include <cstdlib>
 
+// Development aid (-DCRA5_ATTN_TRACE, tools/attn_trace.py; never in the shipped library): CTA 0's lane-quarter-0 softmax
+// warps of tile A and B stamp clock64 at the phase boundaries of their first 64 KV steps.
+#ifdef CRA5_ATTN_TRACE
+__device__ long long g_attn_trace[2 * 64 * 8];
+#define A4_TRACE(tile, step, ph)                                                                      \
+  do {                                                                                                \
+    if (blockIdx.x == 0 && (warp & 3) == 0 && lane == 0 && (step) < 64u) {                            \
+      long long t_;                                                                                   \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_)::"memory");                                    \
+      g_attn_trace[((tile) * 64 + (step)) * 8 + (ph)] = t_;                                           \
+    }                                                                                                 \
+  } while (0)
+extern "C" __attribute__((visibility("default"))) int cra5_debug_attn_trace(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_attn_trace, sizeof(g_attn_trace));
+}
+#else
+#define A4_TRACE(tile, step, ph) do {} while (0)
+#endif
+
 namespace cra5 {
 
 namespace {
@@ -201,7 +220,24 @@ __device__ __forceinline__ Item decode_item(const A4Params& p, int item) {
 // POLY: of every 8 column pairs, this many take the polynomial exp2. F16: Q, K, V arrive as fp16 (EPI_QKV_F16) and P is
 // written as fp16 -- 11 instead of 8 significand bits on every attention operand, the format the reference's own GPU
 // path uses (flash-attn on .half() tensors, vit_nlc.py:105-110); same tcgen05 kind::f16 pipeline, same speed.
-// (Tried and dropped in round 2, tools/perf_attn.py: four instead of two running maxima per row -- no change, the
+// Where a KV step's cycles go (tools/attn_trace.py, clock64 stamps of one softmax warp, global shape, B200): 2740 per
+// step and tile = wait S 140 + TMEM load and maximum 540 + exponentials 1700 + wait PV 105 + store P 97, tiles A and B
+// of a scheduler nearly in phase. tools/micro/softmax_ops.cu gives the pipe rates behind it (cycles per warp
+// instruction and scheduler): MUFU.EX2 8 (ex2.f16x2 / bf16x2 are two MUFUs: no gain), FFMA2 2.24, FADD2 / FMNMX3 / F2FP 2,
+// FFMA / IADD 1. Per tile and warp the exponentials occupy the MUFU for 640 cycles and the FMA pipe for ~680 (the
+// cubic costs the FMA pipe 8.5 cycles per exponential it takes off the MUFU's 8: POLY = 3 is the balance point), so
+// two warps cannot finish them in less than ~1360; measured 1700.
+// (Tried and dropped in round 2, tools/perf_attn.py, global shape at 8 frames per launch, all bit-identical:
+//   * two threads per query row -- 16 softmax warps with 64 scores each, tile maxima swapped through shared memory
+//     behind 64-thread named barriers, half tiles for a segment's 64-key tail: 715 TFLOP/s against 901 (the partner
+//     warps run in lock step, so the phases still collide, and 112 registers per thread leave ptxas no room);
+//   * speculative maximum -- exponentials against the current reference while the tile maximum is reduced alongside,
+//     redo from TMEM when the reference has to move: 767, because S can then only be released to the MMA issuer after
+//     the exponentials and the next S arrives 700 cycles late;
+//   * ping-pong -- the two tiles' exponential phases exclude each other through named barriers, FA3-style: 775 alone,
+//     845 with the speculative maximum; a single warp needs 1340 cycles for its exponentials, so exclusion loses more
+//     than the overlap of the other tile's load / store phases wins.)
+// (Also tried: four instead of two running maxima per row -- no change, the
 // FMNMX3 chain already hides behind the second TMEM load; computing the exponentials speculatively against the previous
 // reference maximum while the tile maximum is still being reduced -- the scores then have to stay live for a possible
 // redo and the kernel spills. POLY = 3 remains the best split: 907 / 881 / 726 TFLOP/s for POLY 3 / 2 / 4 on the global
@@ -385,8 +421,10 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float m_ref = -INFINITY, l = 0.f;
       for (int j = 0; j < n_kv; ++j, ++cnt) {
         const int valid = p.seg_len - j * A4_BN;   // >= 128 for all but a segment's last tile
+        A4_TRACE(x, cnt, 0);
         mbar_wait(&s_full[x], cnt & 1);
         tc_fence_after();
+        A4_TRACE(x, cnt, 1);
         uint32_t s[NC];
         float mt0 = -INFINITY, mt1 = -INFINITY;
         // full tiles read S in two halves: the row maximum of columns 0..63 is taken while the TMEM load of columns
@@ -459,19 +497,23 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
           tmem_st_wait();
         }
+        A4_TRACE(x, cnt, 2);
         lsum = softmax_row<POLY, F16>(s, -m_ref * LOG2E, pk);
         l += lsum;
         // the previous PV product of this tile reads P: it must have retired before P is overwritten (it was issued a
         // whole softmax step ago, so this wait does not stall in steady state)
+        A4_TRACE(x, cnt, 4);
         if (j > 0) {
           mbar_wait(&pv_done[x], (cnt - 1) & 1);
           tc_fence_after();
         }
+        A4_TRACE(x, cnt, 5);
 #pragma unroll
         for (int c = 0; c < NC / 2; c += 32) tmem_st_32x32(t_p + c, *reinterpret_cast<uint32_t(*)[32]>(&pk[c]));
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[x]);
+        A4_TRACE(x, cnt, 6);
       }
       // ---- item epilogue: O / l -> bf16 -> global
       mbar_wait(&pv_done[x], (cnt - 1) & 1);
