@@ -236,7 +236,10 @@ __device__ __forceinline__ Item decode_item(const A4Params& p, int item) {
 //     the exponentials and the next S arrives 700 cycles late;
 //   * ping-pong -- the two tiles' exponential phases exclude each other through named barriers, FA3-style: 775 alone,
 //     845 with the speculative maximum; a single warp needs 1340 cycles for its exponentials, so exclusion loses more
-//     than the overlap of the other tile's load / store phases wins.)
+//     than the overlap of the other tile's load / store phases wins;
+//   * S fetched one step ahead (TMEM load issued after the exponentials, landing during the P store) with P stored in
+//     two halves to make room in the register file: 810 -- the barrier wait in the middle of the exponentials splits
+//     ptxas' scheduling region.)
 // (Also tried: four instead of two running maxima per row -- no change, the
 // FMNMX3 chain already hides behind the second TMEM load; computing the exponentials speculatively against the previous
 // reference maximum while the tile maximum is still being reduced -- the scores then have to stay live for a possible
