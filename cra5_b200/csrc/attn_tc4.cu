@@ -239,7 +239,16 @@ __device__ __forceinline__ Item decode_item(const A4Params& p, int item) {
 //     than the overlap of the other tile's load / store phases wins;
 //   * S fetched one step ahead (TMEM load issued after the exponentials, landing during the P store) with P stored in
 //     two halves to make room in the register file: 810 -- the barrier wait in the middle of the exponentials splits
-//     ptxas' scheduling region.)
+//     ptxas' scheduling region;
+//   * more softmax warps per scheduler with 64-key steps (thread = row, 64 scores, no exchange between warps): four
+//     tiles with P stored over S (TMEM 4 x 64 + 4 x 64 = 512 columns): 630 -- S(j+1) then depends on PV(j) through TMEM
+//     and the tensor pipe drains between them (8 MMAs took 1200 cycles to issue); three tiles with the protocol of this
+//     kernel (TMEM 3 x 64 S + 3 x 32 P + 3 x 64 O, control warps at the highest warp ids): 860-890 on the global shape,
+//     560-575 against 520 on the 576-token windows, 800-855 against 765-790 at one frame per launch -- and a step of 64
+//     keys still takes 1900 cycles: left alone the three tiles fall in step, and when a ring of named barriers keeps
+//     them a third of a step apart each warp's exponentials take as long as before (~1000 cycles for 64 columns). One
+//     in-order warp issues this instruction mix at an IPC of ~0.4; the FMA pipe is 60 % busy, the MUFU 50 %, with
+//     two or with three warps per scheduler. Not kept: no gain on the shape that dominates the step.)
 // (Also tried: four instead of two running maxima per row -- no change, the
 // FMNMX3 chain already hides behind the second TMEM load; computing the exponentials speculatively against the previous
 // reference maximum while the tile maximum is still being reduced -- the scores then have to stay live for a possible

@@ -166,6 +166,7 @@ struct EpiParams {
   int ct_Himg, ct_Wimg;
   const float *ct_mean, *ct_std;   // optional per-channel de-normalisation fused into the store: x * std[c] + mean[c]
                                    // (cra5_api.de_normalization, cra5_api.py:268-271); null = normalised units
+  int gelu_fast;                   // EPI_GELU_BF16: 0 = erf by A&S 7.1.26 (gelu_erf), 1 = gelu_bf16out (trunk fc1)
 };
 
 // exact (erf) GELU, nn.GELU default (vit_nlc.py:53). erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32
@@ -184,6 +185,21 @@ __device__ __forceinline__ float gelu_erf(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
   const float erf_abs = fmaf(-p, e, 1.0f);            // erf(|x|/sqrt2)
   return 0.5f * x + 0.5f * fabsf(x) * erf_abs;          // 0.5 x (1 + sign(x) erf(|x|/sqrt2))
+}
+
+// The same function for bf16 OUTPUTS (fc1's epilogue): x * Phi(x) with Phi(x) = 0.5 (1 + tanh(x (c0 + c1 x^2 + c2 x^4))),
+// coefficients fitted to the erf form (max |error| 2.5e-5 over the real line in exact arithmetic; this is NOT the
+// "tanh GELU" of the literature, whose two-term fit is off by 3e-4) and one MUFU.TANH: 1 MUFU + 7 FMA-pipe instructions
+// per element instead of 2 + 12. Measured against fp64 erf-GELU on a B200 (tools/micro/tanh_err.cu): see
+// profiles/r2_micro_tanh.txt -- the error stays an order of magnitude below the bf16 rounding of the stored value.
+// Every fp32-output and split-precision path keeps gelu_erf.
+__device__ __forceinline__ float gelu_bf16out(float x) {
+  const float x2 = x * x;
+  const float u = x * fmaf(x2, fmaf(x2, -0.0003515175339619918f, 0.037005650955991044f), 0.797507878425557f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float h = 0.5f * x;
+  return fmaf(h, t, h);
 }
 
 // 16-bit output element of an epilogue kind: bf16, or fp16 bits travelling in bf16-typed buffers for EPI_QKV_F16
@@ -560,7 +576,7 @@ __device__ __forceinline__ void epilogue_resid_finish(const EpiParams& p, const 
 template <int KIND>
 __device__ __forceinline__ void epilogue_bf16_fast(const uint32_t (&acc)[32], const float* __restrict__ bias, int col0,
                                                    float scale, uint8_t* stage, __nv_bfloat16* dst_row0, size_t ld,
-                                                   int rows_valid, int lane) {
+                                                   int rows_valid, int lane, bool gelu_fast = false) {
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
@@ -572,8 +588,13 @@ __device__ __forceinline__ void epilogue_bf16_fast(const uint32_t (&acc)[32], co
     v[i + 3] = __uint_as_float(acc[i + 3]) + b.w;
   }
   if constexpr (KIND == EPI_GELU_BF16) {
+    if (gelu_fast) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+      for (int i = 0; i < 32; ++i) v[i] = gelu_bf16out(v[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    }
   }
   if constexpr (is_qkv<KIND>()) {
 #pragma unroll
@@ -935,7 +956,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (fast)
             epilogue_bf16_fast<KIND>(acc, epi.bias, col0, 1.0f, reinterpret_cast<uint8_t*>(stg),
                                      epi.out_bf16 + (size_t)row_base * epi.ldo + col0, (size_t)epi.ldo,
-                                     min(32, shp.M - row_base), lane);
+                                     min(32, shp.M - row_base), lane, epi.gelu_fast != 0);
         }
         if constexpr (is_qkv<KIND>()) {   // a chunk wholly inside one head of Q or K
           fast = !direct && (col0 + 32 <= shp.N) && (((epi.D | epi.hd) & 31) == 0) && (col0 < 2 * epi.D) &&
@@ -1190,7 +1211,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (fast)
             epilogue_bf16_fast<KIND>(acc, epi.bias, col0, 1.0f, reinterpret_cast<uint8_t*>(stg),
                                      epi.out_bf16 + (size_t)row_base * epi.ldo + col0, (size_t)epi.ldo,
-                                     min(32, shp.M - row_base), lane);
+                                     min(32, shp.M - row_base), lane, epi.gelu_fast != 0);
         }
         if constexpr (is_qkv<KIND>()) {   // a chunk wholly inside one head of Q or K
           fast = !direct && (col0 + 32 <= shp.N) && (((epi.D | epi.hd) & 31) == 0) && (col0 < 2 * epi.D) &&

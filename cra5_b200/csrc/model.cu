@@ -370,6 +370,8 @@ void Model::run_block(cudaStream_t st, const BlockWeights& w, const TrunkBuffers
       EpiParams e{};
       e.bias = w.fc1_b;
       e.out_bf16 = tb.h; e.ldo = mlp * D;
+      static const bool exact = [] { const char* v = getenv("CRA5_GELU_EXACT"); return v != nullptr && atoi(v) != 0; }();
+      e.gelu_fast = exact ? 0 : 1;
       TagScope tag_("fc1");
       gemm_plain(st, EPI_GELU_BF16, tb.a, D, w.fc1_w, D, T_, mlp * D, D, e);
     }
