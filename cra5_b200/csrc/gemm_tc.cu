@@ -17,10 +17,13 @@ static void launch_one(cudaStream_t st, const CUtensorMap& tmA, const CUtensorMa
   int grid = m_tiles * n_tiles;
   const int sms = device_sm_count();
   if (grid > sms) grid = sms;
-  // (split-bf16 launches execute 2-3x the tensor work of their algorithmic flops; the profiler counts the algorithmic ones)
-  LaunchScope scope(st, (shp.a_split || shp.b_split) ? "gemm_tc_split" : "gemm_tc", 2.0 * shp.M * shp.N * shp.K,
+  // (split-bf16 launches execute 2-3x the tensor work of their algorithmic flops, the grouped un-patchify order 32/30 of
+  // them for its zero-weight pad columns; the profiler counts the algorithmic ones)
+  double n_alg = shp.N;
+  if (KIND == EPI_CONVT && epi.ct_cpg > 0) n_alg = (double)(shp.N / epi.ct_CS) * epi.ct_C * epi.ct_pw;
+  LaunchScope scope(st, (shp.a_split || shp.b_split) ? "gemm_tc_split" : "gemm_tc", 2.0 * shp.M * n_alg * shp.K,
                     2.0 * ((double)shp.M * shp.K + (double)shp.N * shp.K) +
-                        (double)shp.M * shp.N * ((KIND == EPI_BF16 || KIND == EPI_GELU_BF16 || KIND == EPI_QKV || KIND == EPI_QKV_F16) ? 2.0 : 4.0));
+                        (double)shp.M * n_alg * ((KIND == EPI_BF16 || KIND == EPI_GELU_BF16 || KIND == EPI_QKV || KIND == EPI_QKV_F16) ? 2.0 : 4.0));
   launch_chained(kern, dim3(grid), dim3(GEMM_THREADS), GemmSmem<BN>::TOTAL, st, tmA, tmB, shp, epi);
 }
 

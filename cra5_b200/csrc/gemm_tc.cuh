@@ -167,6 +167,10 @@ struct EpiParams {
   const float *ct_mean, *ct_std;   // optional per-channel de-normalisation fused into the store: x * std[c] + mean[c]
                                    // (cra5_api.de_normalization, cra5_api.py:268-271); null = normalised units
   int gelu_fast;                   // EPI_GELU_BF16: 0 = erf by A&S 7.1.26 (gelu_erf), 1 = gelu_bf16out (trunk fc1)
+  // EPI_CONVT, channel-grouped column order (ct_cpg > 0): within a kernel row the N columns come in groups of 32 =
+  // ct_cpg whole channels x pw (+ zero padding), ct_CS = 32 * groups per kernel row; see epilogue_convt_grouped
+  int ct_cpg;
+  int ct_C;                        // number of real channels (groups are padded up)
 };
 
 // exact (erf) GELU, nn.GELU default (vit_nlc.py:53). erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32
@@ -536,6 +540,72 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& p, const float* s
       }
     }
   }
+}
+
+// EPI_CONVT with the channel-grouped column order. The plain order (r, c, s) makes a warp's 32 columns 3.2 channels, and
+// a store instruction (lane = column, one token) 3-4 runs of 40 bytes in different channel planes, with ~30
+// instructions of index arithmetic per stored row: ncu showed the epilogue warps issue-bound (34 % tensor pipe) and
+// 12.3 GB of DRAM traffic for 8.2 GB of output (every 32-byte sector written in pieces, so L2 fetches it first). Here a
+// 32-column chunk is CPG WHOLE channels (3 x 10 columns + 2 zero-weight pad columns for pw = 10; the weight is packed
+// that way at upload, +7 % MMA work), the chunk is staged column-major, and for each channel the warp's 32 tokens x pw
+// values -- contiguous in the output row while the tokens stay in one image row -- leave as pw full 128-byte lines
+// (lane = position in that run). Everything that depends on the lane's position only -- pixel offset, staging index,
+// validity -- is computed once per tile (ConvtLane); a store costs LDS + FFMA + address add + STG.
+constexpr int CT_LD = 35;   // staged column stride (words): 35 = 3 mod 32 makes the (token, s) reads conflict-free
+constexpr int CT_PW = 10;   // patch width the grouped path is built for (every shipped geometry)
+__device__ __forceinline__ uint32_t convt_rowword(const EpiParams& p, int row, int M) {
+  if (row >= M) return 0xffffffffu;
+  int b = 0, rf = row;
+  if (p.fr_rows > 0) { b = row / p.fr_rows; rf = row - b * p.fr_rows; }
+  const int i_ = rf / p.ct_Wp, j_ = rf - i_ * p.ct_Wp;
+  return (uint32_t)(p.ct_sh * i_ * p.ct_Wimg + p.ct_pw * j_) | ((uint32_t)b << 20);   // checked on the host: 20 bits
+}
+template <int KIND>
+struct ConvtLane {};                 // nothing to carry for the other epilogue kinds
+template <>
+struct ConvtLane<EPI_CONVT> {
+  size_t pix[CT_PW];                 // output element offset of this lane's k-th value inside a channel's row class
+  uint32_t offs[CT_PW];              // the same inside its frame (validity: offs + kernel-row offset < plane size)
+  int sidx[CT_PW];                   // staging index of the value inside a channel's pw staged columns
+};
+__device__ __forceinline__ void convt_lane_setup(const EpiParams& p, int row, int M, int lane, ConvtLane<EPI_CONVT>& cl) {
+  const uint32_t own = convt_rowword(p, row, M);
+  int rr = lane / CT_PW, s_ = lane - rr * CT_PW;   // store k covers positions 32 k + lane of the warp's 32 x pw run
+#pragma unroll
+  for (int k = 0; k < CT_PW; ++k) {
+    const uint32_t w = __shfl_sync(0xffffffffu, own, rr);
+    const uint32_t off = (w & 0xfffffu) + (uint32_t)s_;
+    cl.offs[k] = (w == 0xffffffffu) ? 0xffffffffu : off;
+    cl.pix[k] = (size_t)(w >> 20) * p.fr_stride + off;
+    cl.sidx[k] = s_ * CT_LD + rr;
+    rr += 32 / CT_PW; s_ += 32 % CT_PW;
+    if (s_ >= CT_PW) { s_ -= CT_PW; ++rr; }
+  }
+}
+__device__ __forceinline__ void epilogue_convt_grouped(const EpiParams& p, const uint32_t (&acc)[32], float* stg,
+                                                       const ConvtLane<EPI_CONVT>& cl, int col0, int lane) {
+  constexpr int CPG = 30 / CT_PW;
+#pragma unroll
+  for (int i = 0; i < CPG * CT_PW; ++i) stg[i * CT_LD + lane] = __uint_as_float(acc[i]);   // (pad columns are never read)
+  __syncwarp();
+  const int rk = col0 / p.ct_CS;
+  const int g = (col0 - rk * p.ct_CS) >> 5;
+  const uint32_t row_off = (uint32_t)((p.ct_r0 + rk) * p.ct_Wimg);          // kernel row inside the patch
+  const uint32_t plane_elems = (uint32_t)(p.ct_Himg * p.ct_Wimg);
+  const uint32_t limit = plane_elems - row_off;                              // offs < limit <=> the row is inside the image
+#pragma unroll
+  for (int c3 = 0; c3 < CPG; ++c3) {
+    const int c = g * CPG + c3;
+    if (c >= p.ct_C) break;                                                   // warp-uniform
+    float* base = p.out_f32 + (size_t)c * plane_elems + row_off;
+    const float dn_s = (p.ct_std != nullptr) ? __ldg(p.ct_std + c) : 1.0f;
+    const float dn_m = (p.ct_std != nullptr) ? __ldg(p.ct_mean + c) : 0.0f;
+    const float* sc = stg + c3 * CT_PW * CT_LD;
+#pragma unroll
+    for (int k = 0; k < CT_PW; ++k)
+      if (cl.offs[k] < limit) base[cl.pix[k]] = fmaf(sc[cl.sidx[k]], dn_s, dn_m);
+  }
+  __syncwarp();
 }
 
 // EPI_RESID, phase 1: issue the 32 residual loads of this chunk (clamped, unconditional addresses) -- called BEFORE the
@@ -924,6 +994,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row = row_base + lane;
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN + half * (BN / 2);
       float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET) + ew * (32 * STG_LD);
+      ConvtLane<KIND> ctl;
+      if constexpr (KIND == EPI_CONVT) {
+        if (epi.ct_cpg > 0) convt_lane_setup(epi, row, shp.M, lane, ctl);
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 2; c += 32) {
         const int col0 = n0 + half * (BN / 2) + c;
@@ -980,6 +1054,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                              epi.vt + ((size_t)head * epi.hd + d0) * epi.rows_total + row_base, (size_t)epi.rows_total,
                              min(32, shp.M - row_base), lane);
             fast = true;
+          }
+        }
+        if constexpr (KIND == EPI_CONVT) {
+          if (epi.ct_cpg > 0) {   // warp-uniform
+            epilogue_convt_grouped(epi, acc, stg, ctl, col0, lane);
+            continue;
           }
         }
         if (fast) {
@@ -1180,6 +1260,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int row = row_base + lane;
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN + half * (BN / 2);
       float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET) + ew * (32 * STG_LD);
+      ConvtLane<KIND> ctl;
+      if constexpr (KIND == EPI_CONVT) {
+        if (epi.ct_cpg > 0) convt_lane_setup(epi, row, shp.M, lane, ctl);
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 2; c += 32) {
         const int col0 = n0 + half * (BN / 2) + c;
@@ -1235,6 +1319,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                              epi.vt + ((size_t)head * epi.hd + d0) * epi.rows_total + row_base, (size_t)epi.rows_total,
                              min(32, shp.M - row_base), lane);
             fast = true;
+          }
+        }
+        if constexpr (KIND == EPI_CONVT) {
+          if (epi.ct_cpg > 0) {   // warp-uniform
+            epilogue_convt_grouped(epi, acc, stg, ctl, col0, lane);
+            continue;
           }
         }
         if (fast) {

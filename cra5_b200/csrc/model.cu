@@ -846,14 +846,26 @@ void Model::latent_to_reconstruction(const float* y_hat, float* x_hat, int B, cu
     e.ct_mean = mean; e.ct_std = std_;   // de-normalisation fused into the un-patchify store
     e.fr_rows = M2; e.fr_stride = frame_out;
     if (nA > 0) {
+      // class A runs on the channel-grouped column order when the patch width is the shipped one (gemm_tc.cuh:
+      // epilogue_convt_grouped): per kernel row, groups of 32 columns = 3 whole channels x pw + 2 zero-weight pad
+      // columns; the weight is packed that way at upload (cra5_b200/vaeformer.py::_upload)
+      const bool grouped = c.patch_w == CT_PW;
+      const int cpg = 30 / CT_PW, groups = (c.in_chans + cpg - 1) / cpg;
+      const int CSa = grouped ? 32 * groups : CS;
+      if (grouped) {
+        CRA5_CHECK((int64_t)Hg * c.stride_h * c.img_w + c.img_w <= (1 << 20) && B < 4096, ERR_INVALID,
+                   "unsupported geometry for the grouped un-patchify epilogue");
+        e.ct_cpg = cpg; e.ct_C = c.in_chans; e.ct_CS = CSa;
+      }
       e.ct_r0 = nB;
       TagScope tag_("convT_A");
       if (pr)
-        gemm_plain(st, EPI_CONVT, fin, D, need_x3("g_s.final.A", (int64_t)nA * CS * D), D, MB, nA * CS, D, e,
-                   GemmSplit{fin_half, (size_t)nA * CS * D});
+        gemm_plain(st, EPI_CONVT, fin, D, need_x3("g_s.final.A", (int64_t)nA * CSa * D), D, MB, nA * CSa, D, e,
+                   GemmSplit{fin_half, (size_t)nA * CSa * D});
       else
-        gemm_plain(st, EPI_CONVT, fin, D, (const __nv_bfloat16*)need("g_s.final.A", CRA5_DT_BF16, (int64_t)nA * CS * D), D, MB,
-                   nA * CS, D, e);
+        gemm_plain(st, EPI_CONVT, fin, D, (const __nv_bfloat16*)need("g_s.final.A", CRA5_DT_BF16, (int64_t)nA * CSa * D), D, MB,
+                   nA * CSa, D, e);
+      e.ct_cpg = 0; e.ct_CS = CS;
     }
     if (nB > 0) {
       e.ct_r0 = 0;
