@@ -41,6 +41,10 @@ int cra5_op_gemm(const void* A, int lda, const void* B, int ldb, int M, int N, i
     EpiParams e{};
     e.bias = bias;
     e.ldo = ldo;
+    if (epilogue == 9) {   // CRA5_EPI_GELU_BF16_TRUNK
+      epilogue = EPI_GELU_BF16;
+      e.gelu_fast = 1;
+    }
     switch (epilogue) {
       case EPI_F32:
       case EPI_T_F32: e.out_f32 = static_cast<float*>(out); break;

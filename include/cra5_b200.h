@@ -44,6 +44,10 @@ CRA5_API int cra5_abi_version(void);
 #define CRA5_EPI_BF16 1      /* out bf16 = A*B^T + bias                                                          */
 #define CRA5_EPI_GELU_BF16 2 /* out bf16 = gelu_erf(A*B^T + bias)                 (Mlp.fc1+act, vit_nlc.py:63-64) */
 #define CRA5_EPI_RESID 4     /* out f32  = resid + A*B^T + bias                   (Block residual, vit_nlc.py:284) */
+#define CRA5_EPI_GELU_BF16_TRUNK 9 /* the same function as 2, evaluated the way the trunk's fc1 epilogue does at the
+                              * default precision: x * Phi(x) with Phi through one MUFU.TANH of an odd quintic fitted to
+                              * the erf form (|error| <= 3e-5, below the bf16 rounding of the output); kinds 6-8 are
+                              * internal (scatter epilogues of the model entry points) */
 #define CRA5_EPI_T_F32 5     /* out f32 [N][ldo] = (A*B^T + bias)^T               (1x1 conv -> NCHW, vaeformer.py:154) */
 
 /* C[M,N] = A[M,K] * B[N,K]^T with A, B bf16 row-major (lda/ldb in elements, multiples of 8), fp32 accumulate on

@@ -67,6 +67,18 @@ def test_gemm_epilogues():
     _gemm(A, B, bias, 2, o)
     rg = torch.nn.functional.gelu(ref)
     assert (o.float() - rg).abs().max().item() <= 2 ** -7 * rg.abs().max().item()
+    # the trunk's fc1 form of the same function (one MUFU.TANH of a quintic fitted to the erf form): against fp64 erf-GELU
+    # of the GPU's own pre-activation it must stay within a bf16 rounding (2^-8 relative) plus the fit's 3e-5
+    _gemm(A, B, bias, 9, o)
+    o_exact = torch.empty_like(o)
+    _gemm(A, B, bias, 2, o_exact)
+    pre = torch.empty(M, N, device="cuda")
+    _gemm(A, B, bias, 0, pre)
+    g64 = torch.nn.functional.gelu(pre.double())
+    tol = 2.0 ** -8 * g64.abs() + 3.5e-5
+    assert ((o.double() - g64).abs() <= tol).all()
+    assert ((o_exact.double() - g64).abs() <= 2.0 ** -8 * g64.abs() + 1e-6).all()
+    assert (o.float() - o_exact.float()).abs().max().item() <= 2 ** -7 * rg.abs().max().item()
     # residual
     resid = torch.randn(M, N, device="cuda")
     of = torch.empty(M, N, device="cuda")
