@@ -43,7 +43,7 @@ for li, vals in enumerate(launches):
     short = re.sub(r"[^A-Za-z0-9_]+", "_", kname.split("(")[0].replace("void ", "").replace("cra5::", "").replace("<unnamed>::", ""))[:48].strip("_")
     name = f"{prefix}_{li:02d}_{short}"
     lines = [f"# ncu --set full --clock-control none --import-source on: launch {li} of `{kname[:150]}`",
-             f"# captured inside `python bench.py --steps 2 --warmup 3` on a B200 (report {os.path.basename(rep)})", ""]
+             f"# captured inside `python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-kernel-profile --no-e2e` (8 frames per call) on a B200 (report {os.path.basename(rep)})", ""]
     for k in KEEP:
         if k in m:
             lines.append(f"{k:78s} {m[k][0]:>18s} {m[k][1]}")

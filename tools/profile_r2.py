@@ -140,16 +140,73 @@ def main(rnd):
     print("done", sorted(os.listdir(OUT))[:80], flush=True)
 
 
+SITE_NAMES = {   # capture tag + position -> the name the tracked summary carries
+    "gemm_block3_00": "qkv", "gemm_block3_01": "proj", "gemm_block3_02": "fc1", "gemm_block3_03": "fc2",
+    "gemm_patch_embed_00": "patch_embed", "gemm_tail_00": "convT_A", "gemm_tail_01": "convT_B",
+    "attn_00": "attn_window24x24", "attn_01": "attn_window12x48", "attn_02": "attn_window48x12", "attn_03": "attn_global",
+    "attn_hyper_00": "attn_hyperprior", "layernorm_00": "layernorm", "frame_to_patches_00": "frame_to_patches",
+    "quantize_00": "quantize_encode", "quantize_01": "quantize_decode_idx",
+    "rans_enc_00": "rans_enc_z", "rans_enc_01": "rans_enc", "rans_dec_00": "rans_dec_z", "rans_dec_01": "rans_dec",
+}
+
+
 def collect(rnd):
-    """build container: gpurun_out/prof -> profiles/ (tracked)"""
+    """build container: gpurun_out/prof -> profiles/ (tracked): per-site ncu summaries under their site names,
+    <round>_traffic.json (DRAM bytes per launch, read by bench.py for roofline.traffic), the launch list and its summary
+    over the timed step, the bench line, the SASS opcode histogram"""
     dst = os.path.join(ROOT, "profiles")
-    n = 0
+    traffic, n = collections.OrderedDict(), 0
+    summaries = {}
     for f in sorted(os.listdir(OUT)):
-        if f.startswith(rnd + "_") or f in (f"bench_{rnd}.json", f"launches_{rnd}.csv"):
-            name = f if f.startswith(rnd + "_") else (f"{rnd}_bench.json" if f.startswith("bench_") else f"{rnd}_launches.csv")
-            shutil.copyfile(os.path.join(OUT, f), os.path.join(dst, name))
+        if f.startswith(rnd + "_") and f.endswith("_summary.json"):
+            summaries.update(json.load(open(os.path.join(OUT, f))))
+    for f in sorted(os.listdir(OUT)):
+        m = re.match(rf"{rnd}_((?:[a-z0-9]+_)+?\d\d)_.*\.txt$", f)
+        if not m or m.group(1) not in SITE_NAMES:
+            continue
+        site = SITE_NAMES[m.group(1)]
+        shutil.copyfile(os.path.join(OUT, f), os.path.join(dst, f"{rnd}_ncu_{site}.txt"))
+        n += 1
+        key = f[:-4]
+        if key in summaries:
+            traffic[site] = dict(summaries[key], frames_per_launch=8)
+    if traffic:
+        json.dump(traffic, open(os.path.join(dst, f"{rnd}_traffic.json"), "w"), indent=1)
+    for src, name in ((f"bench_{rnd}.json", f"{rnd}_bench.json"), (f"launches_{rnd}.csv", f"{rnd}_launches.csv"),
+                      (f"{rnd}_sass_opcodes.txt", f"{rnd}_sass_opcodes.txt")):
+        if os.path.exists(os.path.join(OUT, src)):
+            if src.startswith("bench_"):
+                line = [l for l in open(os.path.join(OUT, src)) if l.startswith("{")][-1]
+                json.dump(json.loads(line), open(os.path.join(dst, name), "w"), indent=1)
+            else:
+                shutil.copyfile(os.path.join(OUT, src), os.path.join(dst, name))
             n += 1
-    print("copied", n, "files to profiles/")
+    lc = os.path.join(OUT, f"launches_{rnd}.csv")
+    if os.path.exists(lc):
+        rows = list(csv.reader(l for l in open(lc) if l.startswith('"')))
+        hdr = rows[0]
+        ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+        per_step = (len(rows) - 1) // 4                       # 3 warm-up steps + the timed one
+        agg = collections.OrderedDict()
+        for row in rows[1 + 3 * per_step:]:
+            name = row[ki].split("(")[0].replace("void ", "")
+            v = float(row[vi].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0}.get(row[ui], 1e-6)
+            a = agg.setdefault(name, [0, 0.0])
+            a[0] += 1
+            a[1] += v
+        tot = sum(a[1] for a in agg.values())
+        md = [f"# ncu launch list, round {rnd[1:]}", "",
+              "`ncu --metrics gpu__time_duration.sum --clock-control none -k regex:<library kernels> python bench.py --steps 1 "
+              "--warmup 3 --no-cpu-baseline --no-kernel-profile --no-e2e` (batch 8): the launches of the ONE timed step = 8 frames "
+              f"(cold-cache, serialised under the profiler: compare SHARES with the bench's own CUDA-event table in {rnd}_bench.json, "
+              "not absolutes).", "",
+              f"{per_step} launches per step of 8 frames, {tot:.2f} ms summed ({tot / 8:.2f} ms per frame)", "",
+              "| kernel | launches | ms | share |", "|---|---|---|---|"]
+        for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            md.append(f"| `{k}` | {a[0]} | {a[1]:.3f} | {100 * a[1] / tot:.1f} % |")
+        open(os.path.join(dst, f"{rnd}_launch_summary.md"), "w").write("\n".join(md) + "\n")
+        n += 1
+    print("wrote", n, "files to profiles/")
 
 
 if __name__ == "__main__":
