@@ -603,7 +603,8 @@ __device__ __forceinline__ void epilogue_convt_grouped(const EpiParams& p, const
     const float* sc = stg + c3 * CT_PW * CT_LD;
 #pragma unroll
     for (int k = 0; k < CT_PW; ++k)
-      if (cl.offs[k] < limit) base[cl.pix[k]] = fmaf(sc[cl.sidx[k]], dn_s, dn_m);
+      if (cl.offs[k] < limit)   // streaming store: nothing on the GPU re-reads the reconstruction, the weight should stay in L2
+        __stcs(&base[cl.pix[k]], fmaf(sc[cl.sidx[k]], dn_s, dn_m));
   }
   __syncwarp();
 }
