@@ -37,9 +37,11 @@ static void launch_pair(cudaStream_t st, const CUtensorMap& tmA, const CUtensorM
   int clusters = m_tiles * n_tiles;
   const int max_clusters = device_sm_count() / 2;
   if (clusters > max_clusters) clusters = max_clusters;
-  LaunchScope scope(st, "gemm_tc", 2.0 * shp.M * shp.N * shp.K,
+  double n_alg = shp.N;   // the grouped un-patchify order carries zero-weight pad columns: count the algorithmic ones
+  if (KIND == EPI_CONVT && epi.ct_cpg > 0) n_alg = (double)(shp.N / epi.ct_CS) * epi.ct_C * epi.ct_pw;
+  LaunchScope scope(st, "gemm_tc", 2.0 * shp.M * n_alg * shp.K,
                     2.0 * ((double)shp.M * shp.K + (double)shp.N * shp.K) +
-                        (double)shp.M * shp.N * ((KIND == EPI_BF16 || KIND == EPI_GELU_BF16 || KIND == EPI_QKV) ? 2.0 : 4.0));
+                        (double)shp.M * n_alg * ((KIND == EPI_BF16 || KIND == EPI_GELU_BF16 || KIND == EPI_QKV) ? 2.0 : 4.0));
   launch_chained(kern, dim3(2 * clusters), dim3(GEMM_THREADS), GemmSmem2::TOTAL, st, tmA, tmB, shp, epi);  // cluster dims are compiled in
 }
 
@@ -65,8 +67,13 @@ bool gemm_use_pair(int M, int N, int K, int kind) {
   static const char* env = getenv("CRA5_GEMM_PAIR");  // diagnostics: 0 = never, 1 = whenever legal
   if (env != nullptr) return atoi(env) != 0 && N >= 256;
   // measured on B200 (bench.py kernel_sites, 8 frames per call): qkv 1381 TFLOP/s, fc2 1368, proj 822 with the pair
-  // kernel against 1343 / 1281 / 711-773 with 1-CTA tiles; fc1 and the conv layers are within noise and stay 1-CTA
+  // kernel against 1343 / 1281 / 711-773 with 1-CTA tiles. Since the GELU and un-patchify epilogues got cheaper
+  // (end of round 2) the main loop shows there too: fc1 1234 -> 1247, un-patchify class A 0.571 -> 0.542 ms per frame
+  // (the 1-CTA 128 x 256 tile pulls 48 KB per k-block from L2, the pair 32 KB per CTA; ~56 B per clock and SM is what
+  // the GEMM captures show L2 delivering). The small hyperprior GEMMs stay 1-CTA.
   if (kind == EPI_QKV && N >= 3072 && M >= 4096) return true;
+  if (kind == EPI_GELU_BF16 && N >= 3072 && K >= 1024 && M >= 4096) return true;
+  if (kind == EPI_CONVT && N >= 4096 && K >= 1024 && M >= 4096) return true;
   return kind == EPI_RESID && N >= 512 && N <= 1024 && K >= 1024 && M >= 4096;
 }
 
