@@ -248,7 +248,12 @@ __device__ __forceinline__ Item decode_item(const A4Params& p, int item) {
 //     keys still takes 1900 cycles: left alone the three tiles fall in step, and when a ring of named barriers keeps
 //     them a third of a step apart each warp's exponentials take as long as before (~1000 cycles for 64 columns). One
 //     in-order warp issues this instruction mix at an IPC of ~0.4; the FMA pipe is 60 % busy, the MUFU 50 %, with
-//     two or with three warps per scheduler. Not kept: no gain on the shape that dominates the step.)
+//     two or with three warps per scheduler. Not kept: no gain on the shape that dominates the step;
+//   * two threads per row once more, with what the variants above had taught (control warps at the highest ids, lean
+//     issuer loops) and the tiles' exponential phases alternating through mbarriers: 815 (860 with POLY = 2) against
+//     905. The trace shows the alternation working and a tile's two warps taking 1250 cycles for 2 x 64 columns -- what
+//     ONE warp takes for 128. The exponentials are bound by the scheduler's FMA pipe (~700 cycles per tile and warp:
+//     profiles/r2_ncu_attn_stalls.txt) plus MUFU (640), not by how many warps share them.)
 // (Also tried: four instead of two running maxima per row -- no change, the
 // FMNMX3 chain already hides behind the second TMEM load; computing the exponentials speculatively against the previous
 // reference maximum while the tile maximum is still being reduced -- the scores then have to stay live for a possible
