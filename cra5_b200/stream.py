@@ -284,14 +284,19 @@ class FramePipeline:
         for b in range(2):
             in_free[b].record(main)
         prefetch(0)
+        if n > 1:
+            prefetch(1)
         pending = None  # (index, strings, host buffer, event): reconstruction still in flight to the host
         for i in range(n):
             b = i % 2
-            if i + 1 < n:
-                prefetch(i + 1)
             main.wait_event(in_ready[b])
             y = api.encode_to_latent(data=dev_in[b])          # fused normalise + g_a + quant_conv
             in_free[b].record(main)
+            # frame i+2 reuses this buffer: queue its copy NOW, behind frame i+1's on the copy stream, so that the H2D
+            # engine never waits for the host loop to come round again (queued at the top of the next iteration it sat
+            # idle ~2 ms per frame: the loop is paced by the D2H of the previous reconstruction)
+            if i + 2 < n:
+                prefetch(i + 2)
             out = api.latent_to_bin(y)                        # h_a, h_s, quantise, rANS -> host bytes
             if not self.roundtrip:
                 yield i, out["strings"], None
