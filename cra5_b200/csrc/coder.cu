@@ -74,6 +74,9 @@ RansCoder::RansCoder(size_t max_symbols, int max_channels)
     CRA5_CUDA(cudaMalloc(&p.data, ((size_t)PACK_CAP + 8) * 2));
     CRA5_CUDA(cudaMalloc(&p.row_off, ((size_t)PACK_ROWS + 1) * 4));
     CRA5_CUDA(cudaMalloc(&p.lut, ((size_t)PACK_ROWS * 257 + 8) * 2));
+    // the kernels stage these with 16-byte copies that run into the 8-entry slack: give it defined contents
+    CRA5_CUDA(cudaMemset(p.data, 0, ((size_t)PACK_CAP + 8) * 2));
+    CRA5_CUDA(cudaMemset(p.lut, 0, ((size_t)PACK_ROWS * 257 + 8) * 2));
   }
 }
 

@@ -725,7 +725,7 @@ rans_encode_smem_kernel(const int32_t* __restrict__ sym, const uint8_t* __restri
       ci[b] = index_is_channel ? (c % index_is_channel) : (int)idx[pos];
     }
   };
-  gather(count);
+  if (count > 0) gather(count);   // (a sub-stream beyond a short channel's end is empty: nothing of its own to read)
   for (int i0 = count; i0 > 0; i0 -= RANS_BATCH) {
     int32_t mxv[RANS_BATCH], val[RANS_BATCH];
     uint32_t start[RANS_BATCH], freq[RANS_BATCH], raw[RANS_BATCH];
@@ -835,7 +835,7 @@ rans_decode_smem_kernel(const uint8_t* __restrict__ payload, const uint32_t* __r
       mm[b] = (val_out == nullptr) ? 0.f : ((mu != nullptr) ? mu[pos + mu_extra] : med);
     }
   };
-  gather(0, ci, mean);
+  if (count > 0) gather(0, ci, mean);
   for (int i0 = 0; i0 < count; i0 += RANS_BATCH) {
     if (i0 + RANS_BATCH < count) gather(i0 + RANS_BATCH, ci_n, mean_n);
     int32_t outv[RANS_BATCH];
