@@ -652,7 +652,11 @@ void pack_cdf(cudaStream_t st, const int32_t* cdf, int cdf_stride, const int32_t
   CRA5_CUDA(cudaGetLastError());
 }
 
-constexpr int RANS_STHREADS = 64;   // two warps per CTA, each with an SM sub-partition to itself
+constexpr int RANS_STHREADS = 64;   // encoder: two warps per CTA, each with an SM sub-partition to itself
+// decoder: four warps share one staged table (CDF rows + inverse table, ~87 KB for the GaussianConditional: two CTAs per
+// SM). With 64 threads the 512 CTAs of an 8-frame batch were 1.7 waves over the 296 resident slots -- a half-empty
+// second pass over 648-symbol chains; with 128 they are one wave.
+constexpr int RANS_DTHREADS = 128;
 
 struct SmemTables {
   const uint16_t* cdf16;   // [total] packed rows
@@ -801,7 +805,7 @@ struct RansDecP {   // decoder state; the caller peeks the next stream word at t
   }
 };
 
-__global__ void __launch_bounds__(RANS_STHREADS)
+__global__ void __launch_bounds__(RANS_DTHREADS)
 rans_decode_smem_kernel(const uint8_t* __restrict__ payload, const uint32_t* __restrict__ offsets,
                         const uint8_t* __restrict__ idx, int index_is_channel, const uint16_t* __restrict__ packed,
                         const int32_t* __restrict__ row_off, const int32_t* __restrict__ cdf_len,
@@ -954,7 +958,7 @@ void rans_decode_smem(cudaStream_t st, const uint8_t* payload, const uint32_t* o
   const size_t smem = smem_tables_bytes(rows, total, lut != nullptr);
   if (smem > 48 * 1024) ensure_dynamic_smem(rans_decode_smem_kernel, 200 * 1024);
   LaunchScope scope(st, "rans_decode", 0.0, (double)n_channels * L * (chan_mod ? 4.0 : 9.0));
-  rans_decode_smem_kernel<<<(n_streams + RANS_STHREADS - 1) / RANS_STHREADS, RANS_STHREADS, smem, st>>>(
+  rans_decode_smem_kernel<<<(n_streams + RANS_DTHREADS - 1) / RANS_DTHREADS, RANS_DTHREADS, smem, st>>>(
       payload, offsets, idx, chan_mod, packed, row_off, cdf_len, offset, lut, rows, total, n_channels, L,
       spc, chan_len, sym_out, mu, median, val_out, err, ch_per_frame > 0 ? ch_per_frame : (1 << 30), mu_frame_extra);
   CRA5_CUDA(cudaGetLastError());
