@@ -49,7 +49,9 @@ Model::Model(const cra5_config& c) : cfg_(c) {
   // patch-embed implicit GEMM
   const int CS = c.in_chans * c.patch_w;
   kpr = ceil_div(CS, GEMM_BK);
-  cs_pad = (int)align_up((size_t)CS, 8);
+  // row pitch of the re-laid-out frame: a multiple of 64 elements, so that every 128-byte row of a TMA box is ONE aligned
+  // L2 line (with the minimal 16-byte padding the 5360-byte pitch made each of them straddle two)
+  cs_pad = (int)align_up((size_t)CS, 64);
   box_rows = 0;
   for (int b = 128; b >= 16; b >>= 1)   // >= 16 rows per TMA box keeps a 128-row tile within 8 boxes
     if (Wg % b == 0) { box_rows = b; break; }
