@@ -847,31 +847,31 @@ void Model::latent_to_reconstruction(const float* y_hat, float* x_hat, int B, cu
     e.ct_CS = CS; e.ct_pw = c.patch_w; e.ct_sh = c.stride_h; e.ct_Wp = Wg; e.ct_Himg = c.img_h; e.ct_Wimg = c.img_w;
     e.ct_mean = mean; e.ct_std = std_;   // de-normalisation fused into the un-patchify store
     e.fr_rows = M2; e.fr_stride = frame_out;
+    // Both kernel-row classes run on the channel-grouped column order when the patch width is the shipped one
+    // (gemm_tc.cuh: epilogue_convt_grouped): per kernel row, groups of 32 columns = 3 whole channels x pw + 2 zero-weight
+    // pad columns; the weights are packed that way at upload (cra5_b200/vaeformer.py::_upload)
+    const bool grouped = c.patch_w == CT_PW;
+    const int cpg = 30 / CT_PW, groups = (c.in_chans + cpg - 1) / cpg;
+    const int CSg = grouped ? 32 * groups : CS;     // columns per kernel row
+    if (grouped) {
+      CRA5_CHECK((int64_t)Hg * c.stride_h * c.img_w + c.img_w <= (1 << 20) && B < 4096, ERR_INVALID,
+                 "unsupported geometry for the grouped un-patchify epilogue");
+      e.ct_cpg = cpg; e.ct_C = c.in_chans;
+    }
+    e.ct_CS = CSg;
     if (nA > 0) {
-      // class A runs on the channel-grouped column order when the patch width is the shipped one (gemm_tc.cuh:
-      // epilogue_convt_grouped): per kernel row, groups of 32 columns = 3 whole channels x pw + 2 zero-weight pad
-      // columns; the weight is packed that way at upload (cra5_b200/vaeformer.py::_upload)
-      const bool grouped = c.patch_w == CT_PW;
-      const int cpg = 30 / CT_PW, groups = (c.in_chans + cpg - 1) / cpg;
-      const int CSa = grouped ? 32 * groups : CS;
-      if (grouped) {
-        CRA5_CHECK((int64_t)Hg * c.stride_h * c.img_w + c.img_w <= (1 << 20) && B < 4096, ERR_INVALID,
-                   "unsupported geometry for the grouped un-patchify epilogue");
-        e.ct_cpg = cpg; e.ct_C = c.in_chans; e.ct_CS = CSa;
-      }
       e.ct_r0 = nB;
       TagScope tag_("convT_A");
       if (pr)
-        gemm_plain(st, EPI_CONVT, fin, D, need_x3("g_s.final.A", (int64_t)nA * CSa * D), D, MB, nA * CSa, D, e,
-                   GemmSplit{fin_half, (size_t)nA * CSa * D});
+        gemm_plain(st, EPI_CONVT, fin, D, need_x3("g_s.final.A", (int64_t)nA * CSg * D), D, MB, nA * CSg, D, e,
+                   GemmSplit{fin_half, (size_t)nA * CSg * D});
       else
-        gemm_plain(st, EPI_CONVT, fin, D, (const __nv_bfloat16*)need("g_s.final.A", CRA5_DT_BF16, (int64_t)nA * CSa * D), D, MB,
-                   nA * CSa, D, e);
-      e.ct_cpg = 0; e.ct_CS = CS;
+        gemm_plain(st, EPI_CONVT, fin, D, (const __nv_bfloat16*)need("g_s.final.A", CRA5_DT_BF16, (int64_t)nA * CSg * D), D, MB,
+                   nA * CSg, D, e);
     }
     if (nB > 0) {
       e.ct_r0 = 0;
-      const int N2 = nB * CS, K2 = 2 * D;
+      const int N2 = nB * CSg, K2 = 2 * D;
       CRA5_CHECK(D % GEMM_BK == 0, ERR_INVALID, "unsupported geometry: width must be a multiple of 64 for the conv head");
       const int bn = gemm_pick_bn(N2);
       CUtensorMap tmA, tmB;

@@ -320,20 +320,22 @@ class VAEformer:
         if cfg.conv_head:
             P = wf.permute(2, 1, 3, 0).contiguous()          # [ph][C][pw][D]
             nB = ph - sh
+            def grouped(Pr):
+                """[rows][C][pw][K] -> the channel-grouped column order of csrc/gemm_tc.cuh::epilogue_convt_grouped: per
+                kernel row, groups of 32 columns = 3 whole channels x pw + 2 zero-weight pad columns (pw == 10 only)"""
+                if pw != 10:
+                    return Pr
+                cpg = 30 // pw
+                groups = (Cc + cpg - 1) // cpg
+                Pp = torch.zeros(Pr.shape[0], groups * cpg, pw, Pr.shape[-1], device=dev)
+                Pp[:, :Cc] = Pr
+                out = torch.zeros(Pr.shape[0], groups, 32, Pr.shape[-1], device=dev)
+                out[:, :, : cpg * pw] = Pp.reshape(Pr.shape[0], groups, cpg * pw, Pr.shape[-1])
+                return out
             if sh - nB > 0:
-                PA = P[nB:sh]
-                if pw == 10:
-                    # class A in the channel-grouped column order (csrc/gemm_tc.cuh: epilogue_convt_grouped): per
-                    # kernel row, groups of 32 columns = 3 whole channels x pw + 2 zero-weight pad columns
-                    cpg = 30 // pw
-                    groups = (Cc + cpg - 1) // cpg
-                    Pp = torch.zeros(sh - nB, groups * cpg, pw, D, device=dev)
-                    Pp[:, :Cc] = PA
-                    PA = torch.zeros(sh - nB, groups, 32, D, device=dev)
-                    PA[:, :, : cpg * pw] = Pp.reshape(sh - nB, groups, cpg * pw, D)
-                set_weight("g_s.final.A", PA.reshape(-1, D))
+                set_weight("g_s.final.A", grouped(P[nB:sh]).reshape(-1, D))
             if nB > 0:
-                set_weight("g_s.final.B", torch.cat([P[:nB], P[sh:sh + nB]], dim=-1).reshape(-1, 2 * D))
+                set_weight("g_s.final.B", grouped(torch.cat([P[:nB], P[sh:sh + nB]], dim=-1)).reshape(-1, 2 * D))
         else:
             set_weight("g_s.final.weight", wf)
         lat = cfg.latent_chans
