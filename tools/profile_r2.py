@@ -102,9 +102,11 @@ def sass_histogram(rnd):
 
 def main(rnd):
     os.makedirs(OUT, exist_ok=True)
-    with open(os.path.join(OUT, f"bench_{rnd}.json"), "w") as f:
-        r = subprocess.run(BENCH, stdout=f, stderr=subprocess.PIPE, text=True, timeout=1200)
-    print("bench rc", r.returncode, r.stderr[-300:], flush=True)
+    partial = any(a.startswith("--only=") for a in sys.argv)
+    if not partial:
+        with open(os.path.join(OUT, f"bench_{rnd}.json"), "w") as f:
+            r = subprocess.run(BENCH, stdout=f, stderr=subprocess.PIPE, text=True, timeout=1200)
+        print("bench rc", r.returncode, r.stderr[-300:], flush=True)
     try:
         d = json.loads([l for l in open(os.path.join(OUT, f"bench_{rnd}.json")) if l.startswith("{")][-1])
         print("value", d["value"], "e2e", (d.get("e2e") or {}).get("value"), "roofline", (d.get("roofline") or {}).get("frac"),
@@ -133,7 +135,10 @@ def main(rnd):
     plan.append(("rans_dec", "rans_decode_smem", base, 2))
     n, base = positions(names, r"attn_mma|attn_small")
     plan.append(("attn_hyper", "attn_mma|attn_small", base, 1))
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]   # e.g. --only=gemm_tail: re-capture one group
     for tag, rgx, skip, cnt in plan:
+        if only and tag not in only:
+            continue
         print("capture", tag, rgx, skip, cnt, flush=True)
         capture(rnd, tag, rgx, skip, cnt)
     sass_histogram(rnd)
@@ -213,4 +218,4 @@ if __name__ == "__main__":
     if "--collect" in sys.argv:
         collect(sys.argv[-1])
     else:
-        main(sys.argv[1] if len(sys.argv) > 1 else "r2")
+        main(next((a for a in sys.argv[1:] if not a.startswith("--")), "r2"))
